@@ -135,7 +135,7 @@ def normalised_smoothness(disp, img):
 # --------------------------------------------------------------------------
 # the path: generate_images_pred + compute_losses for all scales
 # --------------------------------------------------------------------------
-def view_synthesis_losses(inputs, outputs, opt, is_multi=False, noise=None, want_maps=False):
+def view_synthesis_losses(inputs, outputs, opt, is_multi=False, noise=None, want_maps=False, forced=None):
     """Returns (losses, maps).
 
     `noise`: list with one (B,1,H,W) standard-normal tensor per scale (the
@@ -144,6 +144,10 @@ def view_synthesis_losses(inputs, outputs, opt, is_multi=False, noise=None, want
     `maps[s]` (when want_maps): per-pixel tensors r (post selec_reproj), ident
     (min identity loss + noise), mask, src_idx (0/1 source that receives the
     gradient, 2 = none), depth, warped images.
+    `forced`: optional {s: (mask, src_idx)} -- evaluate the loss with a GIVEN selection instead of
+    the oracle's own min/argmin decisions (both are piecewise constant, so autograd is unaffected);
+    used to compare gradients between implementations whose fp32 decisions differ in a few
+    near-tie pixels.
     """
     S = opt.sclm + 1
     srcs = list(opt.frame_ids[1:])
@@ -183,12 +187,19 @@ def view_synthesis_losses(inputs, outputs, opt, is_multi=False, noise=None, want
             src_idx = torch.where(dark_b, torch.zeros_like(src_idx), src_idx)
             src_idx = torch.where(dark_a & dark_b, torch.full_like(src_idx, 2), src_idx)
 
-        if not opt.disable_automasking:                                       # trainer.py:1084-1091
+        # trainer.py:1084-1091: `disable_automasking` only removes the tie-break noise -- the identity
+        # loss is still handed to compute_loss_masks (never None), so the argmin mask is always applied.
+        if not opt.disable_automasking:
             z = noise[s] if noise is not None else torch.randn(ident.shape)
             ident = ident + z.to(ident) * 0.00001
-            mask = (r <= ident).to(r.dtype)          # == (argmin(cat[r,ident])==0), first-min tie rule
-        else:
-            mask = torch.ones_like(r)
+        mask = (r <= ident).to(r.dtype)              # == (argmin(cat[r,ident])==0), first-min tie rule
+
+        if forced is not None:
+            f_mask, f_src = forced[s]
+            f_src = f_src.reshape(r.shape).to(torch.int64)
+            r = torch.where(f_src == 0, per_src[:, 0:1], torch.where(f_src == 1, per_src[:, 1:2], torch.zeros_like(r)))
+            src_idx = f_src
+            mask = f_mask.reshape(r.shape).to(r.dtype)
 
         if is_multi:                                                          # trainer.py:1101-1109
             mask = torch.ones_like(mask)
@@ -231,11 +242,13 @@ def clone_batch(inputs, outputs, dtype=torch.float32, device="cpu", requires_gra
     return ins, outs
 
 
-def run_fwd_bwd(inputs, outputs, opt, is_multi=False, noise=None, dtype=torch.float32, want_maps=False):
+def run_fwd_bwd(inputs, outputs, opt, is_multi=False, noise=None, dtype=torch.float32, want_maps=False, forced=None):
     """One timed unit of the metric: forward, then backward to
     every disp_s and (mono path) every T_f."""
     ins, outs = clone_batch(inputs, outputs, dtype=dtype)
-    losses, maps = view_synthesis_losses(ins, outs, opt, is_multi, noise, want_maps)
+    if noise is not None:
+        noise = [z.to(dtype) for z in noise]
+    losses, maps = view_synthesis_losses(ins, outs, opt, is_multi, noise, want_maps, forced)
     losses["loss"].backward()
     grads = {k: v.grad for k, v in outs.items()
              if isinstance(k, tuple) and k[0] in ("disp", "cam_T_cam") and v.grad is not None}

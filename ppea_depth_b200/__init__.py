@@ -1,2 +1,23 @@
-"""B200-native view-synthesis loss path for PPEA-Depth."""
-__version__ = "0.1.0"
+"""ppea_depth_b200 -- B200-native (sm_100a) view-synthesis loss path of PPEA-Depth.
+
+Public surface (mirrors /root/reference/ppeadepth/layers.py and the loss
+methods of /root/reference/ppeadepth/trainer.py):
+
+    from ppea_depth_b200 import (BackprojectDepth, Project3D, SSIM, get_smooth_loss,
+                                 disp_to_depth, upsample, transformation_from_parameters,
+                                 generate_images_pred, compute_reprojection_loss,
+                                 compute_loss_masks, compute_losses, install,
+                                 view_synthesis_loss, VslConfig)
+"""
+from .layers import (BackprojectDepth, Project3D, SSIM, disp_to_depth, get_smooth_loss, get_translation_matrix,
+                     rot_from_axisangle, transformation_from_parameters, upsample)
+from .functional import VslConfig, VslResult, view_synthesis_loss
+from .loss import (ViewSynthesisLoss, compute_loss_masks, compute_losses, compute_reprojection_loss,
+                   generate_images_pred, install)
+
+__all__ = [
+    "BackprojectDepth", "Project3D", "SSIM", "disp_to_depth", "get_smooth_loss", "get_translation_matrix",
+    "rot_from_axisangle", "transformation_from_parameters", "upsample", "VslConfig", "VslResult",
+    "view_synthesis_loss", "ViewSynthesisLoss", "compute_loss_masks", "compute_losses",
+    "compute_reprojection_loss", "generate_images_pred", "install",
+]

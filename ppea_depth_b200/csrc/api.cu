@@ -1,0 +1,182 @@
+// api.cu -- the C ABI of libppea_vsl.so (include/ppea_vsl.h): argument validation
+// and launch sequencing of the fused view-synthesis loss.  No allocation, no
+// host synchronisation, no global state: every call only enqueues on `stream`.
+#include "vsl_common.cuh"
+
+using namespace ppea;
+
+namespace {
+
+inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+int check_params(const PpeaVslParams* p, bool backward) {
+  if (!p) return PPEA_E_NULL;
+  if (p->struct_size != sizeof(PpeaVslParams)) return PPEA_E_VERSION;
+  if (p->batch <= 0 || p->height < 3 || p->width < 3) return PPEA_E_SHAPE;   // reflection pad 1 + a 3x3 window
+  if (p->num_scales < 1 || p->num_scales > PPEA_MAX_SCALES || p->total_scales < 1 || p->first_scale < 0 ||
+      p->first_scale + p->num_scales > 16)
+    return PPEA_E_SHAPE;
+  if ((size_t)p->batch * p->height * p->width >= (size_t)1 << 31) return PPEA_E_SHAPE;
+  const bool multi = p->flags & PPEA_F_MULTI;
+  if (multi && (p->flags & PPEA_F_GRAD_POSE)) return PPEA_E_FLAGS;   // T is detached on the multi path (trainer.py:900-902)
+  if (!p->tgt || !p->src[0] || !p->src[1] || !p->K || !p->inv_K || !p->T[0] || !p->T[1] || !p->sums || !p->losses)
+    return PPEA_E_NULL;
+  if (multi && (p->flags & PPEA_F_MOTION_MASK) && !p->cons_mask) return PPEA_E_FLAGS;
+  if (multi && (p->flags & PPEA_F_MATCH_AUG) && !p->aug_mask) return PPEA_E_FLAGS;
+  const void* fl[] = {p->tgt, p->src[0], p->src[1], p->K, p->inv_K, p->T[0], p->T[1], p->cons_mask, p->aug_mask, p->sums, p->losses};
+  for (const void* q : fl)
+    if (!aligned(q, 4)) return PPEA_E_ALIGN;
+  for (int s = 0; s < p->num_scales; ++s) {
+    const PpeaVslScale& sc = p->scales[s];
+    if (sc.disp_h < 2 || sc.disp_w < 2 || sc.disp_h > p->height || sc.disp_w > p->width) return PPEA_E_SHAPE;
+    if (!sc.disp || !sc.color || !sc.depth || !sc.sel) return PPEA_E_NULL;
+    if (multi && !sc.mono_depth) return PPEA_E_FLAGS;
+    if (backward && !sc.grad_disp) return PPEA_E_NULL;
+    const void* fs[] = {sc.disp, sc.color, sc.noise, sc.mono_depth, sc.depth, sc.loss_px, sc.grad_disp};
+    for (const void* q : fs)
+      if (!aligned(q, 4)) return PPEA_E_ALIGN;
+  }
+  return PPEA_OK;
+}
+
+void fill_args(const PpeaVslParams* p, VslArgs& a) {
+  a = VslArgs{};
+  a.B = p->batch;
+  a.H = p->height;
+  a.W = p->width;
+  a.S = p->num_scales;
+  a.first_scale = p->first_scale;
+  a.total_scales = p->total_scales;
+  a.flags = p->flags;
+  a.disp_lo = p->disp_lo;
+  a.disp_range = p->disp_range;
+  a.eps = p->eps;
+  a.disparity_smoothness = p->disparity_smoothness;
+  a.tgt = p->tgt;
+  a.src[0] = p->src[0];
+  a.src[1] = p->src[1];
+  a.K = p->K;
+  a.inv_K = p->inv_K;
+  a.T[0] = p->T[0];
+  a.T[1] = p->T[1];
+  a.cons_mask = p->cons_mask;
+  a.aug_mask = p->aug_mask;
+  for (int s = 0; s < p->num_scales; ++s) {
+    const PpeaVslScale& in = p->scales[s];
+    ScaleArgs& sc = a.sc[s];
+    sc.hs = in.disp_h;
+    sc.ws = in.disp_w;
+    sc.up_sy = up_scale(in.disp_h, p->height);
+    sc.up_sx = up_scale(in.disp_w, p->width);
+    sc.disp = in.disp;
+    sc.color = in.color;
+    sc.noise = in.noise;
+    sc.mono_depth = in.mono_depth;
+    sc.depth = in.depth;
+    sc.loss_px = in.loss_px;
+    sc.sel = in.sel;
+    sc.grad_disp = in.grad_disp;
+    sc.grad_dup = nullptr;
+  }
+  a.sums = p->sums;
+  a.losses = p->losses;
+}
+
+#define PPEA_TRY(expr)                \
+  do {                                \
+    cudaError_t e__ = (expr);         \
+    if (e__ != cudaSuccess) return (int)e__; \
+  } while (0)
+
+}  // namespace
+
+extern "C" {
+
+int ppea_abi_version(void) { return PPEA_ABI_VERSION; }
+
+const char* ppea_strerror(int code) {
+  switch (code) {
+    case PPEA_OK: return "success";
+    case PPEA_E_NULL: return "ppea: required pointer is NULL";
+    case PPEA_E_SHAPE: return "ppea: non-positive, inconsistent or unsupported shape";
+    case PPEA_E_ALIGN: return "ppea: misaligned pointer";
+    case PPEA_E_FLAGS: return "ppea: contradictory flags or missing optional input";
+    case PPEA_E_VERSION: return "ppea: struct_size / ABI version mismatch";
+    case PPEA_E_WORKSPACE: return "ppea: workspace too small or misaligned";
+    default: break;
+  }
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  return "ppea: unknown error";
+}
+
+size_t ppea_vsl_workspace_bytes(int batch, int height, int width, int num_scales) {
+  if (batch <= 0 || height <= 0 || width <= 0 || num_scales <= 0) return 0;
+  return fwd_workspace(batch, height, width, num_scales).total_floats * sizeof(float);
+}
+
+size_t ppea_vsl_backward_workspace_bytes(int batch, int height, int width, int num_scales, uint32_t flags) {
+  if (batch <= 0 || height <= 0 || width <= 0 || num_scales <= 0) return 0;
+  return bwd_workspace(batch, height, width, num_scales, flags).total_floats * sizeof(float);
+}
+
+size_t ppea_vsl_sums_floats(int batch, int num_scales) {
+  if (batch <= 0 || num_scales <= 0) return 0;
+  return (size_t)num_scales * sums_stride(batch);
+}
+
+int ppea_vsl_forward(const PpeaVslParams* p, void* stream_) {
+  const int rc = check_params(p, false);
+  if (rc != PPEA_OK) return rc;
+  const FwdWorkspace ws = fwd_workspace(p->batch, p->height, p->width, p->num_scales);
+  if (!p->workspace) return PPEA_E_NULL;
+  if (!aligned(p->workspace, 16) || p->workspace_bytes < ws.total_floats * sizeof(float)) return PPEA_E_WORKSPACE;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  VslArgs a;
+  fill_args(p, a);
+  a.tiles_x = ceil_div(a.W, kFwdTileW);
+  a.tiles_y = ceil_div(a.H, kFwdTileH);
+  a.partials = (float*)p->workspace + ws.off_partials;
+  a.smooth_ws = (float*)p->workspace + ws.off_smooth;
+  PPEA_TRY(launch_smooth_disp_sums(a, stream));
+  PPEA_TRY(launch_vsl_forward(a, stream));
+  PPEA_TRY(launch_smooth_forward(a, stream));
+  PPEA_TRY(launch_vsl_finish(a, fwd_blocks(a.B, a.H, a.W), stream));
+  return PPEA_OK;
+}
+
+int ppea_vsl_backward(const PpeaVslParams* p, const PpeaVslGrads* g, void* stream_) {
+  const int rc = check_params(p, true);
+  if (rc != PPEA_OK) return rc;
+  if (!g) return PPEA_E_NULL;
+  if (g->struct_size != sizeof(PpeaVslGrads)) return PPEA_E_VERSION;
+  if (!g->grad_losses || !g->workspace) return PPEA_E_NULL;
+  const bool pose = p->flags & PPEA_F_GRAD_POSE;
+  if (pose && (!g->grad_T[0] || !g->grad_T[1])) return PPEA_E_NULL;
+  const BwdWorkspace ws = bwd_workspace(p->batch, p->height, p->width, p->num_scales, p->flags);
+  if (!aligned(g->workspace, 16) || g->workspace_bytes < ws.total_floats * sizeof(float)) return PPEA_E_WORKSPACE;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  VslArgs a;
+  fill_args(p, a);
+  a.tiles_x = ceil_div(a.W, kBwdTileW);
+  a.tiles_y = ceil_div(a.H, kBwdTileH);
+  a.grad_losses = g->grad_losses;
+  a.pose_partials = (float*)g->workspace + ws.off_pose;
+  a.grad_T[0] = g->grad_T[0];
+  a.grad_T[1] = g->grad_T[1];
+  bool any_dup = false;
+  if (p->flags & PPEA_F_DETERMINISTIC) {
+    const size_t n = (size_t)a.B * a.H * a.W;
+    for (int s = 0; s < a.S; ++s)
+      if (a.sc[s].hs != a.H || a.sc[s].ws != a.W) {
+        a.sc[s].grad_dup = (float*)g->workspace + ws.off_dup + (size_t)s * n;
+        any_dup = true;
+      }
+  }
+  PPEA_TRY(launch_smooth_backward(a, stream));
+  PPEA_TRY(launch_vsl_backward(a, stream));
+  if (any_dup) PPEA_TRY(launch_upsample_gather(a, stream));
+  if (pose) PPEA_TRY(launch_pose_finish(a, bwd_blocks(a.B, a.H, a.W), stream));
+  return PPEA_OK;
+}
+
+}  // extern "C"

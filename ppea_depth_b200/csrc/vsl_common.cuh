@@ -1,0 +1,128 @@
+// vsl_common.cuh -- launch-side structures shared by the view-synthesis-loss kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ppea_vsl.h"
+#include "vsl_math.cuh"
+
+namespace ppea {
+
+constexpr int kMaxScales = PPEA_MAX_SCALES;
+
+struct ScaleArgs {
+  int hs, ws;           // disp_s resolution
+  float up_sy, up_sx;   // upsample source scales hs/H, ws/W (ATen area_pixel_compute_scale)
+  const float* disp;
+  const float* color;   // smoothness image (B,3,hs,ws)
+  const float* noise;
+  const float* mono_depth;
+  float* depth;
+  float* loss_px;
+  uint8_t* sel;
+  float* grad_disp;
+  float* grad_dup;      // deterministic mode: full-res dL/d disp_up scratch (scales with hs != H only)
+};
+
+// Kernel argument block (passed by value, lives in the constant bank).
+struct VslArgs {
+  int B, H, W;
+  int S;                // scales in this launch
+  int first_scale, total_scales;
+  unsigned flags;
+  float disp_lo, disp_range, eps, disparity_smoothness;
+  int tiles_x, tiles_y; // tiles per image (of the kernel being launched)
+  const float* tgt;
+  const float* src[2];
+  const float* K;
+  const float* inv_K;
+  const float* T[2];
+  const float* cons_mask;
+  const float* aug_mask;
+  ScaleArgs sc[kMaxScales];
+  float* partials;      // forward: [nblk][S][4] block partial sums
+  float* sums;          // [S][8 + 4B]
+  float* losses;        // [1 + 4S]
+  float* smooth_ws;     // [S][B][kSmoothChunks][3]: disp sum, smooth_x sum, smooth_y sum
+  // backward only
+  const float* grad_losses;
+  float* pose_partials; // [nblk_bwd][24]
+  float* grad_T[2];
+};
+
+constexpr int kFwdTileW = 32;
+constexpr int kFwdTileH = 32;
+constexpr int kFwdThreads = 128;
+constexpr int kBwdTileW = 32;
+constexpr int kBwdTileH = 16;
+constexpr int kBwdThreads = 128;
+constexpr int kSmoothChunks = 32;     // blocks per image in the smoothness kernels
+constexpr int kSmoothThreads = 256;
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+inline int fwd_blocks(int B, int H, int W) { return B * ceil_div(W, kFwdTileW) * ceil_div(H, kFwdTileH); }
+inline int bwd_blocks(int B, int H, int W) { return B * ceil_div(W, kBwdTileW) * ceil_div(H, kBwdTileH); }
+__host__ __device__ inline int sums_stride(int B) { return PPEA_SUMS_PER_SCALE + 4 * B; }
+
+// Forward workspace layout (floats): [partials: nblk*S*4][smooth_ws: S*B*kSmoothChunks*3]
+struct FwdWorkspace {
+  size_t off_partials, off_smooth, total_floats;
+};
+inline FwdWorkspace fwd_workspace(int B, int H, int W, int S) {
+  FwdWorkspace w;
+  w.off_partials = 0;
+  w.off_smooth = align_up((size_t)fwd_blocks(B, H, W) * S * 4, 4);
+  w.total_floats = w.off_smooth + (size_t)S * B * kSmoothChunks * 3;
+  return w;
+}
+
+// Backward workspace layout (floats): [pose partials: nblk*24][grad_dup: S*B*H*W when deterministic]
+struct BwdWorkspace {
+  size_t off_pose, off_dup, total_floats;
+};
+inline BwdWorkspace bwd_workspace(int B, int H, int W, int S, unsigned flags) {
+  BwdWorkspace w;
+  w.off_pose = 0;
+  w.off_dup = align_up((size_t)bwd_blocks(B, H, W) * 24, 4);
+  w.total_floats = w.off_dup + ((flags & PPEA_F_DETERMINISTIC) ? (size_t)S * B * H * W : 0);
+  return w;
+}
+
+cudaError_t launch_vsl_forward(const VslArgs& a, cudaStream_t stream);
+cudaError_t launch_vsl_backward(const VslArgs& a, cudaStream_t stream);
+cudaError_t launch_smooth_disp_sums(const VslArgs& a, cudaStream_t stream);
+cudaError_t launch_smooth_forward(const VslArgs& a, cudaStream_t stream);
+cudaError_t launch_vsl_finish(const VslArgs& a, int nblk_fwd, cudaStream_t stream);
+cudaError_t launch_smooth_backward(const VslArgs& a, cudaStream_t stream);
+cudaError_t launch_upsample_gather(const VslArgs& a, cudaStream_t stream);
+cudaError_t launch_pose_finish(const VslArgs& a, int nblk_bwd, cudaStream_t stream);
+
+// ---- device helpers
+#if defined(__CUDACC__)
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Effective upstream weights of the three per-scale terms, from the gradient of the
+// `losses` vector (layout in ppea_vsl.h): losses[0] = sum_s loss_s / total_scales,
+// loss_s = reproj_s + cons_s + (disparity_smoothness / 2^s) * smooth_s.
+struct ScaleGrads {
+  float reproj, cons, smooth;
+};
+__device__ __forceinline__ ScaleGrads scale_grads(const VslArgs& a, int s) {
+  const float* g = a.grad_losses;
+  const float g_loss = g[0] / (float)a.total_scales + g[1 + s * PPEA_LOSSES_PER_SCALE + 0];
+  ScaleGrads o;
+  o.reproj = g_loss + g[1 + s * PPEA_LOSSES_PER_SCALE + 1];
+  o.cons = g_loss + g[1 + s * PPEA_LOSSES_PER_SCALE + 2];
+  o.smooth = g_loss * (a.disparity_smoothness / (float)(1 << (a.first_scale + s))) + g[1 + s * PPEA_LOSSES_PER_SCALE + 3];
+  return o;
+}
+#endif
+
+}  // namespace ppea

@@ -235,26 +235,41 @@ PPEA_HD float bilin_ddy(const Bilin& b, float nw, float ne, float sw, float se) 
 struct SsimY {  // per-window statistics of the target image (shared by every source)
   float s;      // Sy
   float d1;     // Sy^2 + 81 C1
-  float d2;     // 9 Syy - Sy^2 + 81 C2
+  float v;      // 9 Syy - Sy^2   (81 x variance)
 };
 
+// The cancelling differences (9 Sxx - Sx^2, 18 Sxy - 2 Sx Sy) are formed FIRST, with a
+// single rounding each (FMA), and the constants added afterwards: adding 81*C2 to a
+// ~40-magnitude operand before the subtraction rounds it onto that operand's ulp grid
+// and biases the whole loss by ~6e-6 relative (measured; see tests/test_emul.py).
 PPEA_HD SsimY ssim_y_stats(float Sy, float Syy) {
   SsimY y;
   y.s = Sy;
-  y.d1 = Sy * Sy + PPEA_SSIM_K1;
-  y.d2 = (9.f * Syy + PPEA_SSIM_K2) - Sy * Sy;
+  y.d1 = fma_rn(Sy, Sy, PPEA_SSIM_K1);
+  y.v = fma_rn(9.f, Syy, -mul_rn(Sy, Sy));
   return y;
+}
+
+struct SsimTerms {
+  float n1, n2, d1, d2;
+};
+
+PPEA_HD SsimTerms ssim_terms(float Sx, float Sxx, float Sxy, const SsimY& y) {
+  SsimTerms t;
+  const float a2 = 2.f * mul_rn(Sx, y.s);
+  const float sx2 = mul_rn(Sx, Sx);
+  t.n1 = add_rn(a2, PPEA_SSIM_K1);
+  t.n2 = add_rn(fma_rn(18.f, Sxy, -a2), PPEA_SSIM_K2);
+  t.d1 = add_rn(sx2, y.d1);
+  t.d2 = add_rn(add_rn(fma_rn(9.f, Sxx, -sx2), y.v), PPEA_SSIM_K2);
+  return t;
 }
 
 // SSIM dissimilarity clamp((1 - n/d)/2, 0, 1) from the 3x3 window sums
 PPEA_HD float ssim_from_sums(float Sx, float Sxx, float Sxy, const SsimY& y) {
-  float a = Sx * y.s;
-  float n1 = 2.f * a + PPEA_SSIM_K1;
-  float n2 = (18.f * Sxy + PPEA_SSIM_K2) - 2.f * a;
-  float d1 = Sx * Sx + y.d1;
-  float d2 = (9.f * Sxx + y.d2) - Sx * Sx;
-  float R = fast_div(n1 * n2, d1 * d2);
-  return clamp01(0.5f - 0.5f * R);
+  const SsimTerms t = ssim_terms(Sx, Sxx, Sxy, y);
+  const float R = fast_div(t.n1 * t.n2, t.d1 * t.d2);
+  return clamp01(fma_rn(-0.5f, R, 0.5f));
 }
 
 // Adjoint of ssim_from_sums wrt the x-dependent window sums, scaled by `g`
@@ -266,21 +281,16 @@ struct SsimAdj {
 };
 
 PPEA_HD SsimAdj ssim_adjoint(float Sx, float Sxx, float Sxy, const SsimY& y, float g) {
-  float a = Sx * y.s;
-  float sx2 = Sx * Sx;
-  float n1 = 2.f * a + PPEA_SSIM_K1;
-  float n2 = (18.f * Sxy + PPEA_SSIM_K2) - 2.f * a;
-  float d1 = sx2 + y.d1;
-  float d2 = (9.f * Sxx + y.d2) - sx2;
-  float inv_d = 1.f / (d1 * d2);
-  float R = n1 * n2 * inv_d;
-  float v = 0.5f - 0.5f * R;
+  const SsimTerms t = ssim_terms(Sx, Sxx, Sxy, y);
+  const float inv_d = 1.f / (t.d1 * t.d2);
+  const float R = t.n1 * t.n2 * inv_d;
+  const float v = fma_rn(-0.5f, R, 0.5f);
   // torch.clamp backward passes the gradient where min <= v <= max (inclusive)
-  float k = (v >= 0.f && v <= 1.f) ? -0.5f * g * inv_d : 0.f;
+  const float k = (v >= 0.f && v <= 1.f) ? -0.5f * g * inv_d : 0.f;
   SsimAdj o;
-  o.cA = k * (2.f * y.s * (n2 - n1) - 2.f * R * Sx * (d2 - d1));
-  o.cB = k * (-18.f * R * d1);
-  o.cC = k * (18.f * n1);
+  o.cA = k * (2.f * y.s * (t.n2 - t.n1) - 2.f * R * Sx * (t.d2 - t.d1));
+  o.cB = k * (-18.f * R * t.d1);
+  o.cC = k * (18.f * t.n1);
   return o;
 }
 

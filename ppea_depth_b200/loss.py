@@ -1,0 +1,197 @@
+"""Drop-in replacements of the four loss methods of the reference Trainer.
+
+Same names, signatures, dict-key conventions and return values as
+/root/reference/ppeadepth/trainer.py:
+  generate_images_pred(self, inputs, outputs, is_multi=False)      :871-918
+  compute_reprojection_loss(self, pred, target)                    :995-1007
+  compute_loss_masks(reprojection_loss, identity_reprojection_loss):1009-1027 (static)
+  compute_losses(self, inputs, outputs, is_multi=False)            :1032-1160
+
+``install(Trainer)`` rebinds them on the reference's Trainer class, so
+`trainer.py`, `process_batch` and the launch command are used unchanged:
+
+    import ppeadepth.trainer as T, ppea_depth_b200
+    ppea_depth_b200.install(T.Trainer)
+
+`generate_images_pred` runs the fused forward (it must: the reference reads
+outputs[("depth", 0, s)] right after it, trainer.py:443-451, 466) and parks the
+result in ``outputs``; `compute_losses` turns it into the reference's loss
+dict.  The warped images / sampling grids (("color", f, s), ("sample", f, s))
+that the reference also stores are never read again by the training step
+(SURVEY.md §3.2); they are produced only with ``materialize_warps=True``.
+
+The tie-break noise of the automask (trainer.py:1084-1087) is drawn exactly as
+the reference draws it -- ``torch.randn`` on the CPU default generator, one
+(B,1,H,W) draw per scale, scale-ascending -- so seeding reproduces the
+reference's masks; ``noise_mode="device"`` draws on the GPU instead (no H2D
+copy, different stream of numbers).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import functional as Fn
+from .functional import VslConfig
+
+_RESULT_KEY = "_ppea_vsl_result"
+
+
+def _opt(self, name, default):
+    return getattr(self.opt, name, default)
+
+
+def _config(self, is_multi, **kw):
+    o = self.opt
+    return VslConfig(
+        is_multi=bool(is_multi),
+        automask=True,     # the reference never passes identity=None to compute_loss_masks (trainer.py:1088-1091)
+        selec_reproj=bool(_opt(self, "selec_reproj", True)),
+        no_ssim=bool(_opt(self, "no_ssim", False)),
+        motion_mask=not _opt(self, "disable_motion_masking", False),
+        match_aug=not _opt(self, "no_matching_augmentation", False),
+        deterministic=bool(getattr(self, "ppea_deterministic", False)),
+        min_depth=float(o.min_depth), max_depth=float(o.max_depth),
+        disparity_smoothness=float(_opt(self, "disparity_smoothness", 1e-3)),
+        want_loss_px=bool(getattr(self, "ppea_keep_maps", False)),
+        **kw)
+
+
+def _draw_noise(self, shape, device):
+    mode = getattr(self, "ppea_noise_mode", "reference")
+    if mode == "device":
+        return torch.randn(shape, device=device)
+    return torch.randn(shape).to(device, non_blocking=True)   # trainer.py:1086-1087
+
+
+def _run_fused(self, inputs, outputs, is_multi):
+    o = self.opt
+    S = o.sclm + 1
+    f0, f1 = o.frame_ids[1], o.frame_ids[2]
+    if len(o.frame_ids) != 3:
+        raise NotImplementedError("the fused path implements the reference's two-source configuration "
+                                  "(frame_ids [0,-1,1]; selec_reproj hard-codes it, trainer.py:1078-1083)")
+    T = (outputs[("cam_T_cam", 0, f0)], outputs[("cam_T_cam", 0, f1)])
+    dev = outputs[("disp", 0)].device
+    groups = []
+    if _opt(self, "v1_multiscale", False):
+        # every scale has its own image resolution (trainer.py:883-884): one call per scale
+        for s in range(S):
+            groups.append((s, 1, s))
+    else:
+        groups.append((0, S, 0))                     # all scales share source_scale 0 (trainer.py:886-888)
+    results = []
+    for first, n, ss in groups:
+        scales = range(first, first + n)
+        disps = [outputs[("disp", s)] for s in scales]
+        colors = [inputs[("color", 0, s)] for s in scales]
+        tgt = inputs[("color", 0, ss)]
+        kw = {}
+        cfg = _config(self, is_multi, first_scale=first, total_scales=S)
+        if is_multi:
+            kw["mono_depth"] = [outputs[("mono_depth", 0, s)] for s in scales]
+            kw["cons_mask"] = outputs.get("consistency_mask")
+            kw["aug_mask"] = outputs.get("augmentation_mask")
+            if kw["aug_mask"] is not None:
+                kw["aug_mask"] = kw["aug_mask"][:o.batch_size]
+        elif not _opt(self, "disable_automasking", False):    # the flag only removes the noise (trainer.py:1084-1087)
+            kw["noise"] = [_draw_noise(self, (tgt.shape[0], 1, tgt.shape[2], tgt.shape[3]), dev) for _ in scales]
+        res = Fn.view_synthesis_loss(disps, T, tgt, (inputs[("color", f0, ss)], inputs[("color", f1, ss)]),
+                                     inputs[("K", ss)], inputs[("inv_K", ss)], colors, cfg, **kw)
+        results.append((first, n, res))
+    return results
+
+
+def generate_images_pred(self, inputs, outputs, is_multi=False):
+    """Fused stand-in for trainer.py:871-918: writes outputs[("depth", 0, s)] for every
+    scale (and, on request, the warped images) and parks the fused result for compute_losses."""
+    results = _run_fused(self, inputs, outputs, is_multi)
+    for first, n, res in results:
+        for i in range(n):
+            outputs[("depth", 0, first + i)] = res.depth[i]
+    outputs[(_RESULT_KEY, bool(is_multi))] = results
+    if getattr(self, "ppea_materialize_warps", False):
+        _materialize_warps(self, inputs, outputs, is_multi)
+
+
+def _materialize_warps(self, inputs, outputs, is_multi):
+    """The reference's per-source byproducts (trainer.py:904-918), through the piecewise operators."""
+    import torch.nn.functional as F
+    o = self.opt
+    for s in range(o.sclm + 1):
+        ss = s if _opt(self, "v1_multiscale", False) else 0
+        depth = outputs[("depth", 0, s)]
+        for f in o.frame_ids[1:]:
+            T = outputs[("cam_T_cam", 0, f)]
+            if is_multi:
+                T = T.detach()
+            cam = self.backproject_depth[ss](depth, inputs[("inv_K", ss)])
+            pix = self.project_3d[ss](cam, inputs[("K", ss)], T)
+            outputs[("sample", f, s)] = pix
+            outputs[("color", f, s)] = Fn.grid_sample_border(inputs[("color", f, ss)], pix)
+            if not _opt(self, "disable_automasking", False):
+                outputs[("color_identity", f, s)] = inputs[("color", f, ss)]
+
+
+def compute_reprojection_loss(self, pred, target):
+    """0.85 * mean_c SSIM + 0.15 * mean_c |target - pred|  -> (B,1,H,W); trainer.py:995-1007."""
+    return Fn.reprojection_loss(pred, target, bool(_opt(self, "no_ssim", False)))
+
+
+def compute_loss_masks(reprojection_loss, identity_reprojection_loss):
+    """argmin([reproj, identity]) == 0 as float; trainer.py:1009-1027.  A (B,1,H,W) comparison --
+    inside the fused path it is a predicate in the forward kernel's epilogue."""
+    if identity_reprojection_loss is None:
+        return torch.ones_like(reprojection_loss)
+    return (reprojection_loss <= identity_reprojection_loss).float()
+
+
+def compute_losses(self, inputs, outputs, is_multi=False):
+    """Loss dict of trainer.py:1032-1160: "loss", "loss/{s}", "reproj_loss/{s}" and (multi)
+    "consistency_loss/{s}" as 0-dim tensors attached to the fused autograd node."""
+    results = outputs.pop((_RESULT_KEY, bool(is_multi)), None)
+    if results is None:
+        results = _run_fused(self, inputs, outputs, is_multi)
+        for first, n, res in results:
+            for i in range(n):
+                outputs[("depth", 0, first + i)] = res.depth[i]
+    losses = {}
+    total = None
+    for first, n, res in results:
+        for i in range(n):
+            s = first + i
+            losses["reproj_loss/{}".format(s)] = res.reproj_loss(i)
+            if is_multi:
+                losses["consistency_loss/{}".format(s)] = res.consistency_loss(i)
+            losses["loss/{}".format(s)] = res.scale_loss(i)
+        total = res.loss if total is None else total + res.loss     # each call already divides by sclm+1
+    losses["loss"] = total
+    if getattr(self, "ppea_keep_maps", False):
+        outputs[("ppea_maps", bool(is_multi))] = results
+    return losses, []
+
+
+def install(trainer_cls, deterministic=False, noise_mode="reference"):
+    """Rebinds the reference Trainer's loss methods to the fused implementation."""
+    trainer_cls.generate_images_pred = generate_images_pred
+    trainer_cls.compute_reprojection_loss = compute_reprojection_loss
+    trainer_cls.compute_loss_masks = staticmethod(compute_loss_masks)
+    trainer_cls.compute_losses = compute_losses
+    trainer_cls.ppea_deterministic = deterministic
+    trainer_cls.ppea_noise_mode = noise_mode
+    return trainer_cls
+
+
+class ViewSynthesisLoss:
+    """Stand-alone holder of the four methods for callers without the reference Trainer
+    (tests, bench.py): ``ViewSynthesisLoss(opt).generate_images_pred(inputs, outputs)`` etc."""
+
+    def __init__(self, opt, deterministic=False, noise_mode="reference", keep_maps=False):
+        self.opt = opt
+        self.ppea_deterministic = deterministic
+        self.ppea_noise_mode = noise_mode
+        self.ppea_keep_maps = keep_maps
+
+    generate_images_pred = generate_images_pred
+    compute_reprojection_loss = compute_reprojection_loss
+    compute_loss_masks = staticmethod(compute_loss_masks)
+    compute_losses = compute_losses

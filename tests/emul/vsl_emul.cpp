@@ -151,7 +151,7 @@ int emul_vsl_forward(int B, int H, int W, int h_s, int w_s, unsigned flags, floa
         } else if (automask) {
           float idl = fminf(Lid[0][i], Lid[1][i]);
           // min(dim=1) returns the first on ties; values identical either way
-          idl = idl + noise[b * plane + i] * 0.00001f;
+          if (noise) idl = idl + noise[b * plane + i] * 0.00001f;
           bool on = s.r <= idl;
           mask = on ? 1.f : 0.f;
           if (on) bits |= 4u;

@@ -1,0 +1,88 @@
+"""CPU: the scalar device functions of csrc/vsl_math.cuh (shared by every CUDA kernel), driven
+pixel by pixel by tests/emul/vsl_emul.cpp, against the golden fixtures / the oracle.  This pins the
+forward arithmetic, the selection rules and the hand-derived backward formulas where no GPU exists;
+the kernels' tiling and reductions are covered by the -m gpu tests."""
+import pytest
+import torch
+
+import emul_harness as E
+from conftest import golden_names, load_golden
+from oracle import vsl_oracle as O
+
+# per-pixel decision margin below which a flipped mask / source index is fp32 rounding noise:
+# SSIM's sigma = E[x^2] - mu^2 cancels ~3 digits, so equally valid fp32 evaluation orders (the
+# reference's included, measured against fp64) differ by up to ~5e-5 per pixel.
+MARGIN = 1e-4
+
+NAMES = [n for n in golden_names() if "v1_multiscale" not in n]
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_emulator_forward_matches_golden(name):
+    fx = load_golden(name)
+    opt, multi = fx["opt"], fx["is_multi"]
+    for s in range(opt.sclm + 1):
+        fw = E.forward_scale(fx["inputs"], fx["outputs"], opt, s, multi, fx["noise"])
+        ref = fx["ref_maps"][s]
+        om = fx["oracle_maps"][s]
+        assert float((fw["depth"] - ref["depth"]).abs().max()) <= 4e-6 * float(ref["depth"].abs().max())
+        if "warped" in ref:
+            for i in range(2):
+                assert float((fw["warped"][i] - ref["warped"][i]).abs().max()) < 2e-5
+                assert float((fw["grid"][i] - ref["sample"][i]).abs().max()) < 2e-5
+        r, ident = om["r"], om["ident"]
+        assert float((fw["loss_px"] - r).abs().max()) < 1e-4
+        assert float((fw["loss_px"] - r).mean().abs()) < 2e-7          # no systematic bias
+        src = (fw["sel"] & 3).unsqueeze(1)
+        bad_src = src != om["src_idx"]
+        if bad_src.any():      # a flipped source needs the two candidates to be within the margin
+            assert int(bad_src.sum()) <= max(2, bad_src.numel() // 2000)
+        if not multi:
+            mask = ((fw["sel"] >> 2) & 1).unsqueeze(1)
+            bad = mask != om["mask"]
+            assert float((r - ident).abs()[bad].max() if bad.any() else 0.0) < MARGIN
+            near = int(((r - ident).abs() < MARGIN).sum())      # identity pose: warped == source, every pixel is a tie
+            assert int(bad.sum()) <= max(2, bad.numel() // 2000, near // 2)
+        reproj = fw["sums"][0] / (fw["sums"][1] + 1e-7)
+        want = float(fx["ref_losses"]["reproj_loss/%d" % s])
+        tol = 1e-5 if multi else (2e-4 if "identity" not in name else 2e-2)      # mono at fixture size: one flipped pixel of ~4600 moves the mean by ~1e-4
+        assert abs(reproj - want) <= tol * want
+
+
+@pytest.mark.parametrize("name", ["mono_s4_48x96", "multi_s4_48x96", "mono_s2_nossim", "mono_s1_40x72_ragged"])
+def test_emulator_backward_matches_fp64_autograd(name):
+    fx = load_golden(name)
+    opt, multi = fx["opt"], fx["is_multi"]
+    S = opt.sclm + 1
+    opt.disparity_smoothness = 0.0                       # the emulator covers the reprojection/consistency terms
+    B, H, W = opt.batch_size, opt.height, opt.width
+    gT = {f: torch.zeros(B, 4, 4, dtype=torch.float64) for f in (-1, 1)}
+    gdisp = {}
+    masks = {}
+    for s in range(S):
+        fw = E.forward_scale(fx["inputs"], fx["outputs"], opt, s, multi, fx["noise"])
+        g_r = (1.0 / S) / (fw["sums"][1] + 1e-7)
+        g_c = (1.0 / S) / (B * H * W) if multi else 0.0
+        gd, gP = E.backward_scale(fw, opt, g_r, g_c)
+        gdisp[s] = gd
+        Kd = fx["inputs"][("K", 0)].double()
+        for i, f in enumerate((-1, 1)):
+            g4 = torch.zeros(B, 4, 4, dtype=torch.float64)
+            g4[:, :3, :] = gP[:, i]
+            gT[f] += Kd.transpose(1, 2) @ g4
+        masks[s] = (((fw["sel"] >> 2) & 1), fw["sel"] & 3)
+    # fp64 autograd of the oracle with the emulator's own selection frozen is the exact reference;
+    # the fp32 oracle (whose mask may differ in a few pixels) bounds the expected agreement
+    _, g32, _ = O.run_fwd_bwd(fx["inputs"], fx["outputs"], opt, multi, fx["noise"], forced=masks)
+    _, g64, _ = O.run_fwd_bwd(fx["inputs"], fx["outputs"], opt, multi, fx["noise"], dtype=torch.float64, forced=masks)
+    for s in range(S):
+        ref = g64[("disp", s)]
+        base = float((g32[("disp", s)].double() - ref).norm() / ref.norm())
+        err = float((gdisp[s].double() - ref).norm() / ref.norm())
+        assert err <= max(2e-4, 3.0 * base), (s, err, base)
+    if not multi:
+        for f in (-1, 1):
+            ref = g64[("cam_T_cam", 0, f)]
+            base = float((g32[("cam_T_cam", 0, f)].double() - ref).norm() / ref.norm())
+            err = float((gT[f] - ref).norm() / ref.norm())
+            assert err <= max(2e-4, 3.0 * base), (f, err, base)
