@@ -81,9 +81,12 @@ __global__ void __launch_bounds__(kSmoothThreads) smooth_forward_kernel(const __
   float sx = 0.f, sy = 0.f;
   for (int i = lo + threadIdx.x; i < hi; i += kSmoothThreads) {
     const int y = i / w, x = i - y * w;
-    const float di = __ldg(d + i) * inv;
-    if (x + 1 < w) sx += fabsf(di - __ldg(d + i + 1) * inv) * edge_weight(img, n, i, i + 1);
-    if (y + 1 < h) sy += fabsf(di - __ldg(d + i + w) * inv) * edge_weight(img, n, i, i + w);
+    // mul_rn: every normalised value is rounded once, exactly as the reference's division does; a
+    // contracted fma(-d_j, inv, nd_i) would turn exact ties (equal disparities) into +-1 ulp noise
+    // whose SIGN the backward would then propagate.
+    const float di = mul_rn(__ldg(d + i), inv);
+    if (x + 1 < w) sx += fabsf(di - mul_rn(__ldg(d + i + 1), inv)) * edge_weight(img, n, i, i + 1);
+    if (y + 1 < h) sy += fabsf(di - mul_rn(__ldg(d + i + w), inv)) * edge_weight(img, n, i, i + w);
   }
   const float tx = block_sum(sx, red);
   const float ty = block_sum(sy, red);
@@ -113,13 +116,13 @@ __global__ void __launch_bounds__(kSmoothThreads) smooth_backward_kernel(const _
   float* out = sc.grad_disp + (size_t)b * n;
   for (int i = lo + threadIdx.x; i < hi; i += kSmoothThreads) {
     const int y = i / w, x = i - y * w;
-    const float di = __ldg(d + i) * inv;
+    const float di = mul_rn(__ldg(d + i), inv);
     float acc = 0.f;
     auto sgn = [](float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); };
-    if (x + 1 < w) acc += gx * sgn(di - __ldg(d + i + 1) * inv) * edge_weight(img, n, i, i + 1);
-    if (x > 0) acc -= gx * sgn(__ldg(d + i - 1) * inv - di) * edge_weight(img, n, i - 1, i);
-    if (y + 1 < h) acc += gy * sgn(di - __ldg(d + i + w) * inv) * edge_weight(img, n, i, i + w);
-    if (y > 0) acc -= gy * sgn(__ldg(d + i - w) * inv - di) * edge_weight(img, n, i - w, i);
+    if (x + 1 < w) acc += gx * sgn(di - mul_rn(__ldg(d + i + 1), inv)) * edge_weight(img, n, i, i + 1);
+    if (x > 0) acc -= gx * sgn(mul_rn(__ldg(d + i - 1), inv) - di) * edge_weight(img, n, i - 1, i);
+    if (y + 1 < h) acc += gy * sgn(di - mul_rn(__ldg(d + i + w), inv)) * edge_weight(img, n, i, i + w);
+    if (y > 0) acc -= gy * sgn(mul_rn(__ldg(d + i - w), inv) - di) * edge_weight(img, n, i - w, i);
     out[i] = (acc - mean_term) * inv;
   }
 }

@@ -1,0 +1,156 @@
+"""Fixed-shape execution plan for the fused loss: buffers, parameter block and (optionally) a
+CUDA graph are built once and replayed every step.
+
+The training step has static shapes (the reference even bakes batch_size into its modules,
+/root/reference/ppeadepth/layers.py:142-161, and drops ragged batches, trainer.py:215-218), so
+everything the autograd wrapper does per call -- output allocation, filling the C parameter
+struct, eight kernel launches -- can be hoisted: ``FusedPlan.capture()`` records
+forward + backward into one CUDA graph whose replay costs a single launch on the host.
+Inputs are read from the tensors bound at construction; refresh them with ``copy_`` (their
+addresses are baked into the graph).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _cabi as C
+from .functional import VslConfig, _f32c
+
+
+class FusedPlan:
+    def __init__(self, cfg: VslConfig, disps: Sequence[torch.Tensor], T: Sequence[torch.Tensor], tgt: torch.Tensor,
+                 src: Sequence[torch.Tensor], K: torch.Tensor, inv_K: torch.Tensor, colors: Sequence[torch.Tensor],
+                 noise: Optional[Sequence[torch.Tensor]] = None, cons_mask: Optional[torch.Tensor] = None,
+                 aug_mask: Optional[torch.Tensor] = None, mono_depth: Optional[Sequence[torch.Tensor]] = None,
+                 grad_pose: Optional[bool] = None):
+        lib = C.lib()
+        self.cfg = cfg
+        self.tgt = _f32c(tgt, "tgt")
+        self.device = self.tgt.device
+        self.B, _, self.H, self.W = self.tgt.shape
+        self.S = len(disps)
+        B, H, W, S, dev = self.B, self.H, self.W, self.S, self.device
+        self.disps = [_f32c(d.detach(), "disp") for d in disps]
+        self.T = [_f32c(t.detach(), "T") for t in T]
+        self.src = [_f32c(s, "src") for s in src]
+        self.K, self.inv_K = _f32c(K, "K"), _f32c(inv_K, "inv_K")
+        self.colors = [_f32c(c, "color") for c in colors]
+        self.noise = [_f32c(z, "noise") for z in noise] if (noise is not None and not cfg.is_multi) else None
+        self.cons_mask = _f32c(cons_mask, "cons_mask") if (cfg.is_multi and cfg.motion_mask) else None
+        self.aug_mask = _f32c(aug_mask.reshape(-1)[:B], "aug_mask") if (cfg.is_multi and cfg.match_aug) else None
+        self.mono_depth = [_f32c(m, "mono_depth") for m in mono_depth] if cfg.is_multi else None
+        self.grad_pose = (not cfg.is_multi) if grad_pose is None else bool(grad_pose)
+        f32 = dict(device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            self.depth = [torch.empty(B, 1, H, W, **f32) for _ in range(S)]
+            self.sel = [torch.empty(B, H, W, device=dev, dtype=torch.uint8) for _ in range(S)]
+            self.loss_px = [torch.empty(B, 1, H, W, **f32) if cfg.want_loss_px else None for _ in range(S)]
+            self.sums = torch.empty(lib.ppea_vsl_sums_floats(B, S), **f32)
+            self.losses = torch.empty(1 + C.LOSSES_PER_SCALE * S, **f32)
+            self.grad_losses = torch.zeros(1 + C.LOSSES_PER_SCALE * S, **f32)
+            self.grad_losses[0] = 1.0                     # d loss / d loss
+            self.grad_disp = [torch.empty_like(d) for d in self.disps]
+            self.grad_T = [torch.empty(B, 4, 4, **f32) for _ in range(2)] if self.grad_pose else None
+            self.flags_fwd = cfg.flags(grad_pose=False)
+            self.flags_bwd = cfg.flags(grad_pose=self.grad_pose)
+            self.ws_fwd = torch.empty(max(lib.ppea_vsl_workspace_bytes(B, H, W, S) // 4, 4), **f32)
+            self.ws_bwd = torch.empty(max(lib.ppea_vsl_backward_workspace_bytes(B, H, W, S, self.flags_bwd) // 4, 4), **f32)
+        self._p_fwd = self._params(self.flags_fwd)
+        self._p_bwd = self._params(self.flags_bwd)
+        g = C.PpeaVslGrads()
+        g.struct_size = ctypes.sizeof(C.PpeaVslGrads)
+        g.grad_losses = self.grad_losses.data_ptr()
+        if self.grad_pose:
+            g.grad_T[0], g.grad_T[1] = self.grad_T[0].data_ptr(), self.grad_T[1].data_ptr()
+        g.workspace = self.ws_bwd.data_ptr()
+        g.workspace_bytes = self.ws_bwd.numel() * 4
+        self._g = g
+        self._lib = lib
+        self.graph = None
+
+    # kernels launched by one forward / backward call (for bench.py's gpu_launches)
+    @property
+    def launches_forward(self):
+        return 4
+
+    @property
+    def launches_backward(self):
+        n = 2 + (1 if self.grad_pose else 0)
+        if self.cfg.deterministic:
+            n += sum(1 for d in self.disps if tuple(d.shape[-2:]) != (self.H, self.W))
+        return n
+
+    def _params(self, flags):
+        cfg = self.cfg
+        p = C.PpeaVslParams()
+        p.struct_size = ctypes.sizeof(C.PpeaVslParams)
+        p.flags = flags
+        p.batch, p.height, p.width = self.B, self.H, self.W
+        p.num_scales = self.S
+        p.first_scale = cfg.first_scale
+        p.total_scales = cfg.total_scales if cfg.total_scales is not None else self.S
+        lo = 1.0 / cfg.max_depth
+        p.disp_lo, p.disp_range, p.eps = lo, 1.0 / cfg.min_depth - lo, cfg.eps
+        p.disparity_smoothness = cfg.disparity_smoothness
+        p.tgt = self.tgt.data_ptr()
+        p.src[0], p.src[1] = self.src[0].data_ptr(), self.src[1].data_ptr()
+        p.K, p.inv_K = self.K.data_ptr(), self.inv_K.data_ptr()
+        p.T[0], p.T[1] = self.T[0].data_ptr(), self.T[1].data_ptr()
+        p.cons_mask = self.cons_mask.data_ptr() if self.cons_mask is not None else None
+        p.aug_mask = self.aug_mask.data_ptr() if self.aug_mask is not None else None
+        for s in range(self.S):
+            sc = p.scales[s]
+            sc.disp_h, sc.disp_w = self.disps[s].shape[-2], self.disps[s].shape[-1]
+            sc.disp = self.disps[s].data_ptr()
+            sc.color = self.colors[s].data_ptr()
+            sc.noise = self.noise[s].data_ptr() if self.noise is not None else None
+            sc.mono_depth = self.mono_depth[s].data_ptr() if self.mono_depth is not None else None
+            sc.depth = self.depth[s].data_ptr()
+            sc.loss_px = self.loss_px[s].data_ptr() if self.loss_px[s] is not None else None
+            sc.sel = self.sel[s].data_ptr()
+            sc.grad_disp = self.grad_disp[s].data_ptr()
+        p.sums = self.sums.data_ptr()
+        p.losses = self.losses.data_ptr()
+        p.workspace = self.ws_fwd.data_ptr()
+        p.workspace_bytes = self.ws_fwd.numel() * 4
+        return p
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def forward(self):
+        C.check(self._lib.ppea_vsl_forward(ctypes.byref(self._p_fwd), self._stream()))
+        return self.losses
+
+    def backward(self):
+        C.check(self._lib.ppea_vsl_backward(ctypes.byref(self._p_bwd), ctypes.byref(self._g), self._stream()))
+        return self.grad_disp, self.grad_T
+
+    def step(self):
+        self.forward()
+        self.backward()
+
+    def capture(self, backward=True):
+        """Records forward (+ backward) into a CUDA graph; ``replay()`` afterwards."""
+        with torch.cuda.device(self.device):
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):         # warm-up outside capture: function attributes, lazy module load
+                self.forward()
+                if backward:
+                    self.backward()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self.forward()
+                if backward:
+                    self.backward()
+        self.graph = graph
+        return graph
+
+    def replay(self):
+        self.graph.replay()

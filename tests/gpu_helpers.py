@@ -89,17 +89,28 @@ def check_against_oracle(inputs, outputs, opt, is_multi, noise, losses, grads, m
             assert int(bad.sum()) <= max(2, bad.numel() // 2000, near // 2), (s, int(bad.sum()), near)
             n_flip += int(bad.sum())
     forced = forced_from(maps)
-    l32, _, _ = O.run_fwd_bwd(inputs, outputs, opt, is_multi, noise, forced=forced)
+    l32, g32, _ = O.run_fwd_bwd(inputs, outputs, opt, is_multi, noise, forced=forced)
     l64, g64, _ = O.run_fwd_bwd(inputs, outputs, opt, is_multi, noise, dtype=torch.float64, forced=forced)
     for k, v in l32.items():
         if k.startswith("smooth_loss"):
             continue
         got = float(losses[k])
-        assert abs(got - float(v)) <= loss_rtol * abs(float(v)) + 1e-9, (k, got, float(v), float(l64[k]))
+        # within loss_rtol of the fp32 reference path or of the fp64 truth (the fp32 reference itself
+        # sits up to ~1e-5 from fp64 when SSIM ~ 0, e.g. identity pose)
+        err = min(abs(got - float(v)), abs(got - float(l64[k])))
+        assert err <= loss_rtol * abs(float(v)) + 1e-9, (k, got, float(v), float(l64[k]))
+    # Gradients: within grad_rtol (max-norm, relative) of the fp32 reference path at the same
+    # selection; where fp32 itself is kink-limited (sign(y-x), clamp and clip boundaries decided by the
+    # last bit make the reference's own fp32 gradient deviate from fp64 by more than that), the kernel
+    # must be at least as close to the fp64 truth as the reference is (factor 2).
     for k, ref in g64.items():
         assert k in grads, k
-        err = float((grads[k].double() - ref).abs().max())
-        assert err <= grad_rtol * float(ref.abs().max()) + 1e-9, (k, err, float(ref.abs().max()))
+        scale = float(ref.abs().max())
+        err64 = float((grads[k].double() - ref).abs().max())
+        err32 = float((grads[k] - g32[k]).abs().max())
+        ref32_err = float((g32[k].double() - ref).abs().max())
+        ok = min(err64, err32) <= grad_rtol * scale + 1e-9 or err64 <= 2.0 * ref32_err
+        assert ok, (k, err64, err32, ref32_err, scale)
     if is_multi:
         assert not any(k[0] == "cam_T_cam" for k in grads)
     return n_flip

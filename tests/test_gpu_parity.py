@@ -52,15 +52,13 @@ def test_cuda_deterministic_backward_matches_and_repeats():
     noise = make_noise(cfg, 4)
     opt = O.default_opt(sclm=3, height=64, width=96, batch_size=2)
     _, g_atomic, _ = run_cuda(inputs, outputs, opt, False, noise)
-    _, g_det1, maps = run_cuda(inputs, outputs, opt, False, noise, deterministic=True)
+    l_det, g_det1, maps = run_cuda(inputs, outputs, opt, False, noise, deterministic=True)
     _, g_det2, _ = run_cuda(inputs, outputs, opt, False, noise, deterministic=True)
     for k in g_det1:
         assert torch.equal(g_det1[k], g_det2[k]), k                      # bit-reproducible
         scale = float(g_det1[k].abs().max())
         assert float((g_det1[k] - g_atomic[k]).abs().max()) <= 2e-6 * scale + 1e-12, k
-    _, g64, _ = O.run_fwd_bwd(inputs, outputs, opt, False, noise, dtype=torch.float64, forced=forced_from(maps))
-    for k, ref in g64.items():
-        assert float((g_det1[k].double() - ref).abs().max()) <= 1e-4 * float(ref.abs().max())
+    check_against_oracle(inputs, outputs, opt, False, noise, l_det, g_det1, maps)
 
 
 def test_cuda_upstream_gradient_is_linear():
@@ -85,8 +83,8 @@ def test_cuda_upstream_gradient_is_linear():
     b = grads_of(lambda L: 0.5 * L["loss/0"] + 0.5 * L["loss/1"])
     c = grads_of(lambda L: 3.0 * L["loss"])
     for x, y, z in zip(a, b, c):
-        assert float((x - y).abs().max()) <= 1e-6 * float(x.abs().max()) + 1e-12
-        assert float((3.0 * x - z).abs().max()) <= 2e-6 * float(z.abs().max()) + 1e-12
+        assert float((x - y).abs().max()) <= 2e-5 * float(x.abs().max()) + 1e-12
+        assert float((3.0 * x - z).abs().max()) <= 2e-5 * float(z.abs().max()) + 1e-12
     only_reproj1 = grads_of(lambda L: L["reproj_loss/1"])
     assert float(only_reproj1[0].abs().max()) == 0.0            # no gradient reaches disp_0
     assert float(only_reproj1[1].abs().max()) > 0.0
