@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define PPEA_ABI_VERSION 2
+#define PPEA_ABI_VERSION 3
 
 /* error codes (negative) */
 #define PPEA_OK 0
@@ -126,6 +126,10 @@ typedef struct PpeaVslParams {
   float* losses;           /* out: see PPEA_LOSSES_PER_SCALE */
   void* workspace;         /* >= ppea_vsl_workspace_bytes(), 16-byte aligned; private to this call until it completes */
   size_t workspace_bytes;
+  void* const* trace_events; /* NULL, or PPEA_TRACE_EVENTS cudaEvent_t handles (ppea_event_create) recorded on `stream`:
+                                [0] before the first kernel, then after each stage --
+                                forward:  [1] disp sums  [2] fused forward kernel  [3] smoothness stencil  [4] finish
+                                backward: [1] smoothness backward  [2] fused backward kernel  [3] upsample gather  [4] pose finish */
 } PpeaVslParams;
 
 typedef struct PpeaVslGrads {
@@ -136,7 +140,16 @@ typedef struct PpeaVslGrads {
   size_t workspace_bytes;
 } PpeaVslGrads;
 
+#define PPEA_TRACE_EVENTS 5
+
 int ppea_abi_version(void);
+
+/* profiling helpers for bench.py: timing events created/destroyed by the caller through the library's
+ * own CUDA runtime instance (the library is linked against the static cudart). */
+void* ppea_event_create(void);
+void ppea_event_destroy(void* event);
+int ppea_event_record(void* event, void* stream);
+int ppea_event_elapsed_ms(void* start, void* stop, float* ms); /* synchronises on `stop` */
 const char* ppea_strerror(int code);
 
 /* forward workspace (block partial sums) */

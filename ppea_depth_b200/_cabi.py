@@ -20,7 +20,8 @@ INCLUDE_DIR = os.path.join(os.path.dirname(PKG_DIR), "include")
 SOURCES = ("api.cu", "vsl_fwd.cu", "vsl_bwd.cu", "smooth.cu", "ops.cu")
 HEADERS = ("vsl_common.cuh", "vsl_math.cuh")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
+TRACE_EVENTS = 5
 MAX_SCALES = 4
 SUMS_PER_SCALE = 8
 LOSSES_PER_SCALE = 4
@@ -60,6 +61,7 @@ class PpeaVslParams(ctypes.Structure):
         ("scales", PpeaVslScale * MAX_SCALES),
         ("sums", c_float_p), ("losses", c_float_p),
         ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
+        ("trace_events", ctypes.POINTER(ctypes.c_void_p)),
     ]
 
 
@@ -77,6 +79,10 @@ _I, _P, _F, _SZ, _U = ctypes.c_int, ctypes.c_void_p, ctypes.c_float, ctypes.c_si
 SIGNATURES = {
     "ppea_abi_version": (_I, []),
     "ppea_strerror": (ctypes.c_char_p, [_I]),
+    "ppea_event_create": (_P, []),
+    "ppea_event_destroy": (None, [_P]),
+    "ppea_event_record": (_I, [_P, _P]),
+    "ppea_event_elapsed_ms": (_I, [_P, _P, ctypes.POINTER(ctypes.c_float)]),
     "ppea_vsl_workspace_bytes": (_SZ, [_I, _I, _I, _I]),
     "ppea_vsl_backward_workspace_bytes": (_SZ, [_I, _I, _I, _I, _U]),
     "ppea_vsl_sums_floats": (_SZ, [_I, _I]),

@@ -82,6 +82,14 @@ void fill_args(const PpeaVslParams* p, VslArgs& a) {
   a.losses = p->losses;
 }
 
+#define PPEA_TRACE(p, i)                                                       \
+  do {                                                                         \
+    if ((p)->trace_events) {                                                   \
+      cudaError_t e__ = cudaEventRecord((cudaEvent_t)(p)->trace_events[i], stream); \
+      if (e__ != cudaSuccess) return (int)e__;                                 \
+    }                                                                          \
+  } while (0)
+
 #define PPEA_TRY(expr)                \
   do {                                \
     cudaError_t e__ = (expr);         \
@@ -107,6 +115,25 @@ const char* ppea_strerror(int code) {
   }
   if (code > 0) return cudaGetErrorString((cudaError_t)code);
   return "ppea: unknown error";
+}
+
+void* ppea_event_create(void) {
+  cudaEvent_t ev = nullptr;
+  if (cudaEventCreate(&ev) != cudaSuccess) return nullptr;
+  return (void*)ev;
+}
+void ppea_event_destroy(void* event) {
+  if (event) cudaEventDestroy((cudaEvent_t)event);
+}
+int ppea_event_record(void* event, void* stream) {
+  if (!event) return PPEA_E_NULL;
+  return (int)cudaEventRecord((cudaEvent_t)event, (cudaStream_t)stream);
+}
+int ppea_event_elapsed_ms(void* start, void* stop, float* ms) {
+  if (!start || !stop || !ms) return PPEA_E_NULL;
+  cudaError_t e = cudaEventSynchronize((cudaEvent_t)stop);
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop);
 }
 
 size_t ppea_vsl_workspace_bytes(int batch, int height, int width, int num_scales) {
@@ -137,10 +164,15 @@ int ppea_vsl_forward(const PpeaVslParams* p, void* stream_) {
   a.tiles_y = ceil_div(a.H, kFwdTileH);
   a.partials = (float*)p->workspace + ws.off_partials;
   a.smooth_ws = (float*)p->workspace + ws.off_smooth;
+  PPEA_TRACE(p, 0);
   PPEA_TRY(launch_smooth_disp_sums(a, stream));
+  PPEA_TRACE(p, 1);
   PPEA_TRY(launch_vsl_forward(a, stream));
+  PPEA_TRACE(p, 2);
   PPEA_TRY(launch_smooth_forward(a, stream));
+  PPEA_TRACE(p, 3);
   PPEA_TRY(launch_vsl_finish(a, fwd_blocks(a.B, a.H, a.W), stream));
+  PPEA_TRACE(p, 4);
   return PPEA_OK;
 }
 
@@ -172,10 +204,15 @@ int ppea_vsl_backward(const PpeaVslParams* p, const PpeaVslGrads* g, void* strea
         any_dup = true;
       }
   }
+  PPEA_TRACE(p, 0);
   PPEA_TRY(launch_smooth_backward(a, stream));
+  PPEA_TRACE(p, 1);
   PPEA_TRY(launch_vsl_backward(a, stream));
+  PPEA_TRACE(p, 2);
   if (any_dup) PPEA_TRY(launch_upsample_gather(a, stream));
+  PPEA_TRACE(p, 3);
   if (pose) PPEA_TRY(launch_pose_finish(a, bwd_blocks(a.B, a.H, a.W), stream));
+  PPEA_TRACE(p, 4);
   return PPEA_OK;
 }
 

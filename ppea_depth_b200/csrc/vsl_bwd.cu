@@ -375,12 +375,12 @@ cudaError_t launch_vsl_backward(const VslArgs& a, cudaStream_t stream) {
   cudaError_t e;
   if (a.flags & PPEA_F_GRAD_POSE) {
     auto kern = vsl_backward_kernel<kBwdTileW, kBwdTileH, kBwdThreads, true>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    e = ensure_dynamic_smem(kern, (int)sizeof(Smem));
     if (e != cudaSuccess) return e;
     kern<<<nblk, kBwdThreads, sizeof(Smem), stream>>>(a);
   } else {
     auto kern = vsl_backward_kernel<kBwdTileW, kBwdTileH, kBwdThreads, false>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    e = ensure_dynamic_smem(kern, (int)sizeof(Smem));
     if (e != cudaSuccess) return e;
     kern<<<nblk, kBwdThreads, sizeof(Smem), stream>>>(a);
   }

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+
 #include "../../include/ppea_vsl.h"
 #include "vsl_math.cuh"
 
@@ -99,6 +101,39 @@ cudaError_t launch_vsl_finish(const VslArgs& a, int nblk_fwd, cudaStream_t strea
 cudaError_t launch_smooth_backward(const VslArgs& a, cudaStream_t stream);
 cudaError_t launch_upsample_gather(const VslArgs& a, cudaStream_t stream);
 cudaError_t launch_pose_finish(const VslArgs& a, int nblk_bwd, cudaStream_t stream);
+
+// Opt a kernel into > 48 KB of dynamic shared memory once per device (the attribute is sticky per
+// function and device); keeping it out of the steady state also keeps it out of CUDA-graph capture.
+struct SmemAttrCache {
+  const void* fn[16];
+  unsigned long long devmask[16];
+  int n;
+};
+inline cudaError_t ensure_dynamic_smem_impl(const void* fn, int bytes) {
+  static SmemAttrCache cache = {};
+  static std::mutex mu;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mu);
+  int slot = -1;
+  for (int i = 0; i < cache.n; ++i)
+    if (cache.fn[i] == fn) slot = i;
+  if (slot >= 0 && dev < 64 && (cache.devmask[slot] >> dev) & 1ull) return cudaSuccess;
+  e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return e;
+  if (slot < 0 && cache.n < 16) {
+    slot = cache.n++;
+    cache.fn[slot] = fn;
+    cache.devmask[slot] = 0;
+  }
+  if (slot >= 0 && dev < 64) cache.devmask[slot] |= 1ull << dev;
+  return cudaSuccess;
+}
+template <typename Kern>
+inline cudaError_t ensure_dynamic_smem(Kern kern, int bytes) {
+  return ensure_dynamic_smem_impl(reinterpret_cast<const void*>(kern), bytes);
+}
 
 // ---- device helpers
 #if defined(__CUDACC__)

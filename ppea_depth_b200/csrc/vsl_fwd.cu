@@ -238,7 +238,7 @@ cudaError_t launch_vsl_forward(const VslArgs& a, cudaStream_t stream) {
   using Smem = FwdSmem<kFwdTileW, kFwdTileH>;
   auto kern = vsl_forward_kernel<kFwdTileW, kFwdTileH, kFwdThreads>;
   static_assert(sizeof(Smem) <= 227 * 1024, "shared memory tile too large");
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+  cudaError_t e = ensure_dynamic_smem(kern, (int)sizeof(Smem));
   if (e != cudaSuccess) return e;
   const int nblk = a.B * a.tiles_x * a.tiles_y;
   kern<<<nblk, kFwdThreads, sizeof(Smem), stream>>>(a);

@@ -154,3 +154,38 @@ class FusedPlan:
 
     def replay(self):
         self.graph.replay()
+
+    # ---- per-stage device timing (bench.py's roofline leg) -------------------
+    FWD_STAGES = ("smooth_disp_sums", "vsl_forward_kernel", "smooth_forward", "finish")
+    BWD_STAGES = ("smooth_backward", "vsl_backward_kernel", "upsample_gather", "pose_finish")
+
+    def enable_trace(self):
+        """Asks the library to record a CUDA event before/after every stage of forward and
+        backward (include/ppea_vsl.h: trace_events).  Affects eager calls made after this."""
+        lib = self._lib
+        self._ev = []
+        for p in (self._p_fwd, self._p_bwd):
+            arr = (ctypes.c_void_p * C.TRACE_EVENTS)()
+            for i in range(C.TRACE_EVENTS):
+                arr[i] = lib.ppea_event_create()
+                if not arr[i]:
+                    raise RuntimeError("cudaEventCreate failed")
+            p.trace_events = ctypes.cast(arr, ctypes.POINTER(ctypes.c_void_p))
+            self._ev.append(arr)
+
+    def disable_trace(self):
+        for p, arr in zip((self._p_fwd, self._p_bwd), getattr(self, "_ev", [])):
+            p.trace_events = None
+            for i in range(C.TRACE_EVENTS):
+                self._lib.ppea_event_destroy(arr[i])
+        self._ev = []
+
+    def trace_ms(self):
+        """Stage durations (ms) of the most recent traced forward + backward."""
+        out = {}
+        ms = ctypes.c_float()
+        for arr, names in zip(self._ev, (self.FWD_STAGES, self.BWD_STAGES)):
+            for i, name in enumerate(names):
+                C.check(self._lib.ppea_event_elapsed_ms(arr[i], arr[i + 1], ctypes.byref(ms)))
+                out[name] = ms.value
+        return out
