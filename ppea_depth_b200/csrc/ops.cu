@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(kT) ssim_forward_kernel(const float* __restric
   const size_t pl = idx / plane;
   const int r = (int)(idx - pl * plane), qy = r / W, qx = r - qy * W;
   const WinSums s = window_sums(x + pl * plane, y + pl * plane, H, W, qy, qx);
-  out[idx] = ssim_from_sums(s.Sx, s.Sxx, s.Sxy, ssim_y_stats(s.Sy, s.Syy));
+  out[idx] = ssim_from_sums<float>(s.Sx, s.Sxx, s.Sxy, ssim_y_stats<float>(s.Sy, s.Syy));
 }
 
 // gradient of sum_q g(q) * SSIM(q) wrt x(p) and y(p): gather over the (up to 9) windows containing p,
@@ -71,10 +71,10 @@ __device__ __forceinline__ void ssim_adjoint_gather(const float* __restrict__ X,
       if (g == 0.f) continue;
       const float m = my * (((qx == 0 && px == 1) || (qx == W - 1 && px == W - 2)) ? 2.f : 1.f);
       const WinSums s = window_sums(X, Y, H, W, qy, qx);
-      const SsimAdj ax = ssim_adjoint(s.Sx, s.Sxx, s.Sxy, ssim_y_stats(s.Sy, s.Syy), g);
+      const SsimAdjT<float> ax = ssim_adjoint<float>(s.Sx, s.Sxx, s.Sxy, ssim_y_stats<float>(s.Sy, s.Syy), g);
       gx += m * (ax.cA + ax.cB * xp + ax.cC * yp);
       if (WANT_Y) {
-        const SsimAdj ay = ssim_adjoint(s.Sy, s.Syy, s.Sxy, ssim_y_stats(s.Sx, s.Sxx), g);
+        const SsimAdjT<float> ay = ssim_adjoint<float>(s.Sy, s.Syy, s.Sxy, ssim_y_stats<float>(s.Sx, s.Sxx), g);
         gy += m * (ay.cA + ay.cB * yp + ay.cC * xp);
       }
     }
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(kT) reprojection_forward_kernel(const float* _
       acc += l1 * (1.f / 3.f);
     } else {
       const WinSums s = window_sums(X, Y, H, W, qy, qx);
-      acc += PPEA_W_SSIM * ssim_from_sums(s.Sx, s.Sxx, s.Sxy, ssim_y_stats(s.Sy, s.Syy)) + PPEA_W_L1 * l1;
+      acc += PPEA_W_SSIM * ssim_from_sums<float>(s.Sx, s.Sxx, s.Sxy, ssim_y_stats<float>(s.Sy, s.Syy)) + PPEA_W_L1 * l1;
     }
   }
   out[idx] = acc;
@@ -304,8 +304,8 @@ __device__ __forceinline__ GridPos grid_unnormalize(float gx, float gy, int W, i
   GridPos g;
   g.mx = (fx > 0.f && fx < wm1) ? 0.5f * wm1 : 0.f;
   g.my = (fy > 0.f && fy < hm1) ? 0.5f * hm1 : 0.f;
-  g.ix = fminf(wm1, fmaxf(fx, 0.f));
-  g.iy = fminf(hm1, fmaxf(fy, 0.f));
+  g.ix = clip_coord(fx, coord_max(W));
+  g.iy = clip_coord(fy, coord_max(H));
   return g;
 }
 
@@ -316,10 +316,10 @@ __global__ void __launch_bounds__(kT) warp_forward_kernel(const float* __restric
   if (idx >= oplane * B) return;
   const size_t b = idx / oplane, r = idx - b * oplane;
   const GridPos g = grid_unnormalize(grid[idx * 2], grid[idx * 2 + 1], W, H);
-  const Bilin bl = bilin_setup(g.ix, g.iy, W, H);
+  const Bilin bl = bilin_setup(g.ix, g.iy, W);
   for (int c = 0; c < C; ++c) {
     const float* S = src + (b * C + c) * plane;
-    out[(b * C + c) * oplane + r] = bilin_value(bl, __ldg(S + bl.o00), __ldg(S + bl.o01), __ldg(S + bl.o10), __ldg(S + bl.o11));
+    out[(b * C + c) * oplane + r] = bilin_value(bl, __ldg(S + bl.o00), __ldg(S + bl.o00 + 1), __ldg(S + bl.o00 + W), __ldg(S + bl.o00 + W + 1));
   }
 }
 
@@ -331,11 +331,11 @@ __global__ void __launch_bounds__(kT) warp_backward_kernel(const float* __restri
   if (idx >= oplane * B) return;
   const size_t b = idx / oplane, r = idx - b * oplane;
   const GridPos g = grid_unnormalize(grid[idx * 2], grid[idx * 2 + 1], W, H);
-  const Bilin bl = bilin_setup(g.ix, g.iy, W, H);
+  const Bilin bl = bilin_setup(g.ix, g.iy, W);
   float gx = 0.f, gy = 0.f;
   for (int c = 0; c < C; ++c) {
     const float* S = src + (b * C + c) * plane;
-    const float nw = __ldg(S + bl.o00), ne = __ldg(S + bl.o01), sw = __ldg(S + bl.o10), se = __ldg(S + bl.o11);
+    const float nw = __ldg(S + bl.o00), ne = __ldg(S + bl.o00 + 1), sw = __ldg(S + bl.o00 + W), se = __ldg(S + bl.o00 + W + 1);
     const float gv = go[(b * C + c) * oplane + r];
     gx += gv * bilin_ddx(bl, nw, ne, sw, se);
     gy += gv * bilin_ddy(bl, nw, ne, sw, se);

@@ -1,33 +1,30 @@
-// vsl_bwd.cu -- fused backward of the view-synthesis loss, all pyramid scales.
+// vsl_bwd.cu -- fused backward of the view-synthesis loss, all pyramid scales in one launch.
 //
-// Autograd of trainer.py:886-914 + 1050-1141 wrt every disp_s and (mono path)
-// the two poses, recomputing the forward instead of storing it: the only
-// forward products read back are the selection map `sel` (1 B/px) and the
-// reduced sums.  HBM traffic per pixel and scale: tgt 12 B (once per CTA, all
-// scales) + source gathers (24 B compulsory) + sel 1 B (+ cons_mask/mono_depth
-// on the multi path) in; grad_disp_s 4/4^s B out.
+// Autograd of trainer.py:886-914 + 1050-1141 wrt every disp_s and (mono path) the two poses,
+// recomputing the forward instead of storing it: the only forward products read back are the
+// selection map `sel` (1 B/px) and the reduced sums.  HBM traffic per pixel and scale: tgt 12 B
+// (once per CTA, all scales) + source gathers (24 B compulsory) + sel 1 B (+ cons_mask /
+// mono_depth on the multi path) in; grad_disp_s 4/4^s B out.
 //
-// A CTA owns a TW x TH tile of one image.
-//   phase 1  every cell of the tile + 2-pixel halo: depth -> backproject ->
-//            project -> bilinear gather of both sources into shared memory
-//            (halo cells hold the value of the reflected pixel, layers.py:238).
-//            For its own R tile pixels a thread keeps d warped / d (ix, iy)
+// A CTA owns a TW x TH tile of one image; all photometric arithmetic runs 2-wide
+// (FFMA2/FADD2/FMUL2, lanes = the two sources).
+//   phase 1  every cell of the tile + 2-pixel halo: depth -> projection -> bilinear gather of
+//            both sources into shared memory (halo cells hold the value of the reflected pixel,
+//            layers.py:238).  For its own R tile pixels a thread keeps d warped / d (u, v)
 //            (clip-masked, GridSampler.h clip_coordinates_set_grad) in registers.
-//   per source f:
-//   phase 2  every pixel q of the tile + 1-pixel halo whose loss was taken from
-//            source f (sel) and is unmasked: SSIM window sums -> adjoint
-//            coefficients (cA,cB,cC) per channel; zero elsewhere.
-//   phase 3  d L / d warped_f(p) = A + B x(p) + C y(p) + L1 term, where A,B,C
-//            are 3x3 box sums of the coefficients with the reflection
-//            multiplicities (a border window counts its mirrored tap twice),
-//            computed with a sliding three-row window in registers; then the
-//            chain through grid_sample, Project3D (layers.py:185-194) and
-//            BackprojectDepth (layers.py:164-166) to d L / d depth and the
-//            3x4 projection-matrix gradient partials.
-//   phase 4  consistency term (multi path), d depth / d disp (layers.py:21-22),
-//            adjoint of the bilinear upsample (trainer.py:886-887): direct
-//            accumulate at scale 0, float atomics or (deterministic) a
-//            full-res scratch + gather pass for coarser scales.
+//   per channel c:
+//   phase 2  every pixel q of the tile + 1-pixel halo: SSIM window sums -> adjoint coefficients
+//            (cA,cB,cC), weighted per lane by  g_r * mask(q) * [sel(q) == source]  (zero for the
+//            source whose loss was not taken at q).
+//   phase 3  d L / d warped_c(p) = A + B x(p) + C y(p) + L1 term, where A,B,C are 3x3 box sums of
+//            the coefficients with the reflection multiplicities (a border window counts its
+//            mirrored tap twice), computed with a sliding three-row window in registers; folded
+//            into d L / d (u, v) with the kept derivatives.
+//   phase 4  chain through Project3D (layers.py:185-194) and BackprojectDepth (layers.py:164-166)
+//            to d L / d depth and the pose partials; consistency term (multi path);
+//            d depth / d disp (layers.py:21-22); adjoint of the bilinear upsample
+//            (trainer.py:886-887): direct accumulate at scale 0, float atomics or
+//            (deterministic) a full-res scratch + gather pass for coarser scales.
 #include "vsl_common.cuh"
 
 namespace ppea {
@@ -36,40 +33,26 @@ template <int TW, int TH>
 struct BwdSmem {
   static constexpr int RW = TW + 4, RH = TH + 4, RP = RW * RH;   // value region (2-pixel halo)
   static constexpr int QW = TW + 2, QH = TH + 2, QP = QW * QH;   // coefficient region (1-pixel halo)
-  float y[3][RP];
-  float x[2][3][RP];
-  float cf[9][QP];      // [channel*3 + {A,B,C}]
-  float wl[QP];         // weight of the L1 term at q (0 unless q selected the current source)
-  float P[2][12];
-  float iK[9];
-  float red[24][4];
+  f2 y[3][RP];          // target, duplicated lanes
+  f2 x[3][RP];          // warped (source 0, source 1)
+  f2 cf[3][QP];         // cA, cB, cC of the current channel
+  f2 wq[QP];            // g_r * mask(q) * [sel(q) == lane]
+  f2 G[12];             // per-source geometry (vsl_math.cuh Geom), lanes = sources
+  float red[24][8];
 };
 
-struct WarpDeriv {
-  float dx[3], dy[3];   // d warped_c / d u, d warped_c / d v (already multiplied by the clip masks)
-};
-
-// depth -> cam point -> projection + gather for one pixel and one source
-template <bool WANT_DERIV>
-__device__ __forceinline__ void warp_pixel(const float* __restrict__ P, const float* cam, float eps, float wm1, float hm1,
-                                           int W, int H, const float* __restrict__ src_b, size_t plane, float* val,
-                                           WarpDeriv* der) {
-  const Proj pr = project_point(P, cam, eps, wm1, hm1);
-  const Bilin bl = bilin_setup(pr.ix, pr.iy, W, H);
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const float* S = src_b + c * plane;
-    const float nw = __ldg(S + bl.o00), ne = __ldg(S + bl.o01), sw = __ldg(S + bl.o10), se = __ldg(S + bl.o11);
-    val[c] = bilin_value(bl, nw, ne, sw, se);
-    if (WANT_DERIV) {
-      der->dx[c] = bilin_ddx(bl, nw, ne, sw, se) * pr.mx;
-      der->dy[c] = bilin_ddy(bl, nw, ne, sw, se) * pr.my;
-    }
-  }
+// projection of one pixel into both sources
+__device__ __forceinline__ ProjT<f2> project_pixel(const f2* __restrict__ G, float dep, int px, int py, float eps, float wmax,
+                                                   float hmax, f2 (&A)[3]) {
+  const f2 fx = dup2(int_to_float(px)), fy = dup2(int_to_float(py));
+  A[0] = vfma(G[1], fy, vfma(G[0], fx, G[2]));
+  A[1] = vfma(G[4], fy, vfma(G[3], fx, G[5]));
+  A[2] = vfma(G[7], fy, vfma(G[6], fx, G[8]));
+  return project_fast(dep, A[0], A[1], A[2], G[9], G[10], G[11], eps, wmax, hmax);
 }
 
 template <int TW, int TH, int NT, bool POSE>
-__global__ void __launch_bounds__(NT) vsl_backward_kernel(const __grid_constant__ VslArgs a) {
+__global__ void __launch_bounds__(NT, (NT >= 256 ? 2 : 4)) vsl_backward_kernel(const __grid_constant__ VslArgs a) {
   using Smem = BwdSmem<TW, TH>;
   constexpr int RW = Smem::RW, RP = Smem::RP, QW = Smem::QW, QP = Smem::QP;
   constexpr int R = (TW * TH) / NT;
@@ -92,17 +75,9 @@ __global__ void __launch_bounds__(NT) vsl_backward_kernel(const __grid_constant_
   const float l1w = no_ssim ? (1.f / 3.f) : PPEA_W_L1;
 
   if (tid < 24) {
-    const int f = tid / 12, e = tid % 12, i = e / 4, j = e % 4;
-    const float* K = a.K + b * 16;
-    const float* T = a.T[f] + b * 16;
-    float acc = mul_rn(K[i * 4 + 0], T[0 * 4 + j]);
-    acc = add_rn(acc, mul_rn(K[i * 4 + 1], T[1 * 4 + j]));
-    acc = add_rn(acc, mul_rn(K[i * 4 + 2], T[2 * 4 + j]));
-    acc = add_rn(acc, mul_rn(K[i * 4 + 3], T[3 * 4 + j]));
-    sm.P[f][e] = acc;
-  } else if (tid >= 32 && tid < 41) {
-    const int e = tid - 32;
-    sm.iK[e] = a.inv_K[b * 16 + (e / 3) * 4 + (e % 3)];
+    const int f = tid / 12, e = tid % 12;
+    const float v = geom_entry(a.K + b * 16, a.T[f] + b * 16, a.inv_K + b * 16, e);
+    (f ? sm.G[e].y : sm.G[e].x) = v;
   }
 
   const float* tgt_b = a.tgt + (size_t)b * 3 * plane;
@@ -114,56 +89,74 @@ __global__ void __launch_bounds__(NT) vsl_backward_kernel(const __grid_constant_
     const int py = reflect_index(y0 - 2 + i, H), px = reflect_index(x0 - 2 + j, W);
     const size_t o = (size_t)py * W + px;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) sm.y[c][idx] = __ldg(tgt_b + c * plane + o);
+    for (int c = 0; c < 3; ++c) sm.y[c][idx] = dup2(__ldg(tgt_b + c * plane + o));
   }
   __syncthreads();
 
+  const float wmax = coord_max(W), hmax = coord_max(H);
   const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
-  float iK[9];
-#pragma unroll
-  for (int e = 0; e < 9; ++e) iK[e] = sm.iK[e];
   const int col = tid % TW;
   const int row0 = (tid / TW) * R;
   const int gx_own = x0 + col;
+  const int px_own = reflect_index(gx_own, W);                   // clamp for partial tiles
   const float one_minus_aug = (multi && (a.flags & PPEA_F_MATCH_AUG)) ? 1.f - a.aug_mask[b] : 1.f;
   // reflection multiplicities of the taps left/right of this thread's column
-  const float mL = (gx_own == 1) ? 2.f : 1.f, mR = (gx_own == W - 2) ? 2.f : 1.f;
+  const f2 mL = dup2((gx_own == 1) ? 2.f : 1.f), mR = dup2((gx_own == W - 2) ? 2.f : 1.f);
 
-  float gp[POSE ? 24 : 1];
+  // pose partials: Sw[r] = sum gc_r*depth, Swy[r] = sum gc_r*depth*y, Sg[r] = sum gc_r (x is this thread's constant column)
+  f2 Sw[POSE ? 3 : 1], Swy[POSE ? 3 : 1], Sg[POSE ? 3 : 1];
 #pragma unroll
-  for (int e = 0; e < (POSE ? 24 : 1); ++e) gp[e] = 0.f;
+  for (int e = 0; e < (POSE ? 3 : 1); ++e) Sw[e] = Swy[e] = Sg[e] = dup2(0.f);
 
 #pragma unroll 1
   for (int s = 0; s < a.S; ++s) {
     const ScaleArgs& sc = a.sc[s];
     const float* disp_b = sc.disp + (size_t)b * sc.hs * sc.ws;
+    const bool same_res = (sc.hs == H && sc.ws == W);
     const float* srow = a.sums + (size_t)s * sums_stride(a.B);
     const ScaleGrads sg = scale_grads(a, s);
     const float g_r = sg.reproj / (srow[1] + 1e-7f);           // d reproj_s / d (r*mask)(q)   trainer.py:1114
     const float g_c = sg.cons / ((float)a.B * (float)plane);   // d cons_s / d (|depth-mono|*(1-mask))(q)
 
     float dep[R];
-    WarpDeriv der[R][2];
-    float gdep[R];
+    f2 ddx[R][3], ddy[R][3];     // d warped_c / d u, d warped_c / d v  (lanes = sources)
+    f2 gu[R], gv[R];
 
-    // ---- phase 1a: own tile pixels (keeps derivatives in registers)
+    auto depth_at = [&](int py, int px) {
+      float dup;
+      if (same_res) {
+        dup = __ldg(disp_b + (size_t)py * W + px);
+      } else {
+        const UpCoef cy = up_coef(py, sc.hs, sc.up_sy), cx = up_coef(px, sc.ws, sc.up_sx);
+        dup = up_sample(disp_b, sc.ws, cy, cx);
+      }
+      return depth_from_disp(dup, a.disp_lo, a.disp_range);
+    };
+
+    // ---- phase 1a: own tile pixels (keeps the derivatives in registers)
 #pragma unroll
     for (int k = 0; k < R; ++k) {
-      const int py = reflect_index(y0 + row0 + k, H), px = reflect_index(gx_own, W);   // clamp for partial tiles
-      const UpCoef cy = up_coef(py, sc.hs, sc.up_sy), cx = up_coef(px, sc.ws, sc.up_sx);
-      dep[k] = depth_from_disp(up_sample(disp_b, sc.ws, cy, cx), a.disp_lo, a.disp_range);
-      gdep[k] = 0.f;
-      float ray[3], cam[3];
-      pixel_ray(iK, (float)px, (float)py, ray);
-#pragma unroll
-      for (int e = 0; e < 3; ++e) cam[e] = mul_rn(dep[k], ray[e]);
+      const int py = reflect_index(y0 + row0 + k, H);
+      dep[k] = depth_at(py, px_own);
+      gu[k] = gv[k] = dup2(0.f);
+      f2 A[3];
+      const ProjT<f2> pr = project_pixel(sm.G, dep[k], px_own, py, a.eps, wmax, hmax, A);
+      const Bilin b0 = bilin_setup(pr.ix.x, pr.iy.x, W), b1 = bilin_setup(pr.ix.y, pr.iy.y, W);
+      const f2 wnw = mk2(b0.wnw, b1.wnw), wne = mk2(b0.wne, b1.wne), wsw = mk2(b0.wsw, b1.wsw), wse = mk2(b0.wse, b1.wse);
+      const f2 tx = mk2(b0.tx, b1.tx), ty = mk2(b0.ty, b1.ty);
+      const f2 ex = vsub(dup2(1.f), tx), ey = vsub(dup2(1.f), ty);
+      const f2 mx = mk2(clip_mask(pr.u.x, wm1), clip_mask(pr.u.y, wm1)), my = mk2(clip_mask(pr.v.x, hm1), clip_mask(pr.v.y, hm1));
+      const f2 eym = vmul(ey, mx), tym = vmul(ty, mx), exm = vmul(ex, my), txm = vmul(tx, my);
       const int ridx = (row0 + k + 2) * RW + col + 2;
 #pragma unroll
-      for (int f = 0; f < 2; ++f) {
-        float val[3];
-        warp_pixel<true>(sm.P[f], cam, a.eps, wm1, hm1, W, H, src_b[f], plane, val, &der[k][f]);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) sm.x[f][c][ridx] = val[c];
+      for (int c = 0; c < 3; ++c) {
+        const float* S0 = src_b[0] + c * plane + b0.o00;
+        const float* S1 = src_b[1] + c * plane + b1.o00;
+        const f2 nw = mk2(__ldg(S0), __ldg(S1)), ne = mk2(__ldg(S0 + 1), __ldg(S1 + 1));
+        const f2 sw = mk2(__ldg(S0 + W), __ldg(S1 + W)), se = mk2(__ldg(S0 + W + 1), __ldg(S1 + W + 1));
+        sm.x[c][ridx] = vfma(se, wse, vfma(sw, wsw, vfma(ne, wne, vmul(nw, wnw))));
+        ddx[k][c] = vfma(vsub(se, sw), tym, vmul(vsub(ne, nw), eym));      // bilin_ddx * clip mask
+        ddy[k][c] = vfma(vsub(se, ne), txm, vmul(vsub(sw, nw), exm));      // bilin_ddy * clip mask
       }
     }
     // ---- phase 1b: halo ring (top 2 rows, bottom 2 rows, then left/right 2 columns of the tile rows)
@@ -183,157 +176,144 @@ __global__ void __launch_bounds__(NT) vsl_backward_kernel(const __grid_constant_
         j = jj < 2 ? jj : TW + jj;
       }
       const int py = reflect_index(y0 - 2 + i, H), px = reflect_index(x0 - 2 + j, W);
-      const UpCoef cy = up_coef(py, sc.hs, sc.up_sy), cx = up_coef(px, sc.ws, sc.up_sx);
-      const float d = depth_from_disp(up_sample(disp_b, sc.ws, cy, cx), a.disp_lo, a.disp_range);
-      float ray[3], cam[3];
-      pixel_ray(iK, (float)px, (float)py, ray);
-#pragma unroll
-      for (int e = 0; e < 3; ++e) cam[e] = mul_rn(d, ray[e]);
+      const float d = depth_at(py, px);
+      f2 A[3];
+      const ProjT<f2> pr = project_pixel(sm.G, d, px, py, a.eps, wmax, hmax, A);
+      const Bilin b0 = bilin_setup(pr.ix.x, pr.iy.x, W), b1 = bilin_setup(pr.ix.y, pr.iy.y, W);
+      const f2 wnw = mk2(b0.wnw, b1.wnw), wne = mk2(b0.wne, b1.wne), wsw = mk2(b0.wsw, b1.wsw), wse = mk2(b0.wse, b1.wse);
       const int ridx = i * RW + j;
 #pragma unroll
-      for (int f = 0; f < 2; ++f) {
-        float val[3];
-        warp_pixel<false>(sm.P[f], cam, a.eps, wm1, hm1, W, H, src_b[f], plane, val, nullptr);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) sm.x[f][c][ridx] = val[c];
+      for (int c = 0; c < 3; ++c) {
+        const float* S0 = src_b[0] + c * plane + b0.o00;
+        const float* S1 = src_b[1] + c * plane + b1.o00;
+        const f2 nw = mk2(__ldg(S0), __ldg(S1)), ne = mk2(__ldg(S0 + 1), __ldg(S1 + 1));
+        const f2 sw = mk2(__ldg(S0 + W), __ldg(S1 + W)), se = mk2(__ldg(S0 + W + 1), __ldg(S1 + W + 1));
+        sm.x[c][ridx] = vfma(se, wse, vfma(sw, wsw, vfma(ne, wne, vmul(nw, wnw))));
       }
+    }
+    // ---- per-q weights  g_r * mask(q) * [sel(q) == lane]   (zero outside the image)
+    for (int qi = tid; qi < QP; qi += NT) {
+      const int i = qi / QW, j = qi - i * QW;
+      const int qy = y0 - 1 + i, qx = x0 - 1 + j;
+      f2 w = dup2(0.f);
+      if (qy >= 0 && qy < H && qx >= 0 && qx < W) {
+        const size_t o = (size_t)b * plane + (size_t)qy * W + qx;
+        const unsigned bits = sc.sel[o];
+        float mask;
+        if (multi) {
+          mask = (a.flags & PPEA_F_MOTION_MASK) ? a.cons_mask[o] : 1.f;
+          mask *= one_minus_aug;
+        } else {
+          mask = (bits & PPEA_SEL_AUTOMASK) ? 1.f : 0.f;
+        }
+        const float wv = g_r * mask;
+        const unsigned src = bits & PPEA_SEL_SRC_MASK;
+        w = mk2(src == 0u ? wv : 0.f, src == 1u ? wv : 0.f);
+      }
+      sm.wq[qi] = w;
     }
     __syncthreads();
 
 #pragma unroll
-    for (int f = 0; f < 2; ++f) {   // unrolled: der[k][f] / gp[f*12+e] must be statically indexed registers
+    for (int c = 0; c < 3; ++c) {
       // ---- phase 2: adjoint coefficients of the SSIM windows centred in the tile + 1 halo
-      for (int qi = tid; qi < QP; qi += NT) {
-        const int i = qi / QW, j = qi - i * QW;
-        const int qy = y0 - 1 + i, qx = x0 - 1 + j;
-        float wq = 0.f;
-        if (qy >= 0 && qy < H && qx >= 0 && qx < W) {
-          const size_t o = (size_t)b * plane + (size_t)qy * W + qx;
-          const unsigned bits = sc.sel[o];
-          if ((int)(bits & PPEA_SEL_SRC_MASK) == f) {
-            float mask;
-            if (multi) {
-              mask = (a.flags & PPEA_F_MOTION_MASK) ? a.cons_mask[o] : 1.f;
-              mask *= one_minus_aug;
-            } else {
-              mask = (bits & PPEA_SEL_AUTOMASK) ? 1.f : 0.f;
-            }
-            wq = g_r * mask;
-          }
-        }
-        sm.wl[qi] = wq;
-        if (wq != 0.f && !no_ssim) {
-          const float gs = wq * PPEA_W_SSIM;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const float* xp = &sm.x[f][c][i * RW + j];
-            const float* yp = &sm.y[c][i * RW + j];
-            float Sx = 0.f, Sxx = 0.f, Sxy = 0.f, Sy = 0.f, Syy = 0.f;
+      if (!no_ssim) {
+        for (int qi = tid; qi < QP; qi += NT) {
+          const int i = qi / QW, j = qi - i * QW;
+          const f2 w = sm.wq[qi];
+          SsimAdjT<f2> ad;
+          ad.cA = ad.cB = ad.cC = dup2(0.f);
+          if (w.x != 0.f || w.y != 0.f) {
+            const f2* xp = &sm.x[c][i * RW + j];
+            const f2* yp = &sm.y[c][i * RW + j];
+            f2 hx[3], hxx[3], hxy[3], hy[3], hyy[3];
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy) {
-              const float xa = xp[dy * RW], xb = xp[dy * RW + 1], xc = xp[dy * RW + 2];
-              const float ya = yp[dy * RW], yb = yp[dy * RW + 1], yc = yp[dy * RW + 2];
-              // same association as the forward's sliding window: horizontal triples, then rows
-              const float hx = xa + xb + xc, hy = ya + yb + yc;
-              const float hxx = xa * xa + xb * xb + xc * xc, hyy = ya * ya + yb * yb + yc * yc;
-              const float hxy = xa * ya + xb * yb + xc * yc;
-              Sx = dy ? Sx + hx : hx;
-              Sy = dy ? Sy + hy : hy;
-              Sxx = dy ? Sxx + hxx : hxx;
-              Syy = dy ? Syy + hyy : hyy;
-              Sxy = dy ? Sxy + hxy : hxy;
+              const f2 xa = xp[dy * RW], xb = xp[dy * RW + 1], xc = xp[dy * RW + 2];
+              const f2 ya = yp[dy * RW], yb = yp[dy * RW + 1], yc = yp[dy * RW + 2];
+              row_sums_y<f2>(ya, yb, yc, hy[dy], hyy[dy]);
+              row_sums_x<f2>(xa, xb, xc, ya, yb, yc, hx[dy], hxx[dy], hxy[dy]);
             }
-            const SsimAdj ad = ssim_adjoint(Sx, Sxx, Sxy, ssim_y_stats(Sy, Syy), gs);
-            sm.cf[c * 3 + 0][qi] = ad.cA;
-            sm.cf[c * 3 + 1][qi] = ad.cB;
-            sm.cf[c * 3 + 2][qi] = ad.cC;
+            const SsimYT<f2> yst = ssim_y_stats<f2>(sum3(hy[0], hy[1], hy[2]), sum3(hyy[0], hyy[1], hyy[2]));
+            ad = ssim_adjoint<f2>(sum3(hx[0], hx[1], hx[2]), sum3(hxx[0], hxx[1], hxx[2]), sum3(hxy[0], hxy[1], hxy[2]), yst,
+                                  vmul(w, dup2(PPEA_W_SSIM)));
           }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 9; ++e) sm.cf[e][qi] = 0.f;
+          sm.cf[0][qi] = ad.cA;
+          sm.cf[1][qi] = ad.cB;
+          sm.cf[2][qi] = ad.cC;
         }
       }
       __syncthreads();
 
-      // ---- phase 3: box-sum the coefficients (sliding window down this thread's column), chain rule
+      // ---- phase 3: box-sum the coefficients (sliding window down this thread's column), fold into d L / d (u, v)
       {
-        float h[3][9];
+        f2 h[3][3];
 #pragma unroll
         for (int i = 0; i < R + 2; ++i) {
           const int sl = i % 3;
-          const int qrow = (row0 + i) * QW + col;
+          if (!no_ssim) {
+            const int qrow = (row0 + i) * QW + col;
 #pragma unroll
-          for (int e = 0; e < 9; ++e) {
-            const float* cp = &sm.cf[e][qrow];
-            h[sl][e] = fmaf(mL, cp[0], fmaf(mR, cp[2], cp[1]));
+            for (int e = 0; e < 3; ++e) {
+              const f2* cp = &sm.cf[e][qrow];
+              h[sl][e] = vfma(mL, cp[0], vfma(mR, cp[2], cp[1]));
+            }
           }
           if (i >= 2) {
             const int k = i - 2;
             const int gy = y0 + row0 + k;
-            const float mU = (gy == 1) ? 2.f : 1.f, mD = (gy == H - 2) ? 2.f : 1.f;
-            const int su = (i - 2) % 3, smid = (i - 1) % 3;
             const int ridx = (row0 + k + 2) * RW + col + 2;
-            const float wl = sm.wl[(row0 + k + 1) * QW + col + 1];
-            float gu = 0.f, gv = 0.f;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              const float A = fmaf(mU, h[su][c * 3 + 0], fmaf(mD, h[sl][c * 3 + 0], h[smid][c * 3 + 0]));
-              const float Bc = fmaf(mU, h[su][c * 3 + 1], fmaf(mD, h[sl][c * 3 + 1], h[smid][c * 3 + 1]));
-              const float Cc = fmaf(mU, h[su][c * 3 + 2], fmaf(mD, h[sl][c * 3 + 2], h[smid][c * 3 + 2]));
-              const float xv = sm.x[f][c][ridx], yv = sm.y[c][ridx];
-              const float d = yv - xv;
-              const float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
-              const float G = fmaf(Bc, xv, fmaf(Cc, yv, A)) - wl * l1w * sgn;   // d L / d warped_{f,c}(p)
-              gu = fmaf(G, der[k][f].dx[c], gu);
-              gv = fmaf(G, der[k][f].dy[c], gv);
+            const f2 xv = sm.x[c][ridx], yv = sm.y[c][ridx];
+            const f2 wl = sm.wq[(row0 + k + 1) * QW + col + 1];
+            const f2 d = vsub(yv, xv);
+            // L1 term:  -w * l1w * sign(y - x)
+            f2 G = mk2(-wl.x * l1w * sign_of(d.x), -wl.y * l1w * sign_of(d.y));
+            if (!no_ssim) {
+              const f2 mU = dup2((gy == 1) ? 2.f : 1.f), mD = dup2((gy == H - 2) ? 2.f : 1.f);
+              const int su = (i - 2) % 3, smid = (i - 1) % 3;
+              const f2 A = vfma(mU, h[su][0], vfma(mD, h[sl][0], h[smid][0]));
+              const f2 Bc = vfma(mU, h[su][1], vfma(mD, h[sl][1], h[smid][1]));
+              const f2 Cc = vfma(mU, h[su][2], vfma(mD, h[sl][2], h[smid][2]));
+              G = vadd(G, vfma(Bc, xv, vfma(Cc, yv, A)));               // d L / d warped_c(p), both sources
             }
-            if (gy < H && gx_own < W && (gu != 0.f || gv != 0.f)) {
-              // Project3D / BackprojectDepth adjoint (recomputes the cheap projection)
-              float ray[3], cam[3];
-              pixel_ray(iK, (float)gx_own, (float)gy, ray);
-#pragma unroll
-              for (int e = 0; e < 3; ++e) cam[e] = mul_rn(dep[k], ray[e]);
-              const float* P = sm.P[f];
-              const Proj pr = project_point(P, cam, a.eps, wm1, hm1);
-              const float inv_z = 1.f / pr.z;
-              const float gc0 = gu * inv_z, gc1 = gv * inv_z, gc2 = -(gu * pr.u + gv * pr.v) * inv_z;
-              float gd = 0.f;
-#pragma unroll
-              for (int e = 0; e < 3; ++e) gd = fmaf(fmaf(P[e], gc0, fmaf(P[4 + e], gc1, P[8 + e] * gc2)), ray[e], gd);
-              gdep[k] += gd;
-              if (POSE) {
-#pragma unroll
-                for (int e = 0; e < 3; ++e) {
-                  gp[f * 12 + 0 + e] = fmaf(gc0, cam[e], gp[f * 12 + 0 + e]);
-                  gp[f * 12 + 4 + e] = fmaf(gc1, cam[e], gp[f * 12 + 4 + e]);
-                  gp[f * 12 + 8 + e] = fmaf(gc2, cam[e], gp[f * 12 + 8 + e]);
-                }
-                gp[f * 12 + 3] += gc0;
-                gp[f * 12 + 7] += gc1;
-                gp[f * 12 + 11] += gc2;
-              }
-            }
+            gu[k] = vfma(G, ddx[k][c], gu[k]);
+            gv[k] = vfma(G, ddy[k][c], gv[k]);
           }
         }
       }
-      __syncthreads();   // coefficient planes are rewritten by the next source / x planes by the next scale
+      __syncthreads();   // coefficient planes are rewritten by the next channel / x planes by the next scale
     }
 
-    // ---- phase 4: consistency term, depth -> disp, adjoint of the bilinear upsample
+    // ---- phase 4: projection adjoint, consistency term, depth -> disp, adjoint of the bilinear upsample
     float* gd_b = sc.grad_disp + (size_t)b * sc.hs * sc.ws;
-    const bool same_res = (sc.hs == H && sc.ws == W);
 #pragma unroll
     for (int k = 0; k < R; ++k) {
       const int gy = y0 + row0 + k;
       if (gy < H && gx_own < W) {
         const size_t o = (size_t)b * plane + (size_t)gy * W + gx_own;
-        float g = gdep[k];
+        f2 A[3];
+        const ProjT<f2> pr = project_pixel(sm.G, dep[k], gx_own, gy, a.eps, wmax, hmax, A);
+        const f2 gc0 = vmul(gu[k], pr.rz), gc1 = vmul(gv[k], pr.rz);
+        const f2 gc2 = vneg(vmul(vfma(gu[k], pr.u, vmul(gv[k], pr.v)), pr.rz));
+        const f2 gd2 = vfma(gc2, A[2], vfma(gc1, A[1], vmul(gc0, A[0])));
+        float g = gd2.x + gd2.y;
+        if (POSE) {
+          const f2 dk = dup2(dep[k]), fy = dup2(int_to_float(gy));
+          const f2 w0 = vmul(gc0, dk), w1 = vmul(gc1, dk), w2 = vmul(gc2, dk);
+          Sw[0] = vadd(Sw[0], w0);
+          Sw[1] = vadd(Sw[1], w1);
+          Sw[2] = vadd(Sw[2], w2);
+          Swy[0] = vfma(w0, fy, Swy[0]);
+          Swy[1] = vfma(w1, fy, Swy[1]);
+          Swy[2] = vfma(w2, fy, Swy[2]);
+          Sg[0] = vadd(Sg[0], gc0);
+          Sg[1] = vadd(Sg[1], gc1);
+          Sg[2] = vadd(Sg[2], gc2);
+        }
         if (multi) {
           float mask = (a.flags & PPEA_F_MOTION_MASK) ? a.cons_mask[o] : 1.f;
           mask *= one_minus_aug;
-          const float d = dep[k] - sc.mono_depth[o];
-          const float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
-          g = fmaf(g_c * sgn, 1.f - mask, g);
+          g = fmaf(g_c * sign_of(dep[k] - sc.mono_depth[o]), 1.f - mask, g);
         }
         const float g_dup = g * ddepth_ddisp(dep[k], a.disp_range);
         if (same_res) {
@@ -352,11 +332,25 @@ __global__ void __launch_bounds__(NT) vsl_backward_kernel(const __grid_constant_
   }
 
   if (POSE) {
+    // per source f and row r of dL/dP: (sum gc_r*depth*x, sum gc_r*depth*y, sum gc_r*depth, sum gc_r)
+    const float fx = int_to_float(px_own);
+    float v[24];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      v[0 * 12 + r * 4 + 0] = Sw[r].x * fx;
+      v[0 * 12 + r * 4 + 1] = Swy[r].x;
+      v[0 * 12 + r * 4 + 2] = Sw[r].x;
+      v[0 * 12 + r * 4 + 3] = Sg[r].x;
+      v[1 * 12 + r * 4 + 0] = Sw[r].y * fx;
+      v[1 * 12 + r * 4 + 1] = Swy[r].y;
+      v[1 * 12 + r * 4 + 2] = Sw[r].y;
+      v[1 * 12 + r * 4 + 3] = Sg[r].y;
+    }
     const int lane = tid & 31, wid = tid >> 5;
 #pragma unroll
     for (int e = 0; e < 24; ++e) {
-      const float v = warp_sum(gp[e]);
-      if (lane == 0) sm.red[e][wid] = v;
+      const float t = warp_sum(v[e]);
+      if (lane == 0) sm.red[e][wid] = t;
     }
     __syncthreads();
     if (tid < 24) {
@@ -370,7 +364,7 @@ __global__ void __launch_bounds__(NT) vsl_backward_kernel(const __grid_constant_
 cudaError_t launch_vsl_backward(const VslArgs& a, cudaStream_t stream) {
   using Smem = BwdSmem<kBwdTileW, kBwdTileH>;
   static_assert(sizeof(Smem) <= 227 * 1024, "shared memory tile too large");
-  static_assert(kBwdThreads / 32 <= 4, "red[] rows hold 4 warps");
+  static_assert(kBwdThreads / 32 <= 8, "red[] rows hold 8 warps");
   const int nblk = a.B * a.tiles_x * a.tiles_y;
   cudaError_t e;
   if (a.flags & PPEA_F_GRAD_POSE) {
@@ -440,16 +434,31 @@ cudaError_t launch_upsample_gather(const VslArgs& a, cudaStream_t stream) {
 // image, then d L / d T_f = K[:3,:]^T @ dL/dP_f  (autograd of layers.py:185).
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(32) pose_finish_kernel(const __grid_constant__ VslArgs a, int tiles) {
-  __shared__ double gP[24];
+  __shared__ double Q[24];    // [f][r][(x, y, 1) moments of gc_r*depth, sum gc_r]
+  __shared__ double gP[24];   // dL/dP_f, row-major 3x4
   const int b = blockIdx.x, tid = threadIdx.x;
   if (tid < 24) {
     double t = 0;
     const float* p = a.pose_partials + (size_t)b * tiles * 24 + tid;
     for (int i = 0; i < tiles; ++i) t += (double)p[(size_t)i * 24];
-    gP[tid] = t;
+    Q[tid] = t;
   }
   __syncwarp();
   const float* K = a.K + b * 16;
+  const float* iK = a.inv_K + b * 16;
+  if (tid < 24) {
+    // cam = depth * inv_K[:3,:3] (x,y,1)  =>  dL/dP[r][j] = sum_k Q[r][k] inv_K[j][k];  dL/dP[r][3] = sum gc_r
+    const int f = tid / 12, e = tid % 12, r = e / 4, j = e % 4;
+    double t;
+    if (j == 3) {
+      t = Q[f * 12 + r * 4 + 3];
+    } else {
+      t = 0;
+      for (int k = 0; k < 3; ++k) t += Q[f * 12 + r * 4 + k] * (double)iK[j * 4 + k];
+    }
+    gP[tid] = t;
+  }
+  __syncwarp();
   {
     const int f = tid / 16, e = tid % 16, i = e / 4, j = e % 4;
     // (K3^T gP)[i][j] = sum_r K[r][i] * gP[r][j], r = 0..2

@@ -54,7 +54,7 @@ struct VslArgs {
 };
 
 constexpr int kFwdTileW = 32;
-constexpr int kFwdTileH = 32;
+constexpr int kFwdTileH = 16;
 constexpr int kFwdThreads = 128;
 constexpr int kBwdTileW = 32;
 constexpr int kBwdTileH = 16;

@@ -1,18 +1,20 @@
-// vsl_fwd.cu -- fused forward of one pyramid scale of the view-synthesis loss.
+// vsl_fwd.cu -- fused forward of the view-synthesis loss, all pyramid scales in one launch.
 //
-// One launch replaces, for one scale, trainer.py:886-914 (upsample, depth,
-// backproject, project, grid_sample for both sources) and trainer.py:1050-1141
-// (SSIM+L1 photometric loss of the warped and of the un-warped sources, min over
-// sources, selec_reproj, identity automask / multi-frame mask, masked sums).
+// One launch replaces, for every scale, trainer.py:886-914 (upsample, depth, backproject,
+// project, grid_sample for both sources) and trainer.py:1050-1141 (SSIM+L1 photometric loss of
+// the warped and of the un-warped sources, min over sources, selec_reproj, identity automask /
+// multi-frame mask, masked sums).
 //
-// A CTA owns a TW x TH tile of one image.  Shared memory holds the tile plus a
-// one-pixel reflection halo of: the target (3 planes) and both sources' colour
-// (2 x 3 planes) -- first the un-warped sources (identity loss), then, in place,
-// the warped ones.  Every 3x3 SSIM window is then assembled from shared memory
-// by a thread that walks R consecutive rows of one column with a three-row
-// sliding window of horizontal sums held in registers.
-// HBM traffic per pixel: tgt 12 B + sources 24 B (+ gathers, L1/L2-resident) +
-// noise 4 B + disp 4/4^s B in; depth 4 B + loss 4 B + sel 1 B out.
+// A CTA owns a TW x TH tile of one image.  Shared memory holds the tile plus a one-pixel
+// reflection halo of the target (3 planes, each value duplicated into both lanes of an f2) and
+// of the two sources (3 planes of f2 = (source -1, source +1)): first the un-warped sources
+// (identity loss, once for all scales), then, per scale, the warped ones.  All photometric
+// arithmetic runs 2-wide (FFMA2/FADD2/FMUL2, lanes = sources).  Every 3x3 SSIM window is
+// assembled by a thread that walks R consecutive rows of one column with a three-row sliding
+// window of horizontal sums held in registers.
+// HBM traffic per pixel: tgt 12 B + sources 24 B once per CTA, per scale the gathers (24 B
+// compulsory, L1/L2-resident after the first scale) + noise 4 B + disp 4/4^s B in; depth 4 B +
+// sel 1 B (+ loss 4 B on request) out.
 #include "vsl_common.cuh"
 
 namespace ppea {
@@ -22,65 +24,53 @@ struct FwdSmem {
   static constexpr int EW = TW + 2;
   static constexpr int EH = TH + 2;
   static constexpr int PLANE = EW * EH;
-  float y[3][PLANE];
-  float x[2][3][PLANE];
-  float P[2][12];
-  float iK[9];
-  float red[3][32];
+  f2 y[3][PLANE];      // target, duplicated lanes
+  f2 x[3][PLANE];      // (source 0, source 1): un-warped, then warped
+  f2 G[12];            // per-source geometry M[0..8], t[0..2] (vsl_math.cuh Geom), lanes = sources
+  float red[3][8];
 };
 
-// Photometric loss 0.85*mean_c SSIM + 0.15*mean_c |y-x| (trainer.py:995-1007) of both
-// x-planes against y for the R pixels (rows row0..row0+R-1, column col) of this thread.
+// Photometric loss 0.85*mean_c SSIM + 0.15*mean_c |y-x| (trainer.py:995-1007) of both sources
+// against the target for the R pixels (rows row0..row0+R-1, column col) of this thread.
 template <int R, int EW, int PLANE, bool WITH_CSUM>
-__device__ __forceinline__ void photometric_pass(const float* __restrict__ xs, const float* __restrict__ ys, int row0,
-                                                 int col, bool no_ssim, float (&acc)[2][R], float (&cs)[2][R]) {
+__device__ __forceinline__ void photometric_pass(const f2* __restrict__ xs, const f2* __restrict__ ys, int row0, int col,
+                                                 bool no_ssim, f2 (&acc)[R], f2 (&cs)[R]) {
 #pragma unroll
-  for (int f = 0; f < 2; ++f)
-#pragma unroll
-    for (int k = 0; k < R; ++k) {
-      acc[f][k] = 0.f;
-      cs[f][k] = 0.f;
-    }
+  for (int k = 0; k < R; ++k) {
+    acc[k] = dup2(0.f);
+    cs[k] = dup2(0.f);
+  }
   const float w_l1 = no_ssim ? (1.f / 3.f) : PPEA_W_L1;
+  const f2 w_ssim = dup2(PPEA_W_SSIM);
 #pragma unroll 1
   for (int c = 0; c < 3; ++c) {
-    const float* yp = ys + c * PLANE + row0 * EW + col;
-    const float* xp0 = xs + c * PLANE + row0 * EW + col;
-    const float* xp1 = xs + (3 + c) * PLANE + row0 * EW + col;
-    float hy[3], hyy[3], hx[2][3], hxx[2][3], hxy[2][3];
+    const f2* yp = ys + c * PLANE + row0 * EW + col;
+    const f2* xp = xs + c * PLANE + row0 * EW + col;
+    f2 hy[3], hyy[3], hx[3], hxx[3], hxy[3];
 #pragma unroll
     for (int i = 0; i < R + 2; ++i) {
       const int s = i % 3;
-      const float y0 = yp[i * EW], y1 = yp[i * EW + 1], y2 = yp[i * EW + 2];
-      hy[s] = y0 + y1 + y2;
-      hyy[s] = y0 * y0 + y1 * y1 + y2 * y2;
-#pragma unroll
-      for (int f = 0; f < 2; ++f) {
-        const float* xp = f ? xp1 : xp0;
-        const float x0 = xp[i * EW], x1 = xp[i * EW + 1], x2 = xp[i * EW + 2];
-        hx[f][s] = x0 + x1 + x2;
-        hxx[f][s] = x0 * x0 + x1 * x1 + x2 * x2;
-        hxy[f][s] = x0 * y0 + x1 * y1 + x2 * y2;
-        if (i >= 1 && i <= R) {
-          acc[f][i - 1] += w_l1 * fabsf(y1 - x1);
-          if (WITH_CSUM) cs[f][i - 1] += x1;
-        }
+      const f2 y0 = yp[i * EW], y1 = yp[i * EW + 1], y2 = yp[i * EW + 2];
+      const f2 x0 = xp[i * EW], x1 = xp[i * EW + 1], x2 = xp[i * EW + 2];
+      row_sums_y<f2>(y0, y1, y2, hy[s], hyy[s]);
+      row_sums_x<f2>(x0, x1, x2, y0, y1, y2, hx[s], hxx[s], hxy[s]);
+      if (i >= 1 && i <= R) {
+        const f2 d = vsub(y1, x1);
+        acc[i - 1].x = fma_rn(w_l1, fabsf(d.x), acc[i - 1].x);
+        acc[i - 1].y = fma_rn(w_l1, fabsf(d.y), acc[i - 1].y);
+        if (WITH_CSUM) cs[i - 1] = vadd(cs[i - 1], x1);
       }
       if (i >= 2 && !no_ssim) {
-        const SsimY yst = ssim_y_stats(hy[0] + hy[1] + hy[2], hyy[0] + hyy[1] + hyy[2]);
-#pragma unroll
-        for (int f = 0; f < 2; ++f) {
-          const float S = ssim_from_sums(hx[f][0] + hx[f][1] + hx[f][2], hxx[f][0] + hxx[f][1] + hxx[f][2],
-                                         hxy[f][0] + hxy[f][1] + hxy[f][2], yst);
-          acc[f][i - 2] += PPEA_W_SSIM * S;
-        }
+        const SsimYT<f2> yst = ssim_y_stats<f2>(sum3(hy[0], hy[1], hy[2]), sum3(hyy[0], hyy[1], hyy[2]));
+        const f2 S = ssim_from_sums<f2>(sum3(hx[0], hx[1], hx[2]), sum3(hxx[0], hxx[1], hxx[2]), sum3(hxy[0], hxy[1], hxy[2]), yst);
+        acc[i - 2] = vfma(w_ssim, S, acc[i - 2]);
       }
     }
   }
 }
 
 template <int TW, int TH, int NT>
-__global__ void __launch_bounds__(NT) vsl_forward_kernel(const __grid_constant__ VslArgs a) {
+__global__ void __launch_bounds__(NT, 5) vsl_forward_kernel(const __grid_constant__ VslArgs a) {
   using Smem = FwdSmem<TW, TH>;
   constexpr int EW = Smem::EW, PLANE = Smem::PLANE;
   constexpr int R = (TW * TH) / NT;
@@ -102,36 +92,24 @@ __global__ void __launch_bounds__(NT) vsl_forward_kernel(const __grid_constant__
   const bool no_ssim = a.flags & PPEA_F_NO_SSIM;
 
   if (tid < 24) {
-    // P_f = (K @ T_f)[:3,:]: one thread per entry
-    const int f = tid / 12, e = tid % 12, i = e / 4, j = e % 4;
-    const float* K = a.K + b * 16;
-    const float* T = a.T[f] + b * 16;
-    float acc = mul_rn(K[i * 4 + 0], T[0 * 4 + j]);
-    acc = add_rn(acc, mul_rn(K[i * 4 + 1], T[1 * 4 + j]));
-    acc = add_rn(acc, mul_rn(K[i * 4 + 2], T[2 * 4 + j]));
-    acc = add_rn(acc, mul_rn(K[i * 4 + 3], T[3 * 4 + j]));
-    sm.P[f][e] = acc;
-  } else if (tid >= 32 && tid < 41) {
-    const int e = tid - 32;
-    sm.iK[e] = a.inv_K[b * 16 + (e / 3) * 4 + (e % 3)];
+    const int f = tid / 12, e = tid % 12;
+    const float v = geom_entry(a.K + b * 16, a.T[f] + b * 16, a.inv_K + b * 16, e);
+    (f ? sm.G[e].y : sm.G[e].x) = v;
   }
 
   const float* tgt_b = a.tgt + (size_t)b * 3 * plane;
   const float* src_b[2] = {a.src[0] + (size_t)b * 3 * plane, a.src[1] + (size_t)b * 3 * plane};
 
-  // ---- pass 1: stage target (+ un-warped sources for the identity loss) with reflection halo
+  // ---- stage the target (+ un-warped sources for the identity loss) with the reflection halo
   for (int idx = tid; idx < PLANE; idx += NT) {
     const int i = idx / EW, j = idx - i * EW;
     const int py = reflect_index(y0 - 1 + i, H), px = reflect_index(x0 - 1 + j, W);
     const size_t o = (size_t)py * W + px;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) sm.y[c][idx] = __ldg(tgt_b + c * plane + o);
+    for (int c = 0; c < 3; ++c) sm.y[c][idx] = dup2(__ldg(tgt_b + c * plane + o));
     if (automask) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        sm.x[0][c][idx] = __ldg(src_b[0] + c * plane + o);
-        sm.x[1][c][idx] = __ldg(src_b[1] + c * plane + o);
-      }
+      for (int c = 0; c < 3; ++c) sm.x[c][idx] = mk2(__ldg(src_b[0] + c * plane + o), __ldg(src_b[1] + c * plane + o));
     }
   }
   __syncthreads();
@@ -139,18 +117,15 @@ __global__ void __launch_bounds__(NT) vsl_forward_kernel(const __grid_constant__
   const int col = tid % TW;
   const int row0 = (tid / TW) * R;
   float ident[R];
-  float acc[2][R], cs[2][R];
+  f2 acc[R], cs[R];
   if (automask) {
-    photometric_pass<R, EW, PLANE, false>(&sm.x[0][0][0], &sm.y[0][0], row0, col, no_ssim, acc, cs);
+    photometric_pass<R, EW, PLANE, false>(&sm.x[0][0], &sm.y[0][0], row0, col, no_ssim, acc, cs);
 #pragma unroll
-    for (int k = 0; k < R; ++k) ident[k] = fminf(acc[0][k], acc[1][k]);   // trainer.py:1069
+    for (int k = 0; k < R; ++k) ident[k] = fminf(acc[k].x, acc[k].y);   // trainer.py:1069
     __syncthreads();
   }
 
-  const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
-  float iK[9];
-#pragma unroll
-  for (int e = 0; e < 9; ++e) iK[e] = sm.iK[e];
+  const float wmax = coord_max(W), hmax = coord_max(H);
   const int gx_own = x0 + col;
   const float one_minus_aug = (multi && (a.flags & PPEA_F_MATCH_AUG)) ? 1.f - a.aug_mask[b] : 1.f;
   const int lane = tid & 31, wid = tid >> 5;
@@ -158,35 +133,43 @@ __global__ void __launch_bounds__(NT) vsl_forward_kernel(const __grid_constant__
 #pragma unroll 1
   for (int s = 0; s < a.S; ++s) {
     const ScaleArgs& sc = a.sc[s];
-    // ---- pass 2: depth, backproject, project, bilinear gather of both sources into the x planes
+    // ---- gather pass: depth, projection into both sources, bilinear samples -> x planes
     {
       const float* disp_b = sc.disp + (size_t)b * sc.hs * sc.ws;
+      const bool same_res = (sc.hs == H && sc.ws == W);
       for (int idx = tid; idx < PLANE; idx += NT) {
         const int i = idx / EW, j = idx - i * EW;
         const int gy = y0 - 1 + i, gx = x0 - 1 + j;
         const int py = reflect_index(gy, H), px = reflect_index(gx, W);
-        const UpCoef cy = up_coef(py, sc.hs, sc.up_sy), cx = up_coef(px, sc.ws, sc.up_sx);
-        const float dep = depth_from_disp(up_sample(disp_b, sc.ws, cy, cx), a.disp_lo, a.disp_range);
+        float dup;
+        if (same_res) {
+          dup = __ldg(disp_b + (size_t)py * W + px);
+        } else {
+          const UpCoef cy = up_coef(py, sc.hs, sc.up_sy), cx = up_coef(px, sc.ws, sc.up_sx);
+          dup = up_sample(disp_b, sc.ws, cy, cx);
+        }
+        const float dep = depth_from_disp(dup, a.disp_lo, a.disp_range);
         if (i >= 1 && i <= TH && j >= 1 && j <= TW && gy < H && gx < W) sc.depth[(size_t)b * plane + (size_t)gy * W + gx] = dep;
-        float ray[3], cam[3];
-        pixel_ray(iK, (float)px, (float)py, ray);
+        const f2 fx = dup2(int_to_float(px)), fy = dup2(int_to_float(py));
+        const f2 A0 = vfma(sm.G[1], fy, vfma(sm.G[0], fx, sm.G[2]));
+        const f2 A1 = vfma(sm.G[4], fy, vfma(sm.G[3], fx, sm.G[5]));
+        const f2 A2 = vfma(sm.G[7], fy, vfma(sm.G[6], fx, sm.G[8]));
+        const ProjT<f2> pr = project_fast(dep, A0, A1, A2, sm.G[9], sm.G[10], sm.G[11], a.eps, wmax, hmax);
+        const Bilin b0 = bilin_setup(pr.ix.x, pr.iy.x, W), b1 = bilin_setup(pr.ix.y, pr.iy.y, W);
+        const f2 wnw = mk2(b0.wnw, b1.wnw), wne = mk2(b0.wne, b1.wne), wsw = mk2(b0.wsw, b1.wsw), wse = mk2(b0.wse, b1.wse);
 #pragma unroll
-        for (int e = 0; e < 3; ++e) cam[e] = mul_rn(dep, ray[e]);
-#pragma unroll
-        for (int f = 0; f < 2; ++f) {
-          const Proj pr = project_point(sm.P[f], cam, a.eps, wm1, hm1);
-          const Bilin bl = bilin_setup(pr.ix, pr.iy, W, H);
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const float* S = src_b[f] + c * plane;
-            sm.x[f][c][idx] = bilin_value(bl, __ldg(S + bl.o00), __ldg(S + bl.o01), __ldg(S + bl.o10), __ldg(S + bl.o11));
-          }
+        for (int c = 0; c < 3; ++c) {
+          const float* S0 = src_b[0] + c * plane + b0.o00;
+          const float* S1 = src_b[1] + c * plane + b1.o00;
+          const f2 nw = mk2(__ldg(S0), __ldg(S1)), ne = mk2(__ldg(S0 + 1), __ldg(S1 + 1));
+          const f2 sw = mk2(__ldg(S0 + W), __ldg(S1 + W)), se = mk2(__ldg(S0 + W + 1), __ldg(S1 + W + 1));
+          sm.x[c][idx] = vfma(se, wse, vfma(sw, wsw, vfma(ne, wne, vmul(nw, wnw))));
         }
       }
     }
     __syncthreads();
 
-    photometric_pass<R, EW, PLANE, true>(&sm.x[0][0][0], &sm.y[0][0], row0, col, no_ssim, acc, cs);
+    photometric_pass<R, EW, PLANE, true>(&sm.x[0][0], &sm.y[0][0], row0, col, no_ssim, acc, cs);
 
     // ---- epilogue: min over sources, selec_reproj, mask, per-pixel outputs, block sums
     float s_rm = 0.f, s_m = 0.f, s_c = 0.f;
@@ -195,7 +178,7 @@ __global__ void __launch_bounds__(NT) vsl_forward_kernel(const __grid_constant__
       const int gy = y0 + row0 + k;
       if (gy < H && gx_own < W) {
         const size_t o = (size_t)b * plane + (size_t)gy * W + gx_own;
-        const Select sl = select_source(acc[0][k], acc[1][k], cs[0][k], cs[1][k], a.flags & PPEA_F_SELEC_REPROJ);
+        const Select sl = select_source(acc[k].x, acc[k].y, cs[k].x, cs[k].y, a.flags & PPEA_F_SELEC_REPROJ);
         unsigned bits = (unsigned)sl.src;
         float mask = 1.f;
         if (multi) {

@@ -5,8 +5,9 @@
 // tests/test_emul.py compiles this file with g++ and checks the *shared
 // arithmetic* (forward values, selection, and above all the hand-derived
 // backward formulas) against the oracle before any GPU time is spent.  The
-// CUDA kernels call the same functions but tile/stage/reduce differently;
-// their plumbing is validated by the `-m gpu` tests.
+// CUDA kernels call the same functions (their f2 instantiations run the two
+// sources in lockstep) but tile/stage/reduce differently; their plumbing is
+// validated by the `-m gpu` tests.
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -17,12 +18,6 @@
 using namespace ppea;
 
 namespace {
-
-struct Img {
-  int H, W;
-  const float* p;
-  float at(int c, int y, int x) const { return p[((size_t)c * H + y) * W + x]; }
-};
 
 // reflect-padded 3x3 window sums of x, x*x, x*y at pixel (y, x) of channel planes
 inline void window_sums(const float* X, const float* Y, int H, int W, int y, int x, float& Sx, float& Sxx, float& Sxy,
@@ -36,40 +31,53 @@ inline void window_sums(const float* X, const float* Y, int H, int W, int y, int
       a[dx + 1] = X[(size_t)yy * W + xx];
       b[dx + 1] = Y[(size_t)yy * W + xx];
     }
-    hx[dy + 1] = a[0] + a[1] + a[2];
-    hxx[dy + 1] = a[0] * a[0] + a[1] * a[1] + a[2] * a[2];
-    hxy[dy + 1] = a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
-    hy[dy + 1] = b[0] + b[1] + b[2];
-    hyy[dy + 1] = b[0] * b[0] + b[1] * b[1] + b[2] * b[2];
+    row_sums_x<float>(a[0], a[1], a[2], b[0], b[1], b[2], hx[dy + 1], hxx[dy + 1], hxy[dy + 1]);
+    row_sums_y<float>(b[0], b[1], b[2], hy[dy + 1], hyy[dy + 1]);
   }
-  Sx = hx[0] + hx[1] + hx[2];
-  Sxx = hxx[0] + hxx[1] + hxx[2];
-  Sxy = hxy[0] + hxy[1] + hxy[2];
-  Sy = hy[0] + hy[1] + hy[2];
-  Syy = hyy[0] + hyy[1] + hyy[2];
+  Sx = sum3(hx[0], hx[1], hx[2]);
+  Sxx = sum3(hxx[0], hxx[1], hxx[2]);
+  Sxy = sum3(hxy[0], hxy[1], hxy[2]);
+  Sy = sum3(hy[0], hy[1], hy[2]);
+  Syy = sum3(hyy[0], hyy[1], hyy[2]);
 }
 
 // photometric loss map 0.85*mean_c SSIM + 0.15*mean_c |y-x|  (trainer.py:995-1007)
 void photometric_map(const float* X, const float* Y, int H, int W, bool no_ssim, float* out) {
   size_t plane = (size_t)H * W;
+  const float w_l1 = no_ssim ? (1.f / 3.f) : PPEA_W_L1;
   for (int y = 0; y < H; ++y)
     for (int x = 0; x < W; ++x) {
       float acc = 0.f;
       for (int c = 0; c < 3; ++c) {
         const float* Xc = X + c * plane;
         const float* Yc = Y + c * plane;
-        float l1 = fabsf(Yc[(size_t)y * W + x] - Xc[(size_t)y * W + x]);
-        if (no_ssim) {
-          acc += l1 * (1.f / 3.f);
-        } else {
+        float l1 = fabsf(add_rn(Yc[(size_t)y * W + x], -Xc[(size_t)y * W + x]));
+        acc = fma_rn(w_l1, l1, acc);
+        if (!no_ssim) {
           float Sx, Sxx, Sxy, Sy, Syy;
           window_sums(Xc, Yc, H, W, y, x, Sx, Sxx, Sxy, Sy, Syy);
-          SsimY ys = ssim_y_stats(Sy, Syy);
-          acc += PPEA_W_SSIM * ssim_from_sums(Sx, Sxx, Sxy, ys) + PPEA_W_L1 * l1;
+          acc = fma_rn(PPEA_W_SSIM, ssim_from_sums<float>(Sx, Sxx, Sxy, ssim_y_stats<float>(Sy, Syy)), acc);
         }
       }
       out[(size_t)y * W + x] = acc;
     }
+}
+
+struct PixelGeom {
+  float A[2][3];
+  ProjT<float> pr[2];
+  Bilin bl[2];
+};
+
+inline PixelGeom pixel_geom(const Geom* g, float dep, int x, int y, float eps, int W, int H) {
+  PixelGeom o;
+  const float fx = (float)x, fy = (float)y;
+  for (int f = 0; f < 2; ++f) {
+    for (int i = 0; i < 3; ++i) o.A[f][i] = fma_rn(g[f].M[i * 3 + 1], fy, fma_rn(g[f].M[i * 3 + 0], fx, g[f].M[i * 3 + 2]));
+    o.pr[f] = project_fast(dep, o.A[f][0], o.A[f][1], o.A[f][2], g[f].t[0], g[f].t[1], g[f].t[2], eps, coord_max(W), coord_max(H));
+    o.bl[f] = bilin_setup(o.pr[f].ix, o.pr[f].iy, W);
+  }
+  return o;
 }
 
 }  // namespace
@@ -91,37 +99,31 @@ int emul_vsl_forward(int B, int H, int W, int h_s, int w_s, unsigned flags, floa
   float* grids[2] = {grid0, grid1};
   size_t plane = (size_t)H * W;
   float sy = up_scale(h_s, H), sx = up_scale(w_s, W);
-  float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
   double s_rm = 0, s_m = 0, s_c = 0;
   std::vector<float> L[2], Lid[2];
   for (int f = 0; f < 2; ++f) { L[f].resize(plane); Lid[f].resize(plane); }
   for (int b = 0; b < B; ++b) {
-    float P[2][12], iK[9];
-    for (int f = 0; f < 2; ++f) compose_P(K + b * 16, Ts[f] + b * 16, P[f]);
-    for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 3; ++j) iK[i * 3 + j] = inv_K[b * 16 + i * 4 + j];
+    Geom g[2];
+    for (int f = 0; f < 2; ++f) compose_geom(K + b * 16, Ts[f] + b * 16, inv_K + b * 16, g[f]);
     const float* d_b = disp + (size_t)b * h_s * w_s;
     for (int y = 0; y < H; ++y) {
       UpCoef cy = up_coef(y, h_s, sy);
       for (int x = 0; x < W; ++x) {
         UpCoef cx = up_coef(x, w_s, sx);
-        float dup = up_sample(d_b, w_s, cy, cx);
+        float dup = (h_s == H && w_s == W) ? d_b[(size_t)y * W + x] : up_sample(d_b, w_s, cy, cx);
         float dep = depth_from_disp(dup, disp_lo, disp_range);
         depth[b * plane + (size_t)y * W + x] = dep;
-        float ray[3], cam[3];
-        pixel_ray(iK, (float)x, (float)y, ray);
-        for (int j = 0; j < 3; ++j) cam[j] = mul_rn(dep, ray[j]);
+        PixelGeom pg = pixel_geom(g, dep, x, y, eps, W, H);
         for (int f = 0; f < 2; ++f) {
-          Proj pr = project_point(P[f], cam, eps, wm1, hm1);
           if (grids[f]) {
-            grids[f][(b * plane + (size_t)y * W + x) * 2 + 0] = pr.gx;
-            grids[f][(b * plane + (size_t)y * W + x) * 2 + 1] = pr.gy;
+            grids[f][(b * plane + (size_t)y * W + x) * 2 + 0] = (pg.pr[f].u / (float)(W - 1) - 0.5f) * 2.f;
+            grids[f][(b * plane + (size_t)y * W + x) * 2 + 1] = (pg.pr[f].v / (float)(H - 1) - 0.5f) * 2.f;
           }
-          Bilin bl = bilin_setup(pr.ix, pr.iy, W, H);
+          const Bilin& bl = pg.bl[f];
           for (int c = 0; c < 3; ++c) {
             const float* S = srcs[f] + ((size_t)b * 3 + c) * plane;
             warped[f][((size_t)b * 3 + c) * plane + (size_t)y * W + x] =
-                bilin_value(bl, S[bl.o00], S[bl.o01], S[bl.o10], S[bl.o11]);
+                bilin_value(bl, S[bl.o00], S[bl.o00 + 1], S[bl.o00 + W], S[bl.o00 + W + 1]);
           }
         }
       }
@@ -172,7 +174,7 @@ int emul_vsl_forward(int B, int H, int W, int h_s, int w_s, unsigned flags, floa
 
 // One scale, backward of
 //   w_r * sum(r*mask)/(sum(mask)+1e-7)  +  w_c * mean(|depth-mono|*(1-mask))
-// wrt disp_s and P_f = (K@T_f)[:3,:]; selection `sel` and `warped` come from the forward.
+// wrt disp_s and P_f = (K@T_f)[:3,:]; selection `sel` comes from the forward.
 // g_r = w_r/(sum(mask)+1e-7), g_c = w_c/(B*H*W) are passed in.
 int emul_vsl_backward(int B, int H, int W, int h_s, int w_s, unsigned flags, float disp_lo, float disp_range, float eps,
                       const float* disp, const float* tgt, const float* src0, const float* src1, const float* K,
@@ -184,34 +186,30 @@ int emul_vsl_backward(int B, int H, int W, int h_s, int w_s, unsigned flags, flo
   const float* Ts[2] = {T0, T1};
   size_t plane = (size_t)H * W;
   float sy = up_scale(h_s, H), sx = up_scale(w_s, W);
-  float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
+  const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
+  const bool same = (h_s == H && w_s == W);
   memset(grad_disp, 0, sizeof(float) * (size_t)B * h_s * w_s);
   memset(grad_P, 0, sizeof(double) * (size_t)B * 24);
   std::vector<float> depth(plane), warped(2 * 3 * plane), gw(2 * 3 * plane);
   std::vector<float> cA(plane), cB(plane), cC(plane), wq(plane);
-  std::vector<double> gdu(plane);
   for (int b = 0; b < B; ++b) {
-    float P[2][12], iK[9];
-    for (int f = 0; f < 2; ++f) compose_P(K + b * 16, Ts[f] + b * 16, P[f]);
-    for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 3; ++j) iK[i * 3 + j] = inv_K[b * 16 + i * 4 + j];
+    Geom g[2];
+    for (int f = 0; f < 2; ++f) compose_geom(K + b * 16, Ts[f] + b * 16, inv_K + b * 16, g[f]);
     const float* d_b = disp + (size_t)b * h_s * w_s;
     // recompute depth + warped
     for (int y = 0; y < H; ++y) {
       UpCoef cy = up_coef(y, h_s, sy);
       for (int x = 0; x < W; ++x) {
         UpCoef cx = up_coef(x, w_s, sx);
-        float dep = depth_from_disp(up_sample(d_b, w_s, cy, cx), disp_lo, disp_range);
+        float dup = same ? d_b[(size_t)y * W + x] : up_sample(d_b, w_s, cy, cx);
+        float dep = depth_from_disp(dup, disp_lo, disp_range);
         depth[(size_t)y * W + x] = dep;
-        float ray[3], cam[3];
-        pixel_ray(iK, (float)x, (float)y, ray);
-        for (int j = 0; j < 3; ++j) cam[j] = mul_rn(dep, ray[j]);
+        PixelGeom pg = pixel_geom(g, dep, x, y, eps, W, H);
         for (int f = 0; f < 2; ++f) {
-          Proj pr = project_point(P[f], cam, eps, wm1, hm1);
-          Bilin bl = bilin_setup(pr.ix, pr.iy, W, H);
+          const Bilin& bl = pg.bl[f];
           for (int c = 0; c < 3; ++c) {
             const float* S = srcs[f] + ((size_t)b * 3 + c) * plane;
-            warped[(f * 3 + c) * plane + (size_t)y * W + x] = bilin_value(bl, S[bl.o00], S[bl.o01], S[bl.o10], S[bl.o11]);
+            warped[(f * 3 + c) * plane + (size_t)y * W + x] = bilin_value(bl, S[bl.o00], S[bl.o00 + 1], S[bl.o00 + W], S[bl.o00 + W + 1]);
           }
         }
       }
@@ -237,11 +235,11 @@ int emul_vsl_backward(int B, int H, int W, int h_s, int w_s, unsigned flags, flo
         for (int y = 0; y < H; ++y)
           for (int x = 0; x < W; ++x) {
             size_t i = (size_t)y * W + x;
-            SsimAdj a = {0.f, 0.f, 0.f};
+            SsimAdjT<float> a = {0.f, 0.f, 0.f};
             if (!no_ssim && wq[i] != 0.f) {
               float Sx, Sxx, Sxy, Sy, Syy;
               window_sums(Xc, Yc, H, W, y, x, Sx, Sxx, Sxy, Sy, Syy);
-              a = ssim_adjoint(Sx, Sxx, Sxy, ssim_y_stats(Sy, Syy), wq[i] * PPEA_W_SSIM);
+              a = ssim_adjoint<float>(Sx, Sxx, Sxy, ssim_y_stats<float>(Sy, Syy), wq[i] * PPEA_W_SSIM);
             }
             cA[i] = a.cA; cB[i] = a.cB; cC[i] = a.cC;
           }
@@ -249,9 +247,7 @@ int emul_vsl_backward(int B, int H, int W, int h_s, int w_s, unsigned flags, flo
         float* G = gw.data() + (f * 3 + c) * plane;
         for (size_t i = 0; i < plane; ++i) {
           float l1w = no_ssim ? (1.f / 3.f) : PPEA_W_L1;
-          float d = Yc[i] - Xc[i];
-          float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
-          G[i] = -wq[i] * l1w * sgn;
+          G[i] = -wq[i] * l1w * sign_of(Yc[i] - Xc[i]);
         }
         if (!no_ssim)
           for (int y = 0; y < H; ++y)
@@ -267,54 +263,67 @@ int emul_vsl_backward(int B, int H, int W, int h_s, int w_s, unsigned flags, flo
       }
     }
     // chain through grid_sample, Project3D, BackprojectDepth, depth, upsample
+    double Q[2][3][3];      // sum gc[r] * depth * (x, y, 1)
+    double Q3[2][3];        // sum gc[r]
+    memset(Q, 0, sizeof(Q));
+    memset(Q3, 0, sizeof(Q3));
     for (int y = 0; y < H; ++y) {
       UpCoef cy = up_coef(y, h_s, sy);
       for (int x = 0; x < W; ++x) {
         UpCoef cx = up_coef(x, w_s, sx);
         size_t i = (size_t)y * W + x;
         float dep = depth[i];
-        float ray[3], cam[3];
-        pixel_ray(iK, (float)x, (float)y, ray);
-        for (int j = 0; j < 3; ++j) cam[j] = mul_rn(dep, ray[j]);
+        PixelGeom pg = pixel_geom(g, dep, x, y, eps, W, H);
         float g_depth = 0.f;
         for (int f = 0; f < 2; ++f) {
-          Proj pr = project_point(P[f], cam, eps, wm1, hm1);
-          Bilin bl = bilin_setup(pr.ix, pr.iy, W, H);
+          const Bilin& bl = pg.bl[f];
+          const ProjT<float>& pr = pg.pr[f];
           float gix = 0.f, giy = 0.f;
           for (int c = 0; c < 3; ++c) {
             const float* S = srcs[f] + ((size_t)b * 3 + c) * plane;
-            float g = gw[(f * 3 + c) * plane + i];
-            gix += g * bilin_ddx(bl, S[bl.o00], S[bl.o01], S[bl.o10], S[bl.o11]);
-            giy += g * bilin_ddy(bl, S[bl.o00], S[bl.o01], S[bl.o10], S[bl.o11]);
+            float gv = gw[(f * 3 + c) * plane + i];
+            gix += gv * bilin_ddx(bl, S[bl.o00], S[bl.o00 + 1], S[bl.o00 + W], S[bl.o00 + W + 1]);
+            giy += gv * bilin_ddy(bl, S[bl.o00], S[bl.o00 + 1], S[bl.o00 + W], S[bl.o00 + W + 1]);
           }
-          float gu = gix * pr.mx, gv = giy * pr.my;
-          float inv_z = 1.f / pr.z;
-          float gc[3] = {gu * inv_z, gv * inv_z, -(gu * pr.u + gv * pr.v) * inv_z};
-          for (int j = 0; j < 3; ++j) {
-            float gcam = P[f][0 * 4 + j] * gc[0] + P[f][1 * 4 + j] * gc[1] + P[f][2 * 4 + j] * gc[2];
-            g_depth += gcam * ray[j];
-          }
+          float gu = gix * clip_mask(pr.u, wm1), gv = giy * clip_mask(pr.v, hm1);
+          float gc[3] = {gu * pr.rz, gv * pr.rz, -(gu * pr.u + gv * pr.v) * pr.rz};
           for (int r = 0; r < 3; ++r) {
-            for (int j = 0; j < 3; ++j) grad_P[(b * 2 + f) * 12 + r * 4 + j] += (double)(gc[r] * cam[j]);
-            grad_P[(b * 2 + f) * 12 + r * 4 + 3] += (double)gc[r];
+            g_depth += gc[r] * pg.A[f][r];
+            Q[f][r][0] += (double)(gc[r] * dep) * x;
+            Q[f][r][1] += (double)(gc[r] * dep) * y;
+            Q[f][r][2] += (double)(gc[r] * dep);
+            Q3[f][r] += (double)gc[r];
           }
         }
         if (multi) {
           float mask = 1.f;
           if (motion) mask *= cons_mask[b * plane + i];
           if (aug) mask *= (1.f - aug_mask[b]);
-          float d = dep - mono_depth[b * plane + i];
-          float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
-          g_depth += g_c * sgn * (1.f - mask);
+          g_depth += g_c * sign_of(dep - mono_depth[b * plane + i]) * (1.f - mask);
         }
         float g_dup = g_depth * ddepth_ddisp(dep, disp_range);
         float* gd = grad_disp + (size_t)b * h_s * w_s;
-        gd[cy.i0 * w_s + cx.i0] += g_dup * cy.l0 * cx.l0;
-        gd[cy.i0 * w_s + cx.i1] += g_dup * cy.l0 * cx.l1;
-        gd[cy.i1 * w_s + cx.i0] += g_dup * cy.l1 * cx.l0;
-        gd[cy.i1 * w_s + cx.i1] += g_dup * cy.l1 * cx.l1;
+        if (same) {
+          gd[i] += g_dup;
+        } else {
+          gd[cy.i0 * w_s + cx.i0] += g_dup * cy.l0 * cx.l0;
+          gd[cy.i0 * w_s + cx.i1] += g_dup * cy.l0 * cx.l1;
+          gd[cy.i1 * w_s + cx.i0] += g_dup * cy.l1 * cx.l0;
+          gd[cy.i1 * w_s + cx.i1] += g_dup * cy.l1 * cx.l1;
+        }
       }
     }
+    // dL/dP[r][j] = sum_j' Q[r][j'] * inv_K[j][j']  (cam = depth * inv_K3 (x,y,1)),  dL/dP[r][3] = sum gc[r]
+    const float* iK = inv_K + b * 16;
+    for (int f = 0; f < 2; ++f)
+      for (int r = 0; r < 3; ++r) {
+        for (int j = 0; j < 3; ++j) {
+          double acc = 0;
+          for (int k = 0; k < 3; ++k) acc += Q[f][r][k] * (double)iK[j * 4 + k];
+          grad_P[(b * 2 + f) * 12 + r * 4 + j] = acc;
+        }
+        grad_P[(b * 2 + f) * 12 + r * 4 + 3] = Q3[f][r];
+      }
   }
   return 0;
 }

