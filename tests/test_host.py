@@ -1,0 +1,106 @@
+"""CPU: host-side logic above the C ABI -- flag mapping, drop-in surface, no-CPU-fallback behaviour,
+synthetic batch generator, algorithmic-byte accounting."""
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+import ppea_depth_b200 as P
+from ppea_depth_b200 import _cabi as C
+from ppea_depth_b200.functional import VslConfig
+from ppea_depth_b200.synth import SynthConfig, algorithmic_bytes, make_batch, make_noise
+
+
+def test_public_surface_mirrors_the_reference():
+    for name in ("BackprojectDepth", "Project3D", "SSIM", "get_smooth_loss", "disp_to_depth", "upsample",
+                 "transformation_from_parameters", "generate_images_pred", "compute_reprojection_loss",
+                 "compute_loss_masks", "compute_losses", "install"):
+        assert hasattr(P, name), name
+    import inspect
+    assert list(inspect.signature(P.generate_images_pred).parameters) == ["self", "inputs", "outputs", "is_multi"]
+    assert list(inspect.signature(P.compute_losses).parameters) == ["self", "inputs", "outputs", "is_multi"]
+    assert list(inspect.signature(P.compute_reprojection_loss).parameters) == ["self", "pred", "target"]
+    assert list(inspect.signature(P.Project3D.__init__).parameters) == ["self", "batch_size", "height", "width", "dc", "eps"]
+    assert list(inspect.signature(P.BackprojectDepth.__init__).parameters) == ["self", "batch_size", "height", "width"]
+
+
+def test_install_rebinds_trainer_methods():
+    class FakeTrainer:
+        def compute_losses(self, inputs, outputs, is_multi=False):
+            return "reference"
+    P.install(FakeTrainer, deterministic=True)
+    assert FakeTrainer.compute_losses is P.compute_losses
+    assert FakeTrainer.generate_images_pred is P.generate_images_pred
+    assert FakeTrainer.ppea_deterministic is True
+    m = FakeTrainer.compute_loss_masks(torch.tensor([1.0, 3.0]), torch.tensor([2.0, 2.0]))
+    assert m.tolist() == [1.0, 0.0]
+    assert FakeTrainer.compute_loss_masks(torch.ones(2), None).tolist() == [1.0, 1.0]
+    assert FakeTrainer.compute_loss_masks(torch.tensor([2.0]), torch.tensor([2.0])).tolist() == [1.0]   # first-min tie rule
+
+
+def test_flags():
+    f = VslConfig().flags(grad_pose=True)
+    assert f == C.F_AUTOMASK | C.F_SELEC_REPROJ | C.F_MOTION_MASK | C.F_MATCH_AUG | C.F_GRAD_POSE
+    f = VslConfig(is_multi=True, selec_reproj=False, no_ssim=True, deterministic=True, motion_mask=False).flags(False)
+    assert f == C.F_MULTI | C.F_AUTOMASK | C.F_NO_SSIM | C.F_DETERMINISTIC | C.F_MATCH_AUG
+
+
+def test_cpu_tensors_raise_instead_of_falling_back():
+    x = torch.rand(1, 3, 8, 8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        P.SSIM()(x, x)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        P.get_smooth_loss(torch.rand(1, 1, 8, 8), x)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        P.BackprojectDepth(1, 8, 8)(torch.rand(1, 1, 8, 8), torch.eye(4)[None])
+    opt = SimpleNamespace(sclm=0, v1_multiscale=False, height=16, width=32, min_depth=0.1, max_depth=100.0,
+                          frame_ids=[0, -1, 1], disable_automasking=False, no_ssim=False, selec_reproj=True,
+                          disable_motion_masking=False, no_matching_augmentation=False, batch_size=1,
+                          disparity_smoothness=1e-3)
+    inputs, outputs = make_batch(SynthConfig(batch=1, height=16, width=32, num_scales=1))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        P.ViewSynthesisLoss(opt).generate_images_pred(inputs, outputs, False)
+
+
+def test_only_two_source_configuration_is_fused():
+    opt = SimpleNamespace(sclm=0, frame_ids=[0, -1], batch_size=1)
+    with pytest.raises((NotImplementedError, IndexError)):
+        P.ViewSynthesisLoss(opt).generate_images_pred({}, {("disp", 0): torch.zeros(1)}, False)
+
+
+def test_pose_helpers_match_known_answers():
+    aa = torch.zeros(2, 1, 3)
+    tr = torch.tensor([[[1.0, 2.0, 3.0]], [[0.0, 0.0, 0.0]]])
+    T = P.transformation_from_parameters(aa, tr)
+    assert torch.allclose(T[0, :3, 3], torch.tensor([1.0, 2.0, 3.0]))
+    assert torch.allclose(T[:, :3, :3], torch.eye(3).expand(2, 3, 3))
+    aa = 0.3 * torch.randn(4, 1, 3)
+    tr = torch.randn(4, 1, 3)
+    prod = P.transformation_from_parameters(aa, tr, invert=True) @ P.transformation_from_parameters(aa, tr)
+    assert torch.allclose(prod, torch.eye(4).expand(4, 4, 4), atol=1e-5)        # layers.py:299-307 smoke block
+    _, depth = P.disp_to_depth(torch.tensor([0.0, 1.0]), 0.1, 100.0)
+    assert torch.allclose(depth, torch.tensor([100.0, 0.1]))
+    assert P.upsample(torch.zeros(1, 1, 2, 3)).shape == (1, 1, 4, 6)
+
+
+def test_synthetic_batch_is_deterministic_and_well_formed():
+    cfg = SynthConfig(batch=2, height=32, width=64, num_scales=3, seed=4)
+    a_in, a_out = make_batch(cfg)
+    b_in, b_out = make_batch(cfg)
+    for k in a_in:
+        assert torch.equal(a_in[k], b_in[k]), k
+    img = a_in[("color", 0, 0)]
+    assert img.shape == (2, 3, 32, 64) and float(img.min()) >= 0 and float(img.max()) <= 1
+    assert torch.equal(img, torch.round(img * 255) / 255)                       # exact k/255 like ToTensor(uint8)
+    assert float((a_in[("color", -1, 0)].sum(1) == 0).float().mean()) > 0.005   # dark pixels for selec_reproj
+    assert a_out[("disp", 2)].shape == (2, 1, 8, 16)
+    assert torch.allclose(a_in[("K", 1)][0] @ a_in[("inv_K", 1)][0], torch.eye(4), atol=1e-4)
+    n = make_noise(cfg, 3)
+    assert len(n) == 3 and n[0].shape == (2, 1, 32, 64)
+
+
+def test_algorithmic_bytes_match_survey_table():
+    n = 12 * 192 * 640
+    assert abs(algorithmic_bytes(12, 192, 640, 4) / n - 375.9) < 0.05
+    assert abs(algorithmic_bytes(12, 192, 640, 4, deterministic=True) / n - 407.9) < 0.05
+    assert abs(algorithmic_bytes(12, 192, 640, 4, is_multi=True) / n - 423.9) < 0.05
