@@ -70,6 +70,8 @@ extern "C" {
 #define PPEA_F_MOTION_MASK (1u << 5)   /* not opt.disable_motion_masking (trainer.py:1103-1105) */
 #define PPEA_F_MATCH_AUG (1u << 6)     /* not opt.no_matching_augmentation (trainer.py:1106-1108) */
 #define PPEA_F_GRAD_POSE (1u << 7)     /* backward: also produce dL/dT (mono path) */
+#define PPEA_F_GRAD_PREZEROED (1u << 8) /* backward: every grad_disp was zero-filled by the forward (which does so when it is
+                                           handed non-NULL grad_disp pointers); skips the backward's own zero-fill */
 
 /* sel map (uint8 per full-res pixel, written by forward, read by backward):
  *   bits 0-1: source frame whose loss is propagated: 0 -> frame_ids[1] (-1),
@@ -84,7 +86,7 @@ extern "C" {
 /* sums: device vector of num_scales rows of (PPEA_SUMS_PER_SCALE + 4*batch) floats, written by forward,
  * read by backward.  row[0] sum(r*mask)  row[1] sum(mask)  row[2] sum(|depth-mono|*(1-mask))
  *   row[3] smooth_x sum  row[4] smooth_y sum  row[5..7] reserved
- *   row[8 + 4*b + k]: per image b: 0 sum(disp_s)  1 smooth_x sum  2 smooth_y sum  3 reserved
+ *   row[8 + 4*b + k]: per image b: 0 sum(disp_s)  1 raw smooth_x sum  2 raw smooth_y sum  3 image b's share of the smoothness term
  * losses: device vector (1 + 4*num_scales):
  *   losses[0] = sum_s loss_s / total_scales
  *   losses[1 + 4*s + k]: 0 loss/s  1 reproj_loss/s  2 consistency_loss/s  3 smoothness term of scale s (unweighted) */
@@ -100,7 +102,8 @@ typedef struct PpeaVslScale {
   float* depth;            /* out (B,1,H,W)  outputs[("depth", 0, s)] -- always materialised (trainer.py:893) */
   float* loss_px;          /* out (B,1,H,W)  per-pixel reprojection loss after min/selec_reproj; may be NULL */
   uint8_t* sel;            /* out (B,H,W)    selection map, see PPEA_SEL_* (input of backward) */
-  float* grad_disp;        /* backward out (B,1,disp_h,disp_w), fully overwritten; unused by forward */
+  float* grad_disp;        /* backward out (B,1,disp_h,disp_w), fully overwritten.  Forward: NULL, or the same buffer to have
+                              it zero-filled on the fly (then pass PPEA_F_GRAD_PREZEROED to backward) */
 } PpeaVslScale;
 
 typedef struct PpeaVslParams {
@@ -128,8 +131,8 @@ typedef struct PpeaVslParams {
   size_t workspace_bytes;
   void* const* trace_events; /* NULL, or PPEA_TRACE_EVENTS cudaEvent_t handles (ppea_event_create) recorded on `stream`:
                                 [0] before the first kernel, then after each stage --
-                                forward:  [1] disp sums  [2] fused forward kernel  [3] smoothness stencil  [4] finish
-                                backward: [1] smoothness backward  [2] fused backward kernel  [3] upsample gather  [4] pose finish */
+                                forward:  [1] (unused)  [2] fused forward kernel  [3] (unused)  [4] finish
+                                backward: [1] grad zero-fill (or smoothness backward when deterministic)  [2] fused backward kernel  [3] upsample gather  [4] pose finish */
 } PpeaVslParams;
 
 typedef struct PpeaVslGrads {

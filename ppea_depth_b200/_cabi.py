@@ -34,6 +34,7 @@ F_DETERMINISTIC = 1 << 4
 F_MOTION_MASK = 1 << 5
 F_MATCH_AUG = 1 << 6
 F_GRAD_POSE = 1 << 7
+F_GRAD_PREZEROED = 1 << 8
 
 SEL_SRC_MASK = 3
 SEL_AUTOMASK = 4

@@ -165,11 +165,9 @@ int ppea_vsl_forward(const PpeaVslParams* p, void* stream_) {
   a.partials = (float*)p->workspace + ws.off_partials;
   a.smooth_ws = (float*)p->workspace + ws.off_smooth;
   PPEA_TRACE(p, 0);
-  PPEA_TRY(launch_smooth_disp_sums(a, stream));
   PPEA_TRACE(p, 1);
-  PPEA_TRY(launch_vsl_forward(a, stream));
+  PPEA_TRY(launch_vsl_forward(a, stream));      // tiles of every scale + the smoothness CTAs
   PPEA_TRACE(p, 2);
-  PPEA_TRY(launch_smooth_forward(a, stream));
   PPEA_TRACE(p, 3);
   PPEA_TRY(launch_vsl_finish(a, fwd_blocks(a.B, a.H, a.W), stream));
   PPEA_TRACE(p, 4);
@@ -205,7 +203,13 @@ int ppea_vsl_backward(const PpeaVslParams* p, const PpeaVslGrads* g, void* strea
       }
   }
   PPEA_TRACE(p, 0);
-  PPEA_TRY(launch_smooth_backward(a, stream));
+  if (p->flags & PPEA_F_DETERMINISTIC) {
+    PPEA_TRY(launch_smooth_backward(a, stream));          // overwrite, then fixed-order adds on top
+  } else if (!(p->flags & PPEA_F_GRAD_PREZEROED)) {
+    // every contribution (tile CTAs and smoothness CTAs of the fused launch) is accumulated atomically
+    for (int s = 0; s < a.S; ++s)
+      PPEA_TRY(cudaMemsetAsync(a.sc[s].grad_disp, 0, sizeof(float) * (size_t)a.B * a.sc[s].hs * a.sc[s].ws, stream));
+  }
   PPEA_TRACE(p, 1);
   PPEA_TRY(launch_vsl_backward(a, stream));
   PPEA_TRACE(p, 2);

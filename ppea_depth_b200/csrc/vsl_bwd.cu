@@ -26,6 +26,10 @@
 //            (trainer.py:886-887): direct accumulate at scale 0, float atomics or
 //            (deterministic) a full-res scratch + gather pass for coarser scales.
 #include "vsl_common.cuh"
+#include <type_traits>
+
+#include "smooth.cuh"
+#include "vsl_gather.cuh"
 
 namespace ppea {
 
@@ -41,26 +45,21 @@ struct BwdSmem {
   float red[24][8];
 };
 
-// projection of one pixel into both sources
-__device__ __forceinline__ ProjT<f2> project_pixel(const f2* __restrict__ G, float dep, int px, int py, float eps, float wmax,
-                                                   float hmax, f2 (&A)[3]) {
-  const f2 fx = dup2(int_to_float(px)), fy = dup2(int_to_float(py));
-  A[0] = vfma(G[1], fy, vfma(G[0], fx, G[2]));
-  A[1] = vfma(G[4], fy, vfma(G[3], fx, G[5]));
-  A[2] = vfma(G[7], fy, vfma(G[6], fx, G[8]));
-  return project_fast(dep, A[0], A[1], A[2], G[9], G[10], G[11], eps, wmax, hmax);
-}
-
 template <int TW, int TH, int NT, bool POSE>
 __global__ void __launch_bounds__(NT, (NT >= 256 ? 2 : 4)) vsl_backward_kernel(const __grid_constant__ VslArgs a) {
   using Smem = BwdSmem<TW, TH>;
   constexpr int RW = Smem::RW, RP = Smem::RP, QW = Smem::QW, QP = Smem::QP;
   constexpr int R = (TW * TH) / NT;
-  constexpr int HALO = RP - TW * TH;
+  static_assert(TW == 32 && NT == 128 && TH == 16, "the gather/row mapping assumes lane == tile column, 4 warps x 4 rows");
   static_assert(NT % TW == 0 && (TW * TH) % NT == 0, "tile/thread mismatch");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
 
+  const int n_tiles = a.B * a.tiles_x * a.tiles_y;
+  if ((int)blockIdx.x >= n_tiles) {        // extra CTAs (non-deterministic mode): smoothness gradient of every scale
+    smooth_backward_role<true>(a, blockIdx.x - n_tiles);
+    return;
+  }
   const int tid = threadIdx.x;
   int blk = blockIdx.x;
   const int tx = blk % a.tiles_x;
@@ -98,7 +97,9 @@ __global__ void __launch_bounds__(NT, (NT >= 256 ? 2 : 4)) vsl_backward_kernel(c
   const int col = tid % TW;
   const int row0 = (tid / TW) * R;
   const int gx_own = x0 + col;
-  const int px_own = reflect_index(gx_own, W);                   // clamp for partial tiles
+  const ColCtx col_own = make_col(sm.G, gx_own, W);              // this thread's tile column (reflect-clamped for partial tiles)
+  const int px_own = col_own.px;
+  const SrcPlanes sp = make_planes(src_b[0], src_b[1], plane);
   const float one_minus_aug = (multi && (a.flags & PPEA_F_MATCH_AUG)) ? 1.f - a.aug_mask[b] : 1.f;
   // reflection multiplicities of the taps left/right of this thread's column
   const f2 mL = dup2((gx_own == 1) ? 2.f : 1.f), mR = dup2((gx_own == W - 2) ? 2.f : 1.f);
@@ -122,73 +123,62 @@ __global__ void __launch_bounds__(NT, (NT >= 256 ? 2 : 4)) vsl_backward_kernel(c
     f2 ddx[R][3], ddy[R][3];     // d warped_c / d u, d warped_c / d v  (lanes = sources)
     f2 gu[R], gv[R];
 
-    auto depth_at = [&](int py, int px) {
-      float dup;
+    // ---- phase 1: gather.  Warp w walks its own R tile rows (lane == tile column, derivatives kept) plus
+    // its share of the four halo rows; the four halo columns are a flat list of extra cells.
+    ColCtx cc = col_own;
+    if (!same_res) cc.cx = up_coef(cc.px, sc.ws, sc.up_sx);
+    auto gather_row = [&](int i, auto want_deriv, f2 (&dx)[3], f2 (&dy)[3]) -> float {
+      const int py = reflect_index(y0 - 2 + i, H);
+      UpCoef cy;
+      float d;
       if (same_res) {
-        dup = __ldg(disp_b + (size_t)py * W + px);
+        d = depth_of<true>(disp_b, W, sc.ws, py, cc, cy, a.disp_lo, a.disp_range);
       } else {
-        const UpCoef cy = up_coef(py, sc.hs, sc.up_sy), cx = up_coef(px, sc.ws, sc.up_sx);
-        dup = up_sample(disp_b, sc.ws, cy, cx);
+        cy = up_coef(py, sc.hs, sc.up_sy);
+        d = depth_of<false>(disp_b, W, sc.ws, py, cc, cy, a.disp_lo, a.disp_range);
       }
-      return depth_from_disp(dup, a.disp_lo, a.disp_range);
+      f2 A[3], val[3];
+      const ProjT<f2> pr = project_cell(sm.G, cc, py, d, a.eps, wmax, hmax, A);
+      sample_sources<decltype(want_deriv)::value>(sp, W, pr, wm1, hm1, val, dx, dy);
+      const int ridx = i * RW + col + 2;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) sm.x[c][ridx] = val[c];
+      return d;
     };
-
-    // ---- phase 1a: own tile pixels (keeps the derivatives in registers)
 #pragma unroll
     for (int k = 0; k < R; ++k) {
-      const int py = reflect_index(y0 + row0 + k, H);
-      dep[k] = depth_at(py, px_own);
+      dep[k] = gather_row(row0 + k + 2, std::true_type{}, ddx[k], ddy[k]);
       gu[k] = gv[k] = dup2(0.f);
-      f2 A[3];
-      const ProjT<f2> pr = project_pixel(sm.G, dep[k], px_own, py, a.eps, wmax, hmax, A);
-      const Bilin b0 = bilin_setup(pr.ix.x, pr.iy.x, W), b1 = bilin_setup(pr.ix.y, pr.iy.y, W);
-      const f2 wnw = mk2(b0.wnw, b1.wnw), wne = mk2(b0.wne, b1.wne), wsw = mk2(b0.wsw, b1.wsw), wse = mk2(b0.wse, b1.wse);
-      const f2 tx = mk2(b0.tx, b1.tx), ty = mk2(b0.ty, b1.ty);
-      const f2 ex = vsub(dup2(1.f), tx), ey = vsub(dup2(1.f), ty);
-      const f2 mx = mk2(clip_mask(pr.u.x, wm1), clip_mask(pr.u.y, wm1)), my = mk2(clip_mask(pr.v.x, hm1), clip_mask(pr.v.y, hm1));
-      const f2 eym = vmul(ey, mx), tym = vmul(ty, mx), exm = vmul(ex, my), txm = vmul(tx, my);
-      const int ridx = (row0 + k + 2) * RW + col + 2;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float* S0 = src_b[0] + c * plane + b0.o00;
-        const float* S1 = src_b[1] + c * plane + b1.o00;
-        const f2 nw = mk2(__ldg(S0), __ldg(S1)), ne = mk2(__ldg(S0 + 1), __ldg(S1 + 1));
-        const f2 sw = mk2(__ldg(S0 + W), __ldg(S1 + W)), se = mk2(__ldg(S0 + W + 1), __ldg(S1 + W + 1));
-        sm.x[c][ridx] = vfma(se, wse, vfma(sw, wsw, vfma(ne, wne, vmul(nw, wnw))));
-        ddx[k][c] = vfma(vsub(se, sw), tym, vmul(vsub(ne, nw), eym));      // bilin_ddx * clip mask
-        ddy[k][c] = vfma(vsub(se, ne), txm, vmul(vsub(sw, nw), exm));      // bilin_ddy * clip mask
-      }
     }
-    // ---- phase 1b: halo ring (top 2 rows, bottom 2 rows, then left/right 2 columns of the tile rows)
-    for (int hidx = tid; hidx < HALO; hidx += NT) {
-      int i, j;
-      if (hidx < 2 * RW) {
-        i = hidx / RW;
-        j = hidx - i * RW;
-      } else if (hidx < 4 * RW) {
-        const int t = hidx - 2 * RW;
-        i = TH + 2 + t / RW;
-        j = t % RW;
-      } else {
-        const int t = hidx - 4 * RW;
-        i = 2 + t / 4;
-        const int jj = t % 4;
-        j = jj < 2 ? jj : TW + jj;
+    {
+      f2 u0[3], u1[3];
+      const int wid = tid >> 5;
+      // halo rows 0, 1, RH-2, RH-1: two each for the upper two warps (the lower two take the extra columns)
+      if (wid >= NT / 32 - 2) {
+        const int base = (wid == NT / 32 - 2) ? 0 : Smem::RH - 2;
+        gather_row(base, std::false_type{}, u0, u1);
+        gather_row(base + 1, std::false_type{}, u0, u1);
       }
-      const int py = reflect_index(y0 - 2 + i, H), px = reflect_index(x0 - 2 + j, W);
-      const float d = depth_at(py, px);
-      f2 A[3];
-      const ProjT<f2> pr = project_pixel(sm.G, d, px, py, a.eps, wmax, hmax, A);
-      const Bilin b0 = bilin_setup(pr.ix.x, pr.iy.x, W), b1 = bilin_setup(pr.ix.y, pr.iy.y, W);
-      const f2 wnw = mk2(b0.wnw, b1.wnw), wne = mk2(b0.wne, b1.wne), wsw = mk2(b0.wsw, b1.wsw), wse = mk2(b0.wse, b1.wse);
-      const int ridx = i * RW + j;
+      // halo columns 0, 1, RW-2, RW-1 of every region row
+      for (int e = tid; e < 4 * Smem::RH && tid < NT - 64; e += NT - 64) {   // taken by the lower warps (no halo rows)
+        const int i = e >> 2, jj = e & 3, j = jj < 2 ? jj : RW - 4 + jj;
+        const int py = reflect_index(y0 - 2 + i, H);
+        ColCtx ce = make_col(sm.G, x0 - 2 + j, W);
+        UpCoef cy;
+        float d;
+        if (same_res) {
+          d = depth_of<true>(disp_b, W, sc.ws, py, ce, cy, a.disp_lo, a.disp_range);
+        } else {
+          ce.cx = up_coef(ce.px, sc.ws, sc.up_sx);
+          cy = up_coef(py, sc.hs, sc.up_sy);
+          d = depth_of<false>(disp_b, W, sc.ws, py, ce, cy, a.disp_lo, a.disp_range);
+        }
+        f2 A[3], val[3];
+        const ProjT<f2> pr = project_cell(sm.G, ce, py, d, a.eps, wmax, hmax, A);
+        sample_sources<false>(sp, W, pr, wm1, hm1, val, u0, u1);
+        const int ridx = i * RW + j;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float* S0 = src_b[0] + c * plane + b0.o00;
-        const float* S1 = src_b[1] + c * plane + b1.o00;
-        const f2 nw = mk2(__ldg(S0), __ldg(S1)), ne = mk2(__ldg(S0 + 1), __ldg(S1 + 1));
-        const f2 sw = mk2(__ldg(S0 + W), __ldg(S1 + W)), se = mk2(__ldg(S0 + W + 1), __ldg(S1 + W + 1));
-        sm.x[c][ridx] = vfma(se, wse, vfma(sw, wsw, vfma(ne, wne, vmul(nw, wnw))));
+        for (int c = 0; c < 3; ++c) sm.x[c][ridx] = val[c];
       }
     }
     // ---- per-q weights  g_r * mask(q) * [sel(q) == lane]   (zero outside the image)
@@ -292,7 +282,7 @@ __global__ void __launch_bounds__(NT, (NT >= 256 ? 2 : 4)) vsl_backward_kernel(c
       if (gy < H && gx_own < W) {
         const size_t o = (size_t)b * plane + (size_t)gy * W + gx_own;
         f2 A[3];
-        const ProjT<f2> pr = project_pixel(sm.G, dep[k], gx_own, gy, a.eps, wmax, hmax, A);
+        const ProjT<f2> pr = project_cell(sm.G, col_own, gy, dep[k], a.eps, wmax, hmax, A);
         const f2 gc0 = vmul(gu[k], pr.rz), gc1 = vmul(gv[k], pr.rz);
         const f2 gc2 = vneg(vmul(vfma(gu[k], pr.u, vmul(gv[k], pr.v)), pr.rz));
         const f2 gd2 = vfma(gc2, A[2], vfma(gc1, A[1], vmul(gc0, A[0])));
@@ -317,7 +307,12 @@ __global__ void __launch_bounds__(NT, (NT >= 256 ? 2 : 4)) vsl_backward_kernel(c
         }
         const float g_dup = g * ddepth_ddisp(dep[k], a.disp_range);
         if (same_res) {
-          gd_b[(size_t)gy * W + gx_own] += g_dup;           // sole owner of this element (after smooth_backward)
+          // deterministic mode: sole owner of this element, after smooth_backward's overwrite; otherwise the
+          // smoothness CTAs of this very launch add into the same zero-initialised element (two commutative adds)
+          if (a.flags & PPEA_F_DETERMINISTIC)
+            gd_b[(unsigned)gy * (unsigned)W + (unsigned)gx_own] += g_dup;
+          else
+            atomicAdd(gd_b + ((unsigned)gy * (unsigned)W + (unsigned)gx_own), g_dup);
         } else if (sc.grad_dup) {
           sc.grad_dup[o] = g_dup;                           // deterministic mode: gathered by a second pass
         } else if (g_dup != 0.f) {
@@ -365,7 +360,7 @@ cudaError_t launch_vsl_backward(const VslArgs& a, cudaStream_t stream) {
   using Smem = BwdSmem<kBwdTileW, kBwdTileH>;
   static_assert(sizeof(Smem) <= 227 * 1024, "shared memory tile too large");
   static_assert(kBwdThreads / 32 <= 8, "red[] rows hold 8 warps");
-  const int nblk = a.B * a.tiles_x * a.tiles_y;
+  const int nblk = a.B * a.tiles_x * a.tiles_y + ((a.flags & PPEA_F_DETERMINISTIC) ? 0 : a.S * a.B * kSmoothChunks);
   cudaError_t e;
   if (a.flags & PPEA_F_GRAD_POSE) {
     auto kern = vsl_backward_kernel<kBwdTileW, kBwdTileH, kBwdThreads, true>;
@@ -433,22 +428,24 @@ cudaError_t launch_upsample_gather(const VslArgs& a, cudaStream_t stream) {
 // Pose gradient: fixed-order reduction of the per-CTA d L / d P_f partials of each
 // image, then d L / d T_f = K[:3,:]^T @ dL/dP_f  (autograd of layers.py:185).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) pose_finish_kernel(const __grid_constant__ VslArgs a, int tiles) {
+__global__ void __launch_bounds__(32 * 24) pose_finish_kernel(const __grid_constant__ VslArgs a, int tiles) {
   __shared__ double Q[24];    // [f][r][(x, y, 1) moments of gc_r*depth, sum gc_r]
   __shared__ double gP[24];   // dL/dP_f, row-major 3x4
-  const int b = blockIdx.x, tid = threadIdx.x;
-  if (tid < 24) {
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, e = tid >> 5;   // warp e reduces entry e over the tiles
+  {
     double t = 0;
-    const float* p = a.pose_partials + (size_t)b * tiles * 24 + tid;
-    for (int i = 0; i < tiles; ++i) t += (double)p[(size_t)i * 24];
-    Q[tid] = t;
+    const float* p = a.pose_partials + (size_t)b * tiles * 24 + e;
+    for (int i = lane; i < tiles; i += 32) t += (double)p[(size_t)i * 24];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) Q[e] = t;
   }
-  __syncwarp();
+  __syncthreads();
   const float* K = a.K + b * 16;
   const float* iK = a.inv_K + b * 16;
   if (tid < 24) {
     // cam = depth * inv_K[:3,:3] (x,y,1)  =>  dL/dP[r][j] = sum_k Q[r][k] inv_K[j][k];  dL/dP[r][3] = sum gc_r
-    const int f = tid / 12, e = tid % 12, r = e / 4, j = e % 4;
+    const int f = tid / 12, ee = tid % 12, r = ee / 4, j = ee % 4;
     double t;
     if (j == 3) {
       t = Q[f * 12 + r * 4 + 3];
@@ -458,18 +455,18 @@ __global__ void __launch_bounds__(32) pose_finish_kernel(const __grid_constant__
     }
     gP[tid] = t;
   }
-  __syncwarp();
-  {
-    const int f = tid / 16, e = tid % 16, i = e / 4, j = e % 4;
+  __syncthreads();
+  if (tid < 32) {
+    const int f = tid / 16, ee = tid % 16, i = ee / 4, j = ee % 4;
     // (K3^T gP)[i][j] = sum_r K[r][i] * gP[r][j], r = 0..2
     double t = 0;
     for (int r = 0; r < 3; ++r) t += (double)K[r * 4 + i] * gP[f * 12 + r * 4 + j];
-    a.grad_T[f][b * 16 + e] = (float)t;
+    a.grad_T[f][b * 16 + ee] = (float)t;
   }
 }
 
 cudaError_t launch_pose_finish(const VslArgs& a, int nblk_bwd, cudaStream_t stream) {
-  pose_finish_kernel<<<a.B, 32, 0, stream>>>(a, nblk_bwd / a.B);
+  pose_finish_kernel<<<a.B, 32 * 24, 0, stream>>>(a, nblk_bwd / a.B);
   return cudaGetLastError();
 }
 

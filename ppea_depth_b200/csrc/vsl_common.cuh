@@ -60,7 +60,7 @@ constexpr int kBwdTileW = 32;
 constexpr int kBwdTileH = 16;
 constexpr int kBwdThreads = 128;
 constexpr int kSmoothChunks = 32;     // blocks per image in the smoothness kernels
-constexpr int kSmoothThreads = 256;
+constexpr int kSmoothThreads = 128;
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -95,8 +95,6 @@ inline BwdWorkspace bwd_workspace(int B, int H, int W, int S, unsigned flags) {
 
 cudaError_t launch_vsl_forward(const VslArgs& a, cudaStream_t stream);
 cudaError_t launch_vsl_backward(const VslArgs& a, cudaStream_t stream);
-cudaError_t launch_smooth_disp_sums(const VslArgs& a, cudaStream_t stream);
-cudaError_t launch_smooth_forward(const VslArgs& a, cudaStream_t stream);
 cudaError_t launch_vsl_finish(const VslArgs& a, int nblk_fwd, cudaStream_t stream);
 cudaError_t launch_smooth_backward(const VslArgs& a, cudaStream_t stream);
 cudaError_t launch_upsample_gather(const VslArgs& a, cudaStream_t stream);

@@ -16,6 +16,8 @@
 // compulsory, L1/L2-resident after the first scale) + noise 4 B + disp 4/4^s B in; depth 4 B +
 // sel 1 B (+ loss 4 B on request) out.
 #include "vsl_common.cuh"
+#include "smooth.cuh"
+#include "vsl_gather.cuh"
 
 namespace ppea {
 
@@ -69,6 +71,51 @@ __device__ __forceinline__ void photometric_pass(const f2* __restrict__ xs, cons
   }
 }
 
+// Gather pass of one scale: fills the (source 0, source 1) planes of the tile + 1-pixel halo and
+// writes the tile's depth.  Warp w walks region rows w, w+nw, ... with lane == tile column; the two
+// halo columns are a flat list of extra cells taken by the upper warps.
+template <int TW, int TH, int NT, bool SAME_RES, class Smem>
+__device__ __forceinline__ void fwd_gather(Smem& sm, const VslArgs& a, const ScaleArgs& sc, const float* __restrict__ disp_b,
+                                           const SrcPlanes& sp, float* __restrict__ depth_b,
+                                           int x0, int y0, int col, int wid, int tid, ColCtx cc, float wmax, float hmax) {
+  constexpr int EW = Smem::EW, EH = Smem::EH, NW = NT / 32;
+  const int H = a.H, W = a.W;
+  const int gx_own = x0 + col;
+  f2 val[3], unused0[3], unused1[3];
+  if (!SAME_RES) cc.cx = up_coef(cc.px, sc.ws, sc.up_sx);
+  for (int i = wid; i < EH; i += NW) {
+    const int gy = y0 - 1 + i, py = reflect_index(gy, H);
+    UpCoef cy;
+    if (!SAME_RES) cy = up_coef(py, sc.hs, sc.up_sy);
+    const float dep = depth_of<SAME_RES>(disp_b, W, sc.ws, py, cc, cy, a.disp_lo, a.disp_range);
+    if (i >= 1 && i <= TH && gy < H && gx_own < W) depth_b[(unsigned)gy * (unsigned)W + (unsigned)gx_own] = dep;
+    f2 A[3];
+    const ProjT<f2> pr = project_cell(sm.G, cc, py, dep, a.eps, wmax, hmax, A);
+    sample_sources<false>(sp, W, pr, 0.f, 0.f, val, unused0, unused1);
+    const int idx = i * EW + col + 1;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) sm.x[c][idx] = val[c];
+  }
+  const int e = tid - (NT - 2 * 32);        // extra cells go to the last two warps (they own fewer rows)
+  if (e >= 0 && e < 2 * EH) {
+    const int i = e >> 1, j = (e & 1) ? EW - 1 : 0;
+    const int py = reflect_index(y0 - 1 + i, H);
+    ColCtx ce = make_col(sm.G, x0 - 1 + j, W);
+    UpCoef cy;
+    if (!SAME_RES) {
+      ce.cx = up_coef(ce.px, sc.ws, sc.up_sx);
+      cy = up_coef(py, sc.hs, sc.up_sy);
+    }
+    const float dep = depth_of<SAME_RES>(disp_b, W, sc.ws, py, ce, cy, a.disp_lo, a.disp_range);
+    f2 A[3];
+    const ProjT<f2> pr = project_cell(sm.G, ce, py, dep, a.eps, wmax, hmax, A);
+    sample_sources<false>(sp, W, pr, 0.f, 0.f, val, unused0, unused1);
+    const int idx = i * EW + j;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) sm.x[c][idx] = val[c];
+  }
+}
+
 template <int TW, int TH, int NT>
 __global__ void __launch_bounds__(NT, 5) vsl_forward_kernel(const __grid_constant__ VslArgs a) {
   using Smem = FwdSmem<TW, TH>;
@@ -78,6 +125,11 @@ __global__ void __launch_bounds__(NT, 5) vsl_forward_kernel(const __grid_constan
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
 
+  const int n_tiles = a.B * a.tiles_x * a.tiles_y;
+  if ((int)blockIdx.x >= n_tiles) {        // extra CTAs: the smoothness term of every scale (smooth.cuh)
+    smooth_forward_role(a, blockIdx.x - n_tiles, reinterpret_cast<float*>(smem_raw));
+    return;
+  }
   const int tid = threadIdx.x;
   int blk = blockIdx.x;
   const int tx = blk % a.tiles_x;
@@ -129,6 +181,8 @@ __global__ void __launch_bounds__(NT, 5) vsl_forward_kernel(const __grid_constan
   const int gx_own = x0 + col;
   const float one_minus_aug = (multi && (a.flags & PPEA_F_MATCH_AUG)) ? 1.f - a.aug_mask[b] : 1.f;
   const int lane = tid & 31, wid = tid >> 5;
+  const ColCtx col_own = make_col(sm.G, gx_own, W);     // this thread's tile column == region column col + 1
+  const SrcPlanes sp = make_planes(src_b[0], src_b[1], plane);
 
 #pragma unroll 1
   for (int s = 0; s < a.S; ++s) {
@@ -136,36 +190,11 @@ __global__ void __launch_bounds__(NT, 5) vsl_forward_kernel(const __grid_constan
     // ---- gather pass: depth, projection into both sources, bilinear samples -> x planes
     {
       const float* disp_b = sc.disp + (size_t)b * sc.hs * sc.ws;
-      const bool same_res = (sc.hs == H && sc.ws == W);
-      for (int idx = tid; idx < PLANE; idx += NT) {
-        const int i = idx / EW, j = idx - i * EW;
-        const int gy = y0 - 1 + i, gx = x0 - 1 + j;
-        const int py = reflect_index(gy, H), px = reflect_index(gx, W);
-        float dup;
-        if (same_res) {
-          dup = __ldg(disp_b + (size_t)py * W + px);
-        } else {
-          const UpCoef cy = up_coef(py, sc.hs, sc.up_sy), cx = up_coef(px, sc.ws, sc.up_sx);
-          dup = up_sample(disp_b, sc.ws, cy, cx);
-        }
-        const float dep = depth_from_disp(dup, a.disp_lo, a.disp_range);
-        if (i >= 1 && i <= TH && j >= 1 && j <= TW && gy < H && gx < W) sc.depth[(size_t)b * plane + (size_t)gy * W + gx] = dep;
-        const f2 fx = dup2(int_to_float(px)), fy = dup2(int_to_float(py));
-        const f2 A0 = vfma(sm.G[1], fy, vfma(sm.G[0], fx, sm.G[2]));
-        const f2 A1 = vfma(sm.G[4], fy, vfma(sm.G[3], fx, sm.G[5]));
-        const f2 A2 = vfma(sm.G[7], fy, vfma(sm.G[6], fx, sm.G[8]));
-        const ProjT<f2> pr = project_fast(dep, A0, A1, A2, sm.G[9], sm.G[10], sm.G[11], a.eps, wmax, hmax);
-        const Bilin b0 = bilin_setup(pr.ix.x, pr.iy.x, W), b1 = bilin_setup(pr.ix.y, pr.iy.y, W);
-        const f2 wnw = mk2(b0.wnw, b1.wnw), wne = mk2(b0.wne, b1.wne), wsw = mk2(b0.wsw, b1.wsw), wse = mk2(b0.wse, b1.wse);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float* S0 = src_b[0] + c * plane + b0.o00;
-          const float* S1 = src_b[1] + c * plane + b1.o00;
-          const f2 nw = mk2(__ldg(S0), __ldg(S1)), ne = mk2(__ldg(S0 + 1), __ldg(S1 + 1));
-          const f2 sw = mk2(__ldg(S0 + W), __ldg(S1 + W)), se = mk2(__ldg(S0 + W + 1), __ldg(S1 + W + 1));
-          sm.x[c][idx] = vfma(se, wse, vfma(sw, wsw, vfma(ne, wne, vmul(nw, wnw))));
-        }
-      }
+      float* depth_b = sc.depth + (size_t)b * plane;
+      if (sc.hs == H && sc.ws == W)
+        fwd_gather<TW, TH, NT, true>(sm, a, sc, disp_b, sp, depth_b, x0, y0, col, wid, tid, col_own, wmax, hmax);
+      else
+        fwd_gather<TW, TH, NT, false>(sm, a, sc, disp_b, sp, depth_b, x0, y0, col, wid, tid, col_own, wmax, hmax);
     }
     __syncthreads();
 
@@ -223,7 +252,7 @@ cudaError_t launch_vsl_forward(const VslArgs& a, cudaStream_t stream) {
   static_assert(sizeof(Smem) <= 227 * 1024, "shared memory tile too large");
   cudaError_t e = ensure_dynamic_smem(kern, (int)sizeof(Smem));
   if (e != cudaSuccess) return e;
-  const int nblk = a.B * a.tiles_x * a.tiles_y;
+  const int nblk = a.B * a.tiles_x * a.tiles_y + a.S * a.B * kSmoothChunks;
   kern<<<nblk, kFwdThreads, sizeof(Smem), stream>>>(a);
   return cudaGetLastError();
 }
@@ -231,80 +260,110 @@ cudaError_t launch_vsl_forward(const VslArgs& a, cudaStream_t stream) {
 // ---------------------------------------------------------------------------
 // finish: fixed-order reduction of every scale's block partials, masked mean,
 // consistency mean, smoothness and the multi-scale total (trainer.py:1113-1114,
-// 1132, 1145-1158).  A single CTA; the partial lists are a few thousand floats.
+// 1132, 1145-1158).  One CTA; warp w reduces the tile partials of scale w, then
+// the per-image smoothness sums; thread 0 assembles the loss vector.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) vsl_finish_kernel(const __grid_constant__ VslArgs a, int nblk) {
-  __shared__ double red[5][8];
-  __shared__ float scale_loss[kMaxScales];
+constexpr int kFinishWarps = 8;                          // warps per scale
+constexpr int kFinishThreads = 32 * kFinishWarps * kMaxScales;
+
+__global__ void __launch_bounds__(kFinishThreads) vsl_finish_kernel(const __grid_constant__ VslArgs a, int nblk) {
+  __shared__ double part[kMaxScales][kFinishWarps][3];
+  __shared__ double tot[kMaxScales][4];     // sum r*mask, sum mask, sum cons, normalised smoothness
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int stride = PPEA_SUMS_PER_SCALE + 4 * a.B;
-  for (int s = 0; s < a.S; ++s) {
-    const ScaleArgs& sc = a.sc[s];
-    float* row = a.sums + (size_t)s * stride;
-    const float* sws = a.smooth_ws + (size_t)s * a.B * kSmoothChunks * 3;
-    double v[5] = {0, 0, 0, 0, 0};
-    // per-image smoothness statistics (needed again by the backward), fixed order
-    for (int b = tid; b < a.B; b += 256) {
-      double ds = 0, sx = 0, sy = 0;
-      for (int c = 0; c < kSmoothChunks; ++c) {
-        ds += (double)sws[(b * kSmoothChunks + c) * 3 + 0];
-        sx += (double)sws[(b * kSmoothChunks + c) * 3 + 1];
-        sy += (double)sws[(b * kSmoothChunks + c) * 3 + 2];
-      }
-      float* img = row + PPEA_SUMS_PER_SCALE + 4 * b;
+  const int s = wid / kFinishWarps, w = wid % kFinishWarps;
+  const int stride = sums_stride(a.B);
+  if (s < a.S) {
+    // tile partials of scale s: 256 threads, independent loads (4 in flight per thread)
+    double v0 = 0, v1 = 0, v2 = 0;
+    const int t = w * 32 + lane, nt = kFinishWarps * 32;
+#pragma unroll 4
+    for (int i = t; i < nblk; i += nt) {
+      const float4 p = *reinterpret_cast<const float4*>(a.partials + ((size_t)i * a.S + s) * 4);
+      v0 += (double)p.x;
+      v1 += (double)p.y;
+      v2 += (double)p.z;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+      v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+      v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+    }
+    if (lane == 0) {
+      part[s][w][0] = v0;
+      part[s][w][1] = v1;
+      part[s][w][2] = v2;
+    }
+  }
+  // per-image smoothness sums (kept for the backward): one warp per (scale, image), one lane per chunk
+  static_assert(kSmoothChunks == 32, "one lane per chunk");
+  for (int pair = wid; pair < a.S * a.B; pair += kFinishThreads / 32) {
+    const int ps = pair / a.B, b = pair - ps * a.B;
+    const ScaleArgs& sc = a.sc[ps];
+    const float* sws = a.smooth_ws + ((size_t)ps * a.B + b) * kSmoothChunks * 3;
+    double ds = (double)sws[lane * 3 + 0], sx = (double)sws[lane * 3 + 1], sy = (double)sws[lane * 3 + 2];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ds += __shfl_xor_sync(0xffffffffu, ds, o);
+      sx += __shfl_xor_sync(0xffffffffu, sx, o);
+      sy += __shfl_xor_sync(0xffffffffu, sy, o);
+    }
+    if (lane == 0) {
+      float* img = a.sums + (size_t)ps * stride + PPEA_SUMS_PER_SCALE + 4 * b;
       img[0] = (float)ds;
       img[1] = (float)sx;
       img[2] = (float)sy;
-      img[3] = 0.f;
-      v[3] += sx;
-      v[4] += sy;
+      const float n_sx = (float)a.B * sc.hs * (sc.ws - 1), n_sy = (float)a.B * (sc.hs - 1) * sc.ws;
+      const float inv = 1.f / ((float)ds / (float)(sc.hs * sc.ws) + 1e-7f);
+      img[3] = inv * ((float)sx / n_sx + (float)sy / n_sy);      // image b's share of the normalised smoothness
     }
-    for (int i = tid; i < nblk; i += 256) {
-      const float* p = a.partials + ((size_t)i * a.S + s) * 4;
-      v[0] += (double)p[0];
-      v[1] += (double)p[1];
-      v[2] += (double)p[2];
+  }
+  __syncthreads();
+  if (s < a.S && w == 0 && lane == 0) {
+    float* row = a.sums + (size_t)s * stride;
+    double v[3] = {0, 0, 0}, v3 = 0, rawx = 0, rawy = 0;
+    for (int k = 0; k < kFinishWarps; ++k)
+      for (int j = 0; j < 3; ++j) v[j] += part[s][k][j];
+    for (int b = 0; b < a.B; ++b) {       // fixed order
+      const float* img = row + PPEA_SUMS_PER_SCALE + 4 * b;
+      rawx += (double)img[1];
+      rawy += (double)img[2];
+      v3 += (double)img[3];
     }
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
-      if (lane == 0) red[k][wid] = v[k];
-    }
-    __syncthreads();
-    if (tid == 0) {
-      double t[5];
-      for (int k = 0; k < 5; ++k) {
-        t[k] = 0;
-        for (int w = 0; w < 8; ++w) t[k] += red[k][w];
-      }
-      for (int k = 0; k < 5; ++k) row[k] = (float)t[k];
-      row[5] = row[6] = row[7] = 0.f;
-      const double n_px = (double)a.B * a.H * a.W;
-      const double n_sx = (double)a.B * sc.hs * (sc.ws - 1), n_sy = (double)a.B * (sc.hs - 1) * sc.ws;
-      const float reproj = (float)t[0] / ((float)t[1] + 1e-7f);
-      const float cons = (a.flags & PPEA_F_MULTI) ? (float)(t[2] / n_px) : 0.f;
-      const float smooth = (float)(t[3] / n_sx) + (float)(t[4] / n_sy);
+    tot[s][0] = v[0];
+    tot[s][1] = v[1];
+    tot[s][2] = v[2];
+    tot[s][3] = v3;
+    row[0] = (float)v[0];
+    row[1] = (float)v[1];
+    row[2] = (float)v[2];
+    row[3] = (float)rawx;
+    row[4] = (float)rawy;
+    row[5] = row[6] = row[7] = 0.f;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float total = 0.f;
+    const double n_px = (double)a.B * a.H * a.W;
+    for (int k = 0; k < a.S; ++k) {
+      const float reproj = (float)tot[k][0] / ((float)tot[k][1] + 1e-7f);
+      const float cons = (a.flags & PPEA_F_MULTI) ? (float)(tot[k][2] / n_px) : 0.f;
+      const float smooth = (float)tot[k][3];
       float loss = reproj + cons;
-      loss += a.disparity_smoothness * smooth / (float)(1 << (a.first_scale + s));
-      float* L = a.losses + 1 + s * PPEA_LOSSES_PER_SCALE;
+      loss += a.disparity_smoothness * smooth / (float)(1 << (a.first_scale + k));
+      float* L = a.losses + 1 + k * PPEA_LOSSES_PER_SCALE;
       L[0] = loss;
       L[1] = reproj;
       L[2] = cons;
       L[3] = smooth;
-      scale_loss[s] = loss;
+      total += loss;
     }
-    __syncthreads();
-  }
-  if (tid == 0) {
-    float total = 0.f;
-    for (int k = 0; k < a.S; ++k) total += scale_loss[k];
     a.losses[0] = total / (float)a.total_scales;
   }
 }
 
 cudaError_t launch_vsl_finish(const VslArgs& a, int nblk_fwd, cudaStream_t stream) {
-  vsl_finish_kernel<<<1, 256, 0, stream>>>(a, nblk_fwd);
+  vsl_finish_kernel<<<1, kFinishThreads, 0, stream>>>(a, nblk_fwd);
   return cudaGetLastError();
 }
 

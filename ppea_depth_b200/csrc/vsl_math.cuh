@@ -68,9 +68,11 @@ PPEA_HD float fma_rn(float a, float b, float c) {
   return fmaf(a, b, c);
 #endif
 }
-PPEA_HD float rcp_fast(float a) {      // MUFU.RCP (<= 1 ulp) on the device
+PPEA_HD float rcp_fast(float a) {      // one MUFU.RCP (<= 1 ulp) on the device
 #if defined(__CUDA_ARCH__)
-  return __fdividef(1.f, a);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
 #else
   return 1.f / a;
 #endif
@@ -224,15 +226,27 @@ PPEA_HD UpCoef up_coef(int dst, int in_size, float scale) {
 }
 
 PPEA_HD float up_sample(const float* __restrict__ d, int w_s, const UpCoef& cy, const UpCoef& cx) {
-  const float* r0 = d + (size_t)cy.i0 * w_s;
-  const float* r1 = d + (size_t)cy.i1 * w_s;
-  return cy.l0 * (cx.l0 * r0[cx.i0] + cx.l1 * r0[cx.i1]) + cy.l1 * (cx.l0 * r1[cx.i0] + cx.l1 * r1[cx.i1]);
+  // 32-bit element offsets from one base pointer: one IMAD.WIDE.U32 per address on the device
+  const unsigned r0 = (unsigned)cy.i0 * (unsigned)w_s, r1 = (unsigned)cy.i1 * (unsigned)w_s;
+  return cy.l0 * (cx.l0 * d[r0 + (unsigned)cx.i0] + cx.l1 * d[r0 + (unsigned)cx.i1]) +
+         cy.l1 * (cx.l0 * d[r1 + (unsigned)cx.i0] + cx.l1 * d[r1 + (unsigned)cx.i1]);
 }
 
 // ---------------------------------------------------------------- depth
 PPEA_HD float depth_from_disp(float disp, float lo, float range) {
   // layers.py:21-22: scaled = lo + range*disp (two torch ops => two roundings); depth = 1/scaled
   return div_rn(1.f, add_rn(lo, mul_rn(range, disp)));
+}
+// The kernels' version: MUFU.RCP + one Newton step (<= 1 ulp from the correctly rounded quotient)
+// instead of the ~11-instruction IEEE division sequence.
+PPEA_HD float depth_from_disp_fast(float disp, float lo, float range) {
+#if defined(__CUDA_ARCH__)
+  const float x = add_rn(lo, mul_rn(range, disp));
+  const float r = rcp_fast(x);
+  return fma_rn(r, fma_rn(-x, r, 1.f), r);
+#else
+  return depth_from_disp(disp, lo, range);
+#endif
 }
 // d depth / d disp = -range * depth^2
 PPEA_HD float ddepth_ddisp(float depth, float range) { return -range * depth * depth; }

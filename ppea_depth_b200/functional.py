@@ -141,7 +141,7 @@ def _fill_params(bundle, flags, T, disps, depth, loss_px, sel, grad_disp, sums, 
         sc.depth = depth[s].data_ptr()
         sc.loss_px = loss_px[s].data_ptr() if loss_px[s] is not None else None
         sc.sel = sel[s].data_ptr()
-        sc.grad_disp = grad_disp[s].data_ptr() if grad_disp is not None else None
+        sc.grad_disp = grad_disp[s].data_ptr() if grad_disp is not None else None   # forward: NULL => no pre-zeroing
     p.sums = sums.data_ptr()
     p.losses = losses.data_ptr()
     p.workspace = workspace.data_ptr()

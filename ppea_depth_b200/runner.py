@@ -56,6 +56,8 @@ class FusedPlan:
             self.grad_T = [torch.empty(B, 4, 4, **f32) for _ in range(2)] if self.grad_pose else None
             self.flags_fwd = cfg.flags(grad_pose=False)
             self.flags_bwd = cfg.flags(grad_pose=self.grad_pose)
+            if not cfg.deterministic:     # the forward zero-fills the persistent grad buffers on the fly
+                self.flags_bwd |= C.F_GRAD_PREZEROED
             self.ws_fwd = torch.empty(max(lib.ppea_vsl_workspace_bytes(B, H, W, S) // 4, 4), **f32)
             self.ws_bwd = torch.empty(max(lib.ppea_vsl_backward_workspace_bytes(B, H, W, S, self.flags_bwd) // 4, 4), **f32)
         self._p_fwd = self._params(self.flags_fwd)
@@ -74,14 +76,14 @@ class FusedPlan:
     # kernels launched by one forward / backward call (for bench.py's gpu_launches)
     @property
     def launches_forward(self):
-        return 4
+        return 2            # fused forward (tiles + smoothness CTAs), finish
 
     @property
     def launches_backward(self):
-        n = 2 + (1 if self.grad_pose else 0)
-        if self.cfg.deterministic:
-            n += sum(1 for d in self.disps if tuple(d.shape[-2:]) != (self.H, self.W))
-        return n
+        n = 1 + (1 if self.grad_pose else 0)     # fused backward (tiles + smoothness CTAs), pose finish
+        if self.cfg.deterministic:               # + smoothness backward + one upsample gather per coarse scale
+            n += 1 + sum(1 for d in self.disps if tuple(d.shape[-2:]) != (self.H, self.W))
+        return n                                 # (the non-deterministic path also enqueues S memset nodes)
 
     def _params(self, flags):
         cfg = self.cfg
@@ -156,8 +158,8 @@ class FusedPlan:
         self.graph.replay()
 
     # ---- per-stage device timing (bench.py's roofline leg) -------------------
-    FWD_STAGES = ("smooth_disp_sums", "vsl_forward_kernel", "smooth_forward", "finish")
-    BWD_STAGES = ("smooth_backward", "vsl_backward_kernel", "upsample_gather", "pose_finish")
+    FWD_STAGES = ("fwd_unused0", "vsl_forward_kernel", "fwd_unused1", "finish")
+    BWD_STAGES = ("grad_init", "vsl_backward_kernel", "upsample_gather", "pose_finish")
 
     def enable_trace(self):
         """Asks the library to record a CUDA event before/after every stage of forward and
