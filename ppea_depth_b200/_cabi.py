@@ -15,7 +15,7 @@ import sys
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(PKG_DIR, "csrc")
-LIB_PATH = os.path.join(PKG_DIR, "libppea_vsl.so")
+LIB_PATH = os.environ.get("PPEA_LIB") or os.path.join(PKG_DIR, "libppea_vsl.so")
 INCLUDE_DIR = os.path.join(os.path.dirname(PKG_DIR), "include")
 SOURCES = ("api.cu", "vsl_fwd.cu", "vsl_bwd.cu", "smooth.cu", "ops.cu")
 HEADERS = ("vsl_common.cuh", "vsl_math.cuh")

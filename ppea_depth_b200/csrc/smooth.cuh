@@ -53,6 +53,7 @@ __device__ __forceinline__ void smooth_forward_role(const VslArgs& a, int role, 
   const float* img = sc.color + (size_t)b * 3 * n;
   float* gz = sc.grad_disp ? sc.grad_disp + (size_t)b * n : nullptr;   // optional: pre-zero the backward's accumulator
   float sd = 0.f, sx = 0.f, sy = 0.f;
+#pragma unroll 2
   for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
     const int y = i / w, x = i - y * w;
     const float di = __ldg(d + i);
@@ -96,6 +97,7 @@ __device__ __forceinline__ void smooth_backward_role(const VslArgs& a, int role)
   const float* d = sc.disp + (size_t)b * n;
   const float* img = sc.color + (size_t)b * 3 * n;
   float* out = sc.grad_disp + (size_t)b * n;
+#pragma unroll 2
   for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
     const int y = i / w, x = i - y * w;
     const float di = __ldg(d + i);

@@ -37,7 +37,7 @@ template <int TW, int TH>
 struct BwdSmem {
   static constexpr int RW = TW + 4, RH = TH + 4, RP = RW * RH;   // value region (2-pixel halo)
   static constexpr int QW = TW + 2, QH = TH + 2, QP = QW * QH;   // coefficient region (1-pixel halo)
-  f2 y[3][RP];          // target, duplicated lanes
+  float y[3][RP];       // target (broadcast into both lanes at use)
   f2 x[3][RP];          // warped (source 0, source 1)
   f2 cf[3][QP];         // cA, cB, cC of the current channel
   f2 wq[QP];            // g_r * mask(q) * [sel(q) == lane]
@@ -45,8 +45,11 @@ struct BwdSmem {
   float red[24][8];
 };
 
+#ifndef PPEA_BWD_CTAS
+#define PPEA_BWD_CTAS 4
+#endif
 template <int TW, int TH, int NT, bool POSE>
-__global__ void __launch_bounds__(NT, (NT >= 256 ? 2 : 4)) vsl_backward_kernel(const __grid_constant__ VslArgs a) {
+__global__ void __launch_bounds__(NT, PPEA_BWD_CTAS) vsl_backward_kernel(const __grid_constant__ VslArgs a) {
   using Smem = BwdSmem<TW, TH>;
   constexpr int RW = Smem::RW, RP = Smem::RP, QW = Smem::QW, QP = Smem::QP;
   constexpr int R = (TW * TH) / NT;
@@ -55,13 +58,15 @@ __global__ void __launch_bounds__(NT, (NT >= 256 ? 2 : 4)) vsl_backward_kernel(c
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
 
-  const int n_tiles = a.B * a.tiles_x * a.tiles_y;
-  if ((int)blockIdx.x >= n_tiles) {        // extra CTAs (non-deterministic mode): smoothness gradient of every scale
-    smooth_backward_role<true>(a, blockIdx.x - n_tiles);
+  // non-deterministic mode: the first CTAs of the grid add the smoothness gradient of every scale (smooth.cuh)
+  const int n_smooth = (a.flags & PPEA_F_DETERMINISTIC) ? 0 : a.S * a.B * kSmoothChunks;
+  if ((int)blockIdx.x < n_smooth) {
+    smooth_backward_role<true>(a, blockIdx.x);
     return;
   }
   const int tid = threadIdx.x;
-  int blk = blockIdx.x;
+  int blk = blockIdx.x - n_smooth;
+  const int tile_id = blk;
   const int tx = blk % a.tiles_x;
   blk /= a.tiles_x;
   const int ty = blk % a.tiles_y;
@@ -88,7 +93,7 @@ __global__ void __launch_bounds__(NT, (NT >= 256 ? 2 : 4)) vsl_backward_kernel(c
     const int py = reflect_index(y0 - 2 + i, H), px = reflect_index(x0 - 2 + j, W);
     const size_t o = (size_t)py * W + px;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) sm.y[c][idx] = dup2(__ldg(tgt_b + c * plane + o));
+    for (int c = 0; c < 3; ++c) sm.y[c][idx] = __ldg(tgt_b + c * plane + o);
   }
   __syncthreads();
 
@@ -153,14 +158,15 @@ __global__ void __launch_bounds__(NT, (NT >= 256 ? 2 : 4)) vsl_backward_kernel(c
     {
       f2 u0[3], u1[3];
       const int wid = tid >> 5;
-      // halo rows 0, 1, RH-2, RH-1: two each for the upper two warps (the lower two take the extra columns)
-      if (wid >= NT / 32 - 2) {
-        const int base = (wid == NT / 32 - 2) ? 0 : Smem::RH - 2;
+      // halo rows 0,1 go to the first warp and RH-2,RH-1 to the last (adjacent to their own rows: L1 reuse);
+      // the four halo columns of every region row are a flat list taken by the middle warps
+      constexpr int NWB = NT / 32;
+      if (wid == 0 || wid == NWB - 1) {
+        const int base = (wid == 0) ? 0 : Smem::RH - 2;
         gather_row(base, std::false_type{}, u0, u1);
         gather_row(base + 1, std::false_type{}, u0, u1);
       }
-      // halo columns 0, 1, RW-2, RW-1 of every region row
-      for (int e = tid; e < 4 * Smem::RH && tid < NT - 64; e += NT - 64) {   // taken by the lower warps (no halo rows)
+      for (int e = tid - 32; e < 4 * Smem::RH && tid >= 32 && tid < NT - 32; e += NT - 64) {
         const int i = e >> 2, jj = e & 3, j = jj < 2 ? jj : RW - 4 + jj;
         const int py = reflect_index(y0 - 2 + i, H);
         ColCtx ce = make_col(sm.G, x0 - 2 + j, W);
@@ -215,12 +221,12 @@ __global__ void __launch_bounds__(NT, (NT >= 256 ? 2 : 4)) vsl_backward_kernel(c
           ad.cA = ad.cB = ad.cC = dup2(0.f);
           if (w.x != 0.f || w.y != 0.f) {
             const f2* xp = &sm.x[c][i * RW + j];
-            const f2* yp = &sm.y[c][i * RW + j];
+            const float* yp = &sm.y[c][i * RW + j];
             f2 hx[3], hxx[3], hxy[3], hy[3], hyy[3];
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy) {
               const f2 xa = xp[dy * RW], xb = xp[dy * RW + 1], xc = xp[dy * RW + 2];
-              const f2 ya = yp[dy * RW], yb = yp[dy * RW + 1], yc = yp[dy * RW + 2];
+              const f2 ya = dup2(yp[dy * RW]), yb = dup2(yp[dy * RW + 1]), yc = dup2(yp[dy * RW + 2]);
               row_sums_y<f2>(ya, yb, yc, hy[dy], hyy[dy]);
               row_sums_x<f2>(xa, xb, xc, ya, yb, yc, hx[dy], hxx[dy], hxy[dy]);
             }
@@ -253,7 +259,7 @@ __global__ void __launch_bounds__(NT, (NT >= 256 ? 2 : 4)) vsl_backward_kernel(c
             const int k = i - 2;
             const int gy = y0 + row0 + k;
             const int ridx = (row0 + k + 2) * RW + col + 2;
-            const f2 xv = sm.x[c][ridx], yv = sm.y[c][ridx];
+            const f2 xv = sm.x[c][ridx], yv = dup2(sm.y[c][ridx]);
             const f2 wl = sm.wq[(row0 + k + 1) * QW + col + 1];
             const f2 d = vsub(yv, xv);
             // L1 term:  -w * l1w * sign(y - x)
@@ -351,7 +357,7 @@ __global__ void __launch_bounds__(NT, (NT >= 256 ? 2 : 4)) vsl_backward_kernel(c
     if (tid < 24) {
       float t = 0.f;
       for (int w = 0; w < NT / 32; ++w) t += sm.red[tid][w];
-      a.pose_partials[(size_t)blockIdx.x * 24 + tid] = t;
+      a.pose_partials[(size_t)tile_id * 24 + tid] = t;
     }
   }
 }

@@ -26,7 +26,7 @@ struct FwdSmem {
   static constexpr int EW = TW + 2;
   static constexpr int EH = TH + 2;
   static constexpr int PLANE = EW * EH;
-  f2 y[3][PLANE];      // target, duplicated lanes
+  float y[3][PLANE];   // target (broadcast into both lanes at use: FFMA2 takes a scalar .F32 operand)
   f2 x[3][PLANE];      // (source 0, source 1): un-warped, then warped
   f2 G[12];            // per-source geometry M[0..8], t[0..2] (vsl_math.cuh Geom), lanes = sources
   float red[3][8];
@@ -35,7 +35,7 @@ struct FwdSmem {
 // Photometric loss 0.85*mean_c SSIM + 0.15*mean_c |y-x| (trainer.py:995-1007) of both sources
 // against the target for the R pixels (rows row0..row0+R-1, column col) of this thread.
 template <int R, int EW, int PLANE, bool WITH_CSUM>
-__device__ __forceinline__ void photometric_pass(const f2* __restrict__ xs, const f2* __restrict__ ys, int row0, int col,
+__device__ __forceinline__ void photometric_pass(const f2* __restrict__ xs, const float* __restrict__ ys, int row0, int col,
                                                  bool no_ssim, f2 (&acc)[R], f2 (&cs)[R]) {
 #pragma unroll
   for (int k = 0; k < R; ++k) {
@@ -46,13 +46,13 @@ __device__ __forceinline__ void photometric_pass(const f2* __restrict__ xs, cons
   const f2 w_ssim = dup2(PPEA_W_SSIM);
 #pragma unroll 1
   for (int c = 0; c < 3; ++c) {
-    const f2* yp = ys + c * PLANE + row0 * EW + col;
+    const float* yp = ys + c * PLANE + row0 * EW + col;
     const f2* xp = xs + c * PLANE + row0 * EW + col;
     f2 hy[3], hyy[3], hx[3], hxx[3], hxy[3];
 #pragma unroll
     for (int i = 0; i < R + 2; ++i) {
       const int s = i % 3;
-      const f2 y0 = yp[i * EW], y1 = yp[i * EW + 1], y2 = yp[i * EW + 2];
+      const f2 y0 = dup2(yp[i * EW]), y1 = dup2(yp[i * EW + 1]), y2 = dup2(yp[i * EW + 2]);
       const f2 x0 = xp[i * EW], x1 = xp[i * EW + 1], x2 = xp[i * EW + 2];
       row_sums_y<f2>(y0, y1, y2, hy[s], hyy[s]);
       row_sums_x<f2>(x0, x1, x2, y0, y1, y2, hx[s], hxx[s], hxy[s]);
@@ -83,11 +83,23 @@ __device__ __forceinline__ void fwd_gather(Smem& sm, const VslArgs& a, const Sca
   const int gx_own = x0 + col;
   f2 val[3], unused0[3], unused1[3];
   if (!SAME_RES) cc.cx = up_coef(cc.px, sc.ws, sc.up_sx);
-  for (int i = wid; i < EH; i += NW) {
+  // contiguous block of region rows per warp: a row's south corners are the next row's north corners (L1 reuse)
+  constexpr int RPW = (EH + NW - 1) / NW;
+  const int i_lo = wid * RPW, i_hi = (i_lo + RPW < EH) ? i_lo + RPW : EH;
+  float dnext = 0.f;
+  if (SAME_RES && i_lo < EH) dnext = __ldg(disp_b + ((unsigned)reflect_index(y0 - 1 + i_lo, H) * (unsigned)W + (unsigned)cc.px));
+  for (int i = i_lo; i < i_hi; ++i) {
     const int gy = y0 - 1 + i, py = reflect_index(gy, H);
     UpCoef cy;
-    if (!SAME_RES) cy = up_coef(py, sc.hs, sc.up_sy);
-    const float dep = depth_of<SAME_RES>(disp_b, W, sc.ws, py, cc, cy, a.disp_lo, a.disp_range);
+    float dep;
+    if (SAME_RES) {
+      const float dcur = dnext;
+      if (i + 1 < i_hi) dnext = __ldg(disp_b + ((unsigned)reflect_index(gy + 1, H) * (unsigned)W + (unsigned)cc.px));
+      dep = depth_from_disp_fast(dcur, a.disp_lo, a.disp_range);
+    } else {
+      cy = up_coef(py, sc.hs, sc.up_sy);
+      dep = depth_of<false>(disp_b, W, sc.ws, py, cc, cy, a.disp_lo, a.disp_range);
+    }
     if (i >= 1 && i <= TH && gy < H && gx_own < W) depth_b[(unsigned)gy * (unsigned)W + (unsigned)gx_own] = dep;
     f2 A[3];
     const ProjT<f2> pr = project_cell(sm.G, cc, py, dep, a.eps, wmax, hmax, A);
@@ -96,7 +108,7 @@ __device__ __forceinline__ void fwd_gather(Smem& sm, const VslArgs& a, const Sca
 #pragma unroll
     for (int c = 0; c < 3; ++c) sm.x[c][idx] = val[c];
   }
-  const int e = tid - (NT - 2 * 32);        // extra cells go to the last two warps (they own fewer rows)
+  const int e = tid - (NT - 2 * 32);        // extra cells go to the last two warps (the last warp owns fewer rows)
   if (e >= 0 && e < 2 * EH) {
     const int i = e >> 1, j = (e & 1) ? EW - 1 : 0;
     const int py = reflect_index(y0 - 1 + i, H);
@@ -125,13 +137,16 @@ __global__ void __launch_bounds__(NT, 5) vsl_forward_kernel(const __grid_constan
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
 
-  const int n_tiles = a.B * a.tiles_x * a.tiles_y;
-  if ((int)blockIdx.x >= n_tiles) {        // extra CTAs: the smoothness term of every scale (smooth.cuh)
-    smooth_forward_role(a, blockIdx.x - n_tiles, reinterpret_cast<float*>(smem_raw));
+  // The first CTAs of the grid run the smoothness term of every scale (smooth.cuh): scheduled first, their
+  // latency-bound work hides among the first wave of tile CTAs instead of stretching the tail.
+  const int n_smooth = a.S * a.B * kSmoothChunks;
+  if ((int)blockIdx.x < n_smooth) {
+    smooth_forward_role(a, blockIdx.x, reinterpret_cast<float*>(smem_raw));
     return;
   }
   const int tid = threadIdx.x;
-  int blk = blockIdx.x;
+  int blk = blockIdx.x - n_smooth;
+  const int tile_id = blk;
   const int tx = blk % a.tiles_x;
   blk /= a.tiles_x;
   const int ty = blk % a.tiles_y;
@@ -158,7 +173,7 @@ __global__ void __launch_bounds__(NT, 5) vsl_forward_kernel(const __grid_constan
     const int py = reflect_index(y0 - 1 + i, H), px = reflect_index(x0 - 1 + j, W);
     const size_t o = (size_t)py * W + px;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) sm.y[c][idx] = dup2(__ldg(tgt_b + c * plane + o));
+    for (int c = 0; c < 3; ++c) sm.y[c][idx] = __ldg(tgt_b + c * plane + o);
     if (automask) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) sm.x[c][idx] = mk2(__ldg(src_b[0] + c * plane + o), __ldg(src_b[1] + c * plane + o));
@@ -191,6 +206,10 @@ __global__ void __launch_bounds__(NT, 5) vsl_forward_kernel(const __grid_constan
     {
       const float* disp_b = sc.disp + (size_t)b * sc.hs * sc.ws;
       float* depth_b = sc.depth + (size_t)b * plane;
+#if defined(PPEA_ABLATE_GATHER)
+      if (tid < 0) {
+      } else
+#endif
       if (sc.hs == H && sc.ws == W)
         fwd_gather<TW, TH, NT, true>(sm, a, sc, disp_b, sp, depth_b, x0, y0, col, wid, tid, col_own, wmax, hmax);
       else
@@ -198,7 +217,29 @@ __global__ void __launch_bounds__(NT, 5) vsl_forward_kernel(const __grid_constan
     }
     __syncthreads();
 
+    // epilogue inputs come from DRAM: issue their loads before the (long) photometric pass
+    float pre[R], pre2[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const int gy = y0 + row0 + k;
+      pre[k] = pre2[k] = 0.f;
+      if (gy < H && gx_own < W) {
+        const unsigned o = (unsigned)gy * (unsigned)W + (unsigned)gx_own;
+        if (multi) {
+          pre[k] = (a.flags & PPEA_F_MOTION_MASK) ? __ldg(a.cons_mask + (size_t)b * plane + o) : 1.f;
+          pre2[k] = __ldg(sc.mono_depth + (size_t)b * plane + o);
+        } else if (automask && sc.noise) {
+          pre[k] = __ldg(sc.noise + (size_t)b * plane + o);
+        }
+      }
+    }
+
+#if defined(PPEA_ABLATE_PHOTO)
+#pragma unroll
+    for (int k = 0; k < R; ++k) { acc[k] = sm.x[0][(row0 + k + 1) * EW + col + 1]; cs[k] = sm.x[1][(row0 + k + 1) * EW + col + 1]; }
+#else
     photometric_pass<R, EW, PLANE, true>(&sm.x[0][0], &sm.y[0][0], row0, col, no_ssim, acc, cs);
+#endif
 
     // ---- epilogue: min over sources, selec_reproj, mask, per-pixel outputs, block sums
     float s_rm = 0.f, s_m = 0.f, s_c = 0.f;
@@ -211,12 +252,11 @@ __global__ void __launch_bounds__(NT, 5) vsl_forward_kernel(const __grid_constan
         unsigned bits = (unsigned)sl.src;
         float mask = 1.f;
         if (multi) {
-          if (a.flags & PPEA_F_MOTION_MASK) mask = a.cons_mask[o];
-          mask *= one_minus_aug;
+          mask = pre[k] * one_minus_aug;
           bits |= PPEA_SEL_AUTOMASK;
-          s_c += fabsf(sc.depth[o] - sc.mono_depth[o]) * (1.f - mask);
+          s_c += fabsf(sc.depth[o] - pre2[k]) * (1.f - mask);
         } else if (automask) {
-          const float idl = sc.noise ? add_rn(ident[k], mul_rn(sc.noise[o], 0.00001f)) : ident[k];   // trainer.py:1086-1087
+          const float idl = sc.noise ? add_rn(ident[k], mul_rn(pre[k], 0.00001f)) : ident[k];   // trainer.py:1086-1087
           const bool on = sl.r <= idl;                                         // argmin([r, id]) == 0
           mask = on ? 1.f : 0.f;
           if (on) bits |= PPEA_SEL_AUTOMASK;
@@ -241,7 +281,7 @@ __global__ void __launch_bounds__(NT, 5) vsl_forward_kernel(const __grid_constan
     if (tid < 3) {
       float t = 0.f;
       for (int w = 0; w < NT / 32; ++w) t += sm.red[tid][w];
-      a.partials[((size_t)blockIdx.x * a.S + s) * 4 + tid] = t;
+      a.partials[((size_t)tile_id * a.S + s) * 4 + tid] = t;
     }
   }
 }

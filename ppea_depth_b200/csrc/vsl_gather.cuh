@@ -98,8 +98,12 @@ __device__ __forceinline__ void sample_sources(const SrcPlanes& sp, int W, const
 #pragma unroll
   for (unsigned c = 0; c < 3; ++c) {
     const unsigned n0 = (unsigned)b.o0 + c * sp.plane, n1 = (unsigned)b.o1 + c * sp.plane;
+#if defined(PPEA_ABLATE_LOADS)
+    const f2 nw = mk2(__int_as_float(n0), __int_as_float(n1)), ne = nw, sw = mk2(__int_as_float(n0 + uW), __int_as_float(n1 + uW)), se = sw;
+#else
     const f2 nw = mk2(__ldg(sp.s0 + n0), __ldg(sp.s1 + n1)), ne = mk2(__ldg(sp.s0 + n0 + 1u), __ldg(sp.s1 + n1 + 1u));
     const f2 sw = mk2(__ldg(sp.s0 + n0 + uW), __ldg(sp.s1 + n1 + uW)), se = mk2(__ldg(sp.s0 + n0 + uW + 1u), __ldg(sp.s1 + n1 + uW + 1u));
+#endif
     val[c] = vfma(se, b.wse, vfma(sw, b.wsw, vfma(ne, b.wne, vmul(nw, b.wnw))));
     if (DERIV) {
       ddx[c] = vfma(vsub(se, sw), tym, vmul(vsub(ne, nw), eym));   // bilin_ddx * clip mask
