@@ -74,8 +74,12 @@ struct SrcPlanes {
 };
 __device__ __forceinline__ SrcPlanes make_planes(const float* s0, const float* s1, size_t plane) {
   SrcPlanes o;
-  o.s0 = s0;
-  o.s1 = s1;
+  // Opaque to the optimiser: otherwise it folds the (64-bit) image offset into every gather address and
+  // each of the 24 loads of a cell gets its own 64-bit add chain instead of one IMAD.WIDE.U32.
+  unsigned long long p0 = reinterpret_cast<unsigned long long>(s0), p1 = reinterpret_cast<unsigned long long>(s1);
+  asm volatile("" : "+l"(p0), "+l"(p1));
+  o.s0 = reinterpret_cast<const float*>(p0);
+  o.s1 = reinterpret_cast<const float*>(p1);
   o.plane = (unsigned)plane;
   return o;
 }
