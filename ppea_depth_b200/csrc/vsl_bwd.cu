@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(NT, PPEA_BWD_CTAS) vsl_backward_kernel(const _
       }
       f2 A[3], val[3];
       const ProjT<f2> pr = project_cell(sm.G, cc, py, d, a.eps, wmax, hmax, A);
-      sample_sources<decltype(want_deriv)::value>(sp, W, pr, wm1, hm1, val, dx, dy);
+      sample_sources<decltype(want_deriv)::value, false>(sp, W, pr, wm1, hm1, val, dx, dy);   // (shuffle-sharing costs registers this kernel does not have)
       const int ridx = i * RW + col + 2;
 #pragma unroll
       for (int c = 0; c < 3; ++c) sm.x[c][ridx] = val[c];
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(NT, PPEA_BWD_CTAS) vsl_backward_kernel(const _
         }
         f2 A[3], val[3];
         const ProjT<f2> pr = project_cell(sm.G, ce, py, d, a.eps, wmax, hmax, A);
-        sample_sources<false>(sp, W, pr, wm1, hm1, val, u0, u1);
+        sample_sources<false, false>(sp, W, pr, wm1, hm1, val, u0, u1);
         const int ridx = i * RW + j;
 #pragma unroll
         for (int c = 0; c < 3; ++c) sm.x[c][ridx] = val[c];

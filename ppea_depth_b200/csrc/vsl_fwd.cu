@@ -103,7 +103,7 @@ __device__ __forceinline__ void fwd_gather(Smem& sm, const VslArgs& a, const Sca
     if (i >= 1 && i <= TH && gy < H && gx_own < W) depth_b[(unsigned)gy * (unsigned)W + (unsigned)gx_own] = dep;
     f2 A[3];
     const ProjT<f2> pr = project_cell(sm.G, cc, py, dep, a.eps, wmax, hmax, A);
-    sample_sources<false>(sp, W, pr, 0.f, 0.f, val, unused0, unused1);
+    sample_sources<false, true>(sp, W, pr, 0.f, 0.f, val, unused0, unused1);
     const int idx = i * EW + col + 1;
 #pragma unroll
     for (int c = 0; c < 3; ++c) sm.x[c][idx] = val[c];
@@ -121,7 +121,7 @@ __device__ __forceinline__ void fwd_gather(Smem& sm, const VslArgs& a, const Sca
     const float dep = depth_of<SAME_RES>(disp_b, W, sc.ws, py, ce, cy, a.disp_lo, a.disp_range);
     f2 A[3];
     const ProjT<f2> pr = project_cell(sm.G, ce, py, dep, a.eps, wmax, hmax, A);
-    sample_sources<false>(sp, W, pr, 0.f, 0.f, val, unused0, unused1);
+    sample_sources<false, false>(sp, W, pr, 0.f, 0.f, val, unused0, unused1);
     const int idx = i * EW + j;
 #pragma unroll
     for (int c = 0; c < 3; ++c) sm.x[c][idx] = val[c];

@@ -86,7 +86,12 @@ __device__ __forceinline__ SrcPlanes make_planes(const float* s0, const float* s
 
 // Samples the three channels of both sources at `pr`; optionally also d value / d (u, v) with the
 // border-clip masks folded in (GridSampler.h clip_coordinates_set_grad).
-template <bool DERIV>
+// SHARE: the warp's lanes are horizontally adjacent pixels of one row (and all 32 are active).  With a
+// smooth flow lane j+1 samples one pixel to the right of lane j, so its west corners ARE lane j's east
+// corners: those come by warp shuffle and only lanes where the footprints do not line up (flow
+// discontinuities, lane 31) load them.  Halves the gather traffic through the L1 data pipe, the busiest
+// unit of both kernels (ncu: l1tex data-pipe wavefronts ~60 % of peak).
+template <bool DERIV, bool SHARE>
 __device__ __forceinline__ void sample_sources(const SrcPlanes& sp, int W, const ProjT<f2>& pr, float wm1, float hm1,
                                                f2 (&val)[3], f2 (&ddx)[3], f2 (&ddy)[3]) {
   const Bilin2 b = bilin_setup2(pr, W);
@@ -99,15 +104,34 @@ __device__ __forceinline__ void sample_sources(const SrcPlanes& sp, int W, const
     txm = vmul(b.tx, my);
   }
   const unsigned uW = (unsigned)W;
+  bool own0 = true, own1 = true;      // must this lane load its own east corners?
+  if (SHARE) {
+    const int lane = threadIdx.x & 31;
+    const int n0 = __shfl_down_sync(0xffffffffu, b.o0, 1), n1 = __shfl_down_sync(0xffffffffu, b.o1, 1);
+    own0 = (lane == 31) || (n0 != b.o0 + 1);
+    own1 = (lane == 31) || (n1 != b.o1 + 1);
+  }
 #pragma unroll
   for (unsigned c = 0; c < 3; ++c) {
     const unsigned n0 = (unsigned)b.o0 + c * sp.plane, n1 = (unsigned)b.o1 + c * sp.plane;
-#if defined(PPEA_ABLATE_LOADS)
-    const f2 nw = mk2(__int_as_float(n0), __int_as_float(n1)), ne = nw, sw = mk2(__int_as_float(n0 + uW), __int_as_float(n1 + uW)), se = sw;
-#else
-    const f2 nw = mk2(__ldg(sp.s0 + n0), __ldg(sp.s1 + n1)), ne = mk2(__ldg(sp.s0 + n0 + 1u), __ldg(sp.s1 + n1 + 1u));
-    const f2 sw = mk2(__ldg(sp.s0 + n0 + uW), __ldg(sp.s1 + n1 + uW)), se = mk2(__ldg(sp.s0 + n0 + uW + 1u), __ldg(sp.s1 + n1 + uW + 1u));
-#endif
+    const f2 nw = mk2(__ldg(sp.s0 + n0), __ldg(sp.s1 + n1));
+    const f2 sw = mk2(__ldg(sp.s0 + n0 + uW), __ldg(sp.s1 + n1 + uW));
+    f2 ne, se;
+    if (SHARE) {
+      ne = mk2(__shfl_down_sync(0xffffffffu, nw.x, 1), __shfl_down_sync(0xffffffffu, nw.y, 1));
+      se = mk2(__shfl_down_sync(0xffffffffu, sw.x, 1), __shfl_down_sync(0xffffffffu, sw.y, 1));
+      if (own0) {
+        ne.x = __ldg(sp.s0 + n0 + 1u);
+        se.x = __ldg(sp.s0 + n0 + uW + 1u);
+      }
+      if (own1) {
+        ne.y = __ldg(sp.s1 + n1 + 1u);
+        se.y = __ldg(sp.s1 + n1 + uW + 1u);
+      }
+    } else {
+      ne = mk2(__ldg(sp.s0 + n0 + 1u), __ldg(sp.s1 + n1 + 1u));
+      se = mk2(__ldg(sp.s0 + n0 + uW + 1u), __ldg(sp.s1 + n1 + uW + 1u));
+    }
     val[c] = vfma(se, b.wse, vfma(sw, b.wsw, vfma(ne, b.wne, vmul(nw, b.wnw))));
     if (DERIV) {
       ddx[c] = vfma(vsub(se, sw), tym, vmul(vsub(ne, nw), eym));   // bilin_ddx * clip mask
