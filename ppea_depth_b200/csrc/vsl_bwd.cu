@@ -46,14 +46,14 @@ struct BwdSmem {
 };
 
 #ifndef PPEA_BWD_CTAS
-#define PPEA_BWD_CTAS 4
+#define PPEA_BWD_CTAS (kBwdThreads >= 256 ? 2 : 4)
 #endif
 template <int TW, int TH, int NT, bool POSE>
 __global__ void __launch_bounds__(NT, PPEA_BWD_CTAS) vsl_backward_kernel(const __grid_constant__ VslArgs a) {
   using Smem = BwdSmem<TW, TH>;
   constexpr int RW = Smem::RW, RP = Smem::RP, QW = Smem::QW, QP = Smem::QP;
   constexpr int R = (TW * TH) / NT;
-  static_assert(TW == 32 && NT == 128 && TH == 16, "the gather/row mapping assumes lane == tile column, 4 warps x 4 rows");
+  static_assert(TW == 32 && (NT / 32) * R == TH && NT >= 128, "the gather/row mapping assumes lane == tile column and R rows per warp");
   static_assert(NT % TW == 0 && (TW * TH) % NT == 0, "tile/thread mismatch");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);

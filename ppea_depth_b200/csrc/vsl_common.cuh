@@ -58,7 +58,10 @@ constexpr int kFwdTileH = 16;
 constexpr int kFwdThreads = 128;
 constexpr int kBwdTileW = 32;
 constexpr int kBwdTileH = 16;
-constexpr int kBwdThreads = 128;
+#ifndef PPEA_BWD_THREADS
+#define PPEA_BWD_THREADS 128
+#endif
+constexpr int kBwdThreads = PPEA_BWD_THREADS;
 constexpr int kSmoothChunks = 32;     // blocks per image in the smoothness kernels
 constexpr int kSmoothThreads = 128;
 
