@@ -41,31 +41,89 @@ __device__ __forceinline__ void smooth_role_ids(const VslArgs& a, int role, int&
   s = role / a.B;
 }
 
+// A role CTA owns one chunk of one image of one scale: a strip of blockDim.x columns x a band of rows.
+// Threads walk DOWN their column: the row just loaded serves as "down neighbour" of the previous row and as
+// "current" of the next, and the right neighbour comes by warp shuffle, so a pixel costs one 4-word load
+// (disp + 3 colour channels) instead of 12-29.
+struct SmoothChunk {
+  int x, y_lo, y_hi;      // column of this thread (may be >= w), row band
+  bool active;            // chunk id maps to work
+};
+__device__ __forceinline__ SmoothChunk smooth_chunk(int w, int h, int chunk) {
+  const int bd = blockDim.x;
+  const int strips = (w + bd - 1) / bd;                    // <= kSmoothChunks is checked by the API (w <= 32 * 128)
+  const int bands = kSmoothChunks / strips > 0 ? kSmoothChunks / strips : 1;
+  const int rows = (h + bands - 1) / bands;
+  SmoothChunk c;
+  const int strip = chunk % strips, band = chunk / strips;
+  c.active = band < bands && band * rows < h;
+  c.x = strip * bd + threadIdx.x;
+  c.y_lo = band * rows;
+  c.y_hi = c.y_lo + rows < h ? c.y_lo + rows : h;
+  return c;
+}
+
+struct SmoothPx {
+  float d, i0, i1, i2;
+};
+__device__ __forceinline__ SmoothPx smooth_load(const float* __restrict__ d, const float* __restrict__ img, unsigned plane,
+                                                unsigned o, bool ok) {
+  SmoothPx p = {0.f, 0.f, 0.f, 0.f};
+  if (ok) {
+    p.d = __ldg(d + o);
+    p.i0 = __ldg(img + o);
+    p.i1 = __ldg(img + plane + o);
+    p.i2 = __ldg(img + 2u * plane + o);
+  }
+  return p;
+}
+__device__ __forceinline__ SmoothPx smooth_shfl_down(const SmoothPx& p) {
+  SmoothPx q;
+  q.d = __shfl_down_sync(0xffffffffu, p.d, 1);
+  q.i0 = __shfl_down_sync(0xffffffffu, p.i0, 1);
+  q.i1 = __shfl_down_sync(0xffffffffu, p.i1, 1);
+  q.i2 = __shfl_down_sync(0xffffffffu, p.i2, 1);
+  return q;
+}
+__device__ __forceinline__ float smooth_weight(const SmoothPx& a, const SmoothPx& b) {
+  // exp(-mean_c |I_a - I_b|)   (layers.py:217-221)
+  return __expf(-(fabsf(a.i0 - b.i0) + fabsf(a.i1 - b.i1) + fabsf(a.i2 - b.i2)) * (1.f / 3.f));
+}
+
 // Forward role: raw sums of one chunk -> smooth_ws[(s, b, chunk)][3] = (sum d, X, Y).  `red` holds 3*nwarps floats.
 __device__ __forceinline__ void smooth_forward_role(const VslArgs& a, int role, float* red) {
   int s, b, chunk;
   smooth_role_ids(a, role, s, b, chunk);
   const ScaleArgs& sc = a.sc[s];
-  const int h = sc.hs, w = sc.ws, n = h * w;
-  int lo, hi;
-  smooth_chunk_range(n, chunk, lo, hi);
+  const int h = sc.hs, w = sc.ws;
+  const unsigned n = (unsigned)(h * w);
   const float* d = sc.disp + (size_t)b * n;
   const float* img = sc.color + (size_t)b * 3 * n;
   float* gz = sc.grad_disp ? sc.grad_disp + (size_t)b * n : nullptr;   // optional: pre-zero the backward's accumulator
+  const SmoothChunk ck = smooth_chunk(w, h, chunk);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   float sd = 0.f, sx = 0.f, sy = 0.f;
-#pragma unroll 2
-  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    const int y = i / w, x = i - y * w;
-    const float di = __ldg(d + i);
-    if (gz) gz[i] = 0.f;
-    sd += di;
-    if (x + 1 < w) sx += fabsf(di - __ldg(d + i + 1)) * smooth_edge_weight(img, n, i, i + 1);
-    if (y + 1 < h) sy += fabsf(di - __ldg(d + i + w)) * smooth_edge_weight(img, n, i, i + w);
+  if (ck.active) {
+    const bool xin = ck.x < w, has_r = ck.x + 1 < w;
+    SmoothPx cur = smooth_load(d, img, n, (unsigned)(ck.y_lo * w + ck.x), xin);
+    for (int y = ck.y_lo; y < ck.y_hi; ++y) {
+      const unsigned o = (unsigned)(y * w + ck.x);
+      const bool has_d = y + 1 < h;
+      const SmoothPx nxt = smooth_load(d, img, n, o + (unsigned)w, xin && has_d);
+      SmoothPx rgt = smooth_shfl_down(cur);
+      if (lane == 31) rgt = smooth_load(d, img, n, o + 1u, has_r);     // the neighbour lives in the next warp / strip
+      if (xin) {
+        sd += cur.d;
+        if (gz) gz[o] = 0.f;
+        if (has_r) sx += fabsf(cur.d - rgt.d) * smooth_weight(cur, rgt);
+        if (has_d) sy += fabsf(cur.d - nxt.d) * smooth_weight(cur, nxt);
+      }
+      cur = nxt;
+    }
   }
   sd = warp_sum(sd);
   sx = warp_sum(sx);
   sy = warp_sum(sy);
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   if (lane == 0) {
     red[wid] = sd;
     red[nw + wid] = sx;
@@ -81,36 +139,58 @@ __device__ __forceinline__ void smooth_forward_role(const VslArgs& a, int role, 
 
 // Backward role: smoothness gradient of one chunk.  ACCUMULATE: atomically add into a zero-initialised
 // (and concurrently accumulated) grad_disp;  otherwise overwrite it.
+//   grad(x,y) = inv * ( R(x,y) - R(x-1,y) + D(x,y) - D(x,y-1) - mean_term ),
+//   R = gx * sign(d - d_right) * e_right,  D = gy * sign(d - d_down) * e_down.
 template <bool ACCUMULATE>
 __device__ __forceinline__ void smooth_backward_role(const VslArgs& a, int role) {
   int s, b, chunk;
   smooth_role_ids(a, role, s, b, chunk);
   const ScaleArgs& sc = a.sc[s];
-  const int h = sc.hs, w = sc.ws, n = h * w;
+  const int h = sc.hs, w = sc.ws;
+  const unsigned n = (unsigned)(h * w);
+  const SmoothChunk ck = smooth_chunk(w, h, chunk);
+  if (!ck.active) return;
   const float* row = a.sums + (size_t)s * sums_stride(a.B) + PPEA_SUMS_PER_SCALE + 4 * b;   // (sum d, X_b, Y_b)
   const float inv = 1.f / (row[0] / (float)n + 1e-7f);
   const float g = scale_grads(a, s).smooth;
   const float gx = g / ((float)a.B * h * (w - 1)), gy = g / ((float)a.B * (h - 1) * w);
   const float mean_term = inv * (gx * row[1] + gy * row[2]) / (float)n;
-  int lo, hi;
-  smooth_chunk_range(n, chunk, lo, hi);
   const float* d = sc.disp + (size_t)b * n;
   const float* img = sc.color + (size_t)b * 3 * n;
   float* out = sc.grad_disp + (size_t)b * n;
-#pragma unroll 2
-  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    const int y = i / w, x = i - y * w;
-    const float di = __ldg(d + i);
-    float acc = 0.f;
-    if (x + 1 < w) acc += gx * sign_of(di - __ldg(d + i + 1)) * smooth_edge_weight(img, n, i, i + 1);
-    if (x > 0) acc -= gx * sign_of(__ldg(d + i - 1) - di) * smooth_edge_weight(img, n, i - 1, i);
-    if (y + 1 < h) acc += gy * sign_of(di - __ldg(d + i + w)) * smooth_edge_weight(img, n, i, i + w);
-    if (y > 0) acc -= gy * sign_of(__ldg(d + i - w) - di) * smooth_edge_weight(img, n, i - w, i);
-    const float v = (acc - mean_term) * inv;
-    if (ACCUMULATE)
-      atomicAdd(out + i, v);
-    else
-      out[i] = v;
+  const int lane = threadIdx.x & 31;
+  const bool xin = ck.x < w, has_r = ck.x + 1 < w, has_l = xin && ck.x > 0;
+  SmoothPx cur = smooth_load(d, img, n, (unsigned)(ck.y_lo * w + ck.x), xin);
+  float d_up = 0.f;                      // D(x, y-1)
+  if (ck.y_lo > 0 && xin) {
+    const SmoothPx up = smooth_load(d, img, n, (unsigned)((ck.y_lo - 1) * w + ck.x), true);
+    d_up = gy * sign_of(up.d - cur.d) * smooth_weight(up, cur);
+  }
+  for (int y = ck.y_lo; y < ck.y_hi; ++y) {
+    const unsigned o = (unsigned)(y * w + ck.x);
+    const bool has_d = y + 1 < h;
+    const SmoothPx nxt = smooth_load(d, img, n, o + (unsigned)w, xin && has_d);
+    SmoothPx rgt = smooth_shfl_down(cur);
+    if (lane == 31) rgt = smooth_load(d, img, n, o + 1u, has_r);
+    const float r_here = (xin && has_r) ? gx * sign_of(cur.d - rgt.d) * smooth_weight(cur, rgt) : 0.f;
+    float r_left = __shfl_up_sync(0xffffffffu, r_here, 1);
+    if (lane == 0) {
+      r_left = 0.f;
+      if (has_l) {
+        const SmoothPx lft = smooth_load(d, img, n, o - 1u, true);
+        r_left = gx * sign_of(lft.d - cur.d) * smooth_weight(lft, cur);
+      }
+    }
+    const float d_here = (xin && has_d) ? gy * sign_of(cur.d - nxt.d) * smooth_weight(cur, nxt) : 0.f;
+    if (xin) {
+      const float v = ((r_here - r_left) + (d_here - d_up) - mean_term) * inv;
+      if (ACCUMULATE)
+        atomicAdd(out + o, v);
+      else
+        out[o] = v;
+    }
+    d_up = d_here;
+    cur = nxt;
   }
 }
 
