@@ -128,8 +128,11 @@ __device__ __forceinline__ void fwd_gather(Smem& sm, const VslArgs& a, const Sca
   }
 }
 
+#ifndef PPEA_FWD_CTAS
+#define PPEA_FWD_CTAS 5
+#endif
 template <int TW, int TH, int NT>
-__global__ void __launch_bounds__(NT, 5) vsl_forward_kernel(const __grid_constant__ VslArgs a) {
+__global__ void __launch_bounds__(NT, PPEA_FWD_CTAS) vsl_forward_kernel(const __grid_constant__ VslArgs a) {
   using Smem = FwdSmem<TW, TH>;
   constexpr int EW = Smem::EW, PLANE = Smem::PLANE;
   constexpr int R = (TW * TH) / NT;
