@@ -316,8 +316,12 @@ def main():
         dom = "vsl_backward_kernel" if stage_ms["vsl_backward_kernel"] >= stage_ms["vsl_forward_kernel"] else "vsl_forward_kernel"
         dom_bytes = bwd_b if dom == "vsl_backward_kernel" else fwd_b
         achieved = dom_bytes / (stage_ms[dom] * 1e-3) / 1e9
+        traffic = None            # DRAM bytes of one launch of that kernel from the committed ncu capture (same workload only)
+        tpath = os.path.join(ROOT, "profiles", "r1f_traffic.json")
+        if os.path.exists(tpath) and args.workload == "kitti" and not is_multi and not args.deterministic:
+            traffic = json.load(open(tpath)).get(dom)
         roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
                 "kernel_ms": stage_ms[dom], "stage_ms": stage_ms,
                 "step_algorithmic_bytes": fwd_b + bwd_b,
                 "step_frac_of_peak": (fwd_b + bwd_b) / (ms_step * 1e-3) / 1e9 / peak,
