@@ -399,22 +399,39 @@ __global__ void __launch_bounds__(256) upsample_gather_kernel(const __grid_const
   const int ylo = max(0, (int)floorf(((float)jy - 0.5f) * inv_sy) - 2), yhi = min(a.H - 1, (int)ceilf(((float)jy + 1.5f) * inv_sy) + 2);
   const int xlo = max(0, (int)floorf(((float)jx - 0.5f) * inv_sx) - 2), xhi = min(a.W - 1, (int)ceilf(((float)jx + 1.5f) * inv_sx) + 2);
   const float* g = sc.grad_dup + (size_t)b * a.H * a.W;
+  auto weight = [](const UpCoef& c, int j) {
+    float w = 0.f;
+    if (c.i0 == j) w += c.l0;
+    if (c.i1 == j) w += c.l1;
+    return w;
+  };
+  constexpr int kMaxTaps = 24;            // 2 * ratio + slack: covers ratios up to 8 (the reference's 4-scale pyramid)
   float acc = 0.f;
-  for (int y = ylo; y <= yhi; ++y) {
-    const UpCoef cy = up_coef(y, sc.hs, sc.up_sy);
-    float wy = 0.f;
-    if (cy.i0 == jy) wy += cy.l0;
-    if (cy.i1 == jy) wy += cy.l1;
-    if (wy == 0.f) continue;
-    float racc = 0.f;
-    for (int x = xlo; x <= xhi; ++x) {
-      const UpCoef cx = up_coef(x, sc.ws, sc.up_sx);
-      float wx = 0.f;
-      if (cx.i0 == jx) wx += cx.l0;
-      if (cx.i1 == jx) wx += cx.l1;
-      if (wx != 0.f) racc = fmaf(wx, g[(size_t)y * a.W + x], racc);
+  if (xhi - xlo < kMaxTaps) {
+    float wx[kMaxTaps];                   // the column weights do not depend on the row: hoisted out of the row loop
+#pragma unroll
+    for (int k = 0; k < kMaxTaps; ++k) wx[k] = (xlo + k <= xhi) ? weight(up_coef(xlo + k, sc.ws, sc.up_sx), jx) : 0.f;
+    for (int y = ylo; y <= yhi; ++y) {
+      const float wy = weight(up_coef(y, sc.hs, sc.up_sy), jy);
+      if (wy == 0.f) continue;
+      const float* row = g + (size_t)y * a.W + xlo;
+      float racc = 0.f;
+#pragma unroll
+      for (int k = 0; k < kMaxTaps; ++k)
+        if (wx[k] != 0.f) racc = fmaf(wx[k], row[k], racc);
+      acc = fmaf(wy, racc, acc);
     }
-    acc = fmaf(wy, racc, acc);
+  } else {                                // arbitrary ratios: same sums, same order, weights recomputed per tap
+    for (int y = ylo; y <= yhi; ++y) {
+      const float wy = weight(up_coef(y, sc.hs, sc.up_sy), jy);
+      if (wy == 0.f) continue;
+      float racc = 0.f;
+      for (int x = xlo; x <= xhi; ++x) {
+        const float w = weight(up_coef(x, sc.ws, sc.up_sx), jx);
+        if (w != 0.f) racc = fmaf(w, g[(size_t)y * a.W + x], racc);
+      }
+      acc = fmaf(wy, racc, acc);
+    }
   }
   sc.grad_disp[idx] += acc;
 }
