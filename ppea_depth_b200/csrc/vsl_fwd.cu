@@ -209,10 +209,6 @@ __global__ void __launch_bounds__(NT, PPEA_FWD_CTAS) vsl_forward_kernel(const __
     {
       const float* disp_b = sc.disp + (size_t)b * sc.hs * sc.ws;
       float* depth_b = sc.depth + (size_t)b * plane;
-#if defined(PPEA_ABLATE_GATHER)
-      if (tid < 0) {
-      } else
-#endif
       if (sc.hs == H && sc.ws == W)
         fwd_gather<TW, TH, NT, true>(sm, a, sc, disp_b, sp, depth_b, x0, y0, col, wid, tid, col_own, wmax, hmax);
       else
@@ -237,12 +233,7 @@ __global__ void __launch_bounds__(NT, PPEA_FWD_CTAS) vsl_forward_kernel(const __
       }
     }
 
-#if defined(PPEA_ABLATE_PHOTO)
-#pragma unroll
-    for (int k = 0; k < R; ++k) { acc[k] = sm.x[0][(row0 + k + 1) * EW + col + 1]; cs[k] = sm.x[1][(row0 + k + 1) * EW + col + 1]; }
-#else
     photometric_pass<R, EW, PLANE, true>(&sm.x[0][0], &sm.y[0][0], row0, col, no_ssim, acc, cs);
-#endif
 
     // ---- epilogue: min over sources, selec_reproj, mask, per-pixel outputs, block sums
     float s_rm = 0.f, s_m = 0.f, s_c = 0.f;
