@@ -57,7 +57,10 @@ constexpr int kFwdTileW = 32;
 constexpr int kFwdTileH = 16;
 constexpr int kFwdThreads = 128;
 constexpr int kBwdTileW = 32;
-constexpr int kBwdTileH = 16;
+#ifndef PPEA_BWD_TILE_H
+#define PPEA_BWD_TILE_H 16
+#endif
+constexpr int kBwdTileH = PPEA_BWD_TILE_H;
 #ifndef PPEA_BWD_THREADS
 #define PPEA_BWD_THREADS 128
 #endif
