@@ -109,10 +109,6 @@ __global__ void __launch_bounds__(NT, PPEA_BWD_CTAS) vsl_backward_kernel(const _
   // reflection multiplicities of the taps left/right of this thread's column
   const f2 mL = dup2((gx_own == 1) ? 2.f : 1.f), mR = dup2((gx_own == W - 2) ? 2.f : 1.f);
 
-  // pose partials: Sw[r] = sum gc_r*depth, Swy[r] = sum gc_r*depth*y, Sg[r] = sum gc_r (x is this thread's constant column)
-  f2 Sw[POSE ? 3 : 1], Swy[POSE ? 3 : 1], Sg[POSE ? 3 : 1];
-#pragma unroll
-  for (int e = 0; e < (POSE ? 3 : 1); ++e) Sw[e] = Swy[e] = Sg[e] = dup2(0.f);
 
 #pragma unroll 1
   for (int s = 0; s < a.S; ++s) {
@@ -282,6 +278,11 @@ __global__ void __launch_bounds__(NT, PPEA_BWD_CTAS) vsl_backward_kernel(const _
 
     // ---- phase 4: projection adjoint, consistency term, depth -> disp, adjoint of the bilinear upsample
     float* gd_b = sc.grad_disp + (size_t)b * sc.hs * sc.ws;
+    // pose partials of this scale: Sw[r] = sum gc_r*depth, Swy[r] = sum gc_r*depth*y, Sg[r] = sum gc_r (x is this thread's
+    // constant column).  Reduced and written per scale so that they are not live across the other phases.
+    f2 Sw[POSE ? 3 : 1], Swy[POSE ? 3 : 1], Sg[POSE ? 3 : 1];
+#pragma unroll
+    for (int e = 0; e < (POSE ? 3 : 1); ++e) Sw[e] = Swy[e] = Sg[e] = dup2(0.f);
 #pragma unroll
     for (int k = 0; k < R; ++k) {
       const int gy = y0 + row0 + k;
@@ -330,35 +331,35 @@ __global__ void __launch_bounds__(NT, PPEA_BWD_CTAS) vsl_backward_kernel(const _
         }
       }
     }
-  }
-
-  if (POSE) {
-    // per source f and row r of dL/dP: (sum gc_r*depth*x, sum gc_r*depth*y, sum gc_r*depth, sum gc_r)
-    const float fx = int_to_float(px_own);
-    float v[24];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      v[0 * 12 + r * 4 + 0] = Sw[r].x * fx;
-      v[0 * 12 + r * 4 + 1] = Swy[r].x;
-      v[0 * 12 + r * 4 + 2] = Sw[r].x;
-      v[0 * 12 + r * 4 + 3] = Sg[r].x;
-      v[1 * 12 + r * 4 + 0] = Sw[r].y * fx;
-      v[1 * 12 + r * 4 + 1] = Swy[r].y;
-      v[1 * 12 + r * 4 + 2] = Sw[r].y;
-      v[1 * 12 + r * 4 + 3] = Sg[r].y;
+    if (POSE) {
+      // per source f and row r of dL/dP: (sum gc_r*depth*x, sum gc_r*depth*y, sum gc_r*depth, sum gc_r)
+      const float fx = int_to_float(px_own);
+      float v[24];
+  #pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        v[0 * 12 + r * 4 + 0] = Sw[r].x * fx;
+        v[0 * 12 + r * 4 + 1] = Swy[r].x;
+        v[0 * 12 + r * 4 + 2] = Sw[r].x;
+        v[0 * 12 + r * 4 + 3] = Sg[r].x;
+        v[1 * 12 + r * 4 + 0] = Sw[r].y * fx;
+        v[1 * 12 + r * 4 + 1] = Swy[r].y;
+        v[1 * 12 + r * 4 + 2] = Sw[r].y;
+        v[1 * 12 + r * 4 + 3] = Sg[r].y;
+      }
+      const int lane = tid & 31, wid = tid >> 5;
+  #pragma unroll
+      for (int e = 0; e < 24; ++e) {
+        const float t = warp_sum(v[e]);
+        if (lane == 0) sm.red[e][wid] = t;
+      }
+      __syncthreads();
+      if (tid < 24) {
+        float t = 0.f;
+        for (int w = 0; w < NT / 32; ++w) t += sm.red[tid][w];
+        a.pose_partials[((size_t)tile_id * a.S + s) * 24 + tid] = t;
+      }
     }
-    const int lane = tid & 31, wid = tid >> 5;
-#pragma unroll
-    for (int e = 0; e < 24; ++e) {
-      const float t = warp_sum(v[e]);
-      if (lane == 0) sm.red[e][wid] = t;
-    }
-    __syncthreads();
-    if (tid < 24) {
-      float t = 0.f;
-      for (int w = 0; w < NT / 32; ++w) t += sm.red[tid][w];
-      a.pose_partials[(size_t)tile_id * 24 + tid] = t;
-    }
+    if (POSE) __syncthreads();   // sm.red is reused by the next scale
   }
 }
 
@@ -489,7 +490,7 @@ __global__ void __launch_bounds__(32 * 24) pose_finish_kernel(const __grid_const
 }
 
 cudaError_t launch_pose_finish(const VslArgs& a, int nblk_bwd, cudaStream_t stream) {
-  pose_finish_kernel<<<a.B, 32 * 24, 0, stream>>>(a, nblk_bwd / a.B);
+  pose_finish_kernel<<<a.B, 32 * 24, 0, stream>>>(a, nblk_bwd / a.B * a.S);
   return cudaGetLastError();
 }
 

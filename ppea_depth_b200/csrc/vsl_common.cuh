@@ -49,7 +49,7 @@ struct VslArgs {
   float* smooth_ws;     // [S][B][kSmoothChunks][3]: disp sum, smooth_x sum, smooth_y sum
   // backward only
   const float* grad_losses;
-  float* pose_partials; // [nblk_bwd][24]
+  float* pose_partials; // [nblk_bwd][S][24]
   float* grad_T[2];
 };
 
@@ -87,14 +87,14 @@ inline FwdWorkspace fwd_workspace(int B, int H, int W, int S) {
   return w;
 }
 
-// Backward workspace layout (floats): [pose partials: nblk*24][grad_dup: S*B*H*W when deterministic]
+// Backward workspace layout (floats): [pose partials: nblk*S*24][grad_dup: S*B*H*W when deterministic]
 struct BwdWorkspace {
   size_t off_pose, off_dup, total_floats;
 };
 inline BwdWorkspace bwd_workspace(int B, int H, int W, int S, unsigned flags) {
   BwdWorkspace w;
   w.off_pose = 0;
-  w.off_dup = align_up((size_t)bwd_blocks(B, H, W) * 24, 4);
+  w.off_dup = align_up((size_t)bwd_blocks(B, H, W) * S * 24, 4);
   w.total_floats = w.off_dup + ((flags & PPEA_F_DETERMINISTIC) ? (size_t)S * B * H * W : 0);
   return w;
 }
