@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--workload", default="kitti", choices=sorted(WORKLOADS))
     ap.add_argument("--path", default="mono", choices=["mono", "multi"])
     ap.add_argument("--deterministic", action="store_true")
+    ap.add_argument("--no-fused", action="store_true", help="forward + backward kernel pair instead of the single-launch step")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the e2e leg (default: min(steps, 50))")
@@ -152,7 +153,7 @@ def tensors_of_step(inputs, outputs, noise, S, is_multi):
     return t
 
 
-def build_plan(tset, wl, device, is_multi, deterministic):
+def build_plan(tset, wl, device, is_multi, deterministic, fused=None):
     from ppea_depth_b200.functional import VslConfig
     from ppea_depth_b200.runner import FusedPlan
     inputs, outputs, noise = tset
@@ -168,7 +169,7 @@ def build_plan(tset, wl, device, is_multi, deterministic):
     return FusedPlan(cfg, [d(outputs[("disp", s)]) for s in range(S)],
                      [d(outputs[("cam_T_cam", 0, -1)]), d(outputs[("cam_T_cam", 0, 1)])],
                      d(inputs[("color", 0, 0)]), [d(inputs[("color", -1, 0)]), d(inputs[("color", 1, 0)])],
-                     d(inputs[("K", 0)]), d(inputs[("inv_K", 0)]), [d(inputs[("color", 0, s)]) for s in range(S)], **kw)
+                     d(inputs[("K", 0)]), d(inputs[("inv_K", 0)]), [d(inputs[("color", 0, s)]) for s in range(S)], fused=fused, **kw)
 
 
 def barrier(world):
@@ -259,7 +260,10 @@ def main():
     n_sets = max(4, int(2.5 * L2_BYTES // step_bytes) + 1)
     n_sets = min(n_sets, 12)
     sets = probe + make_sets(wl, n_sets - 1, 1000 * rank + 1, device, is_multi)
-    plans = [build_plan(t, wl, device, is_multi, args.deterministic) for t in sets]
+    plans = [build_plan(t, wl, device, is_multi, args.deterministic, fused=False if args.no_fused else None) for t in sets]
+    fused = plans[0].fused
+    cfg_desc["kernels"] = ("single-launch fused step (vsl_fused_kernel) + finish + gradient finish + pose finish" if fused
+                           else "vsl_forward_kernel + finish + vsl_backward_kernel + pose finish")
     for p in plans:
         p.capture()
     launches_per_step = plans[0].launches_forward + plans[0].launches_backward
@@ -313,17 +317,25 @@ def main():
         fwd_b = sum((53.0 if is_multi else 49.0) + 16.0 / 4 ** s for s in range(S)) * n_px
         bwd_b = sum((45.0 if is_multi else 37.0) + (8.0 if args.deterministic else 0.0) + 8.0 / 4 ** s for s in range(S)) * n_px
         assert abs((fwd_b + bwd_b) - algorithmic_bytes(B, H, W, S, is_multi, args.deterministic)) < 1.0
-        dom = "vsl_backward_kernel" if stage_ms["vsl_backward_kernel"] >= stage_ms["vsl_forward_kernel"] else "vsl_forward_kernel"
-        dom_bytes = bwd_b if dom == "vsl_backward_kernel" else fwd_b
+        if fused:
+            # The fused launch does the forward AND the backward work of every pixel.scale but has to move less than the
+            # two-launch figure of SURVEY.md §8d: target/sources are read once, sel never round-trips.  Its own compulsory
+            # bytes: tgt 12 + src 24 + noise 4 + depth 4 + sel 1 + loss 4 + (disp 4 + colour 12 + raw grad 4)/4^s.
+            dom = "vsl_fused_kernel"
+            dom_bytes = sum(49.0 + 20.0 / 4 ** s for s in range(S)) * n_px
+        else:
+            dom = "vsl_backward_kernel" if stage_ms["vsl_backward_kernel"] >= stage_ms["vsl_forward_kernel"] else "vsl_forward_kernel"
+            dom_bytes = bwd_b if dom == "vsl_backward_kernel" else fwd_b
         achieved = dom_bytes / (stage_ms[dom] * 1e-3) / 1e9
         traffic = None            # DRAM bytes of one launch of that kernel from the committed ncu capture (same workload only)
-        tpath = os.path.join(ROOT, "profiles", "r1f_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r1g_traffic.json" if fused else "r1f_traffic.json")
         if os.path.exists(tpath) and args.workload == "kitti" and not is_multi and not args.deterministic:
             traffic = json.load(open(tpath)).get(dom)
         roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
                 "kernel_ms": stage_ms[dom], "stage_ms": stage_ms,
                 "step_algorithmic_bytes": fwd_b + bwd_b,
+                "kernel_frac_at_survey_step_bytes": (fwd_b + bwd_b) / (stage_ms[dom] * 1e-3) / 1e9 / peak if fused else None,
                 "step_frac_of_peak": (fwd_b + bwd_b) / (ms_step * 1e-3) / 1e9 / peak,
                 "frac_of_8TBs_nominal": achieved / 8000.0}
 
@@ -336,7 +348,7 @@ def main():
                               frame_ids=[0, -1, 1], disable_automasking=False, no_ssim=False, selec_reproj=True,
                               disable_motion_masking=False, no_matching_augmentation=False, batch_size=B,
                               disparity_smoothness=1e-3)
-        mod = ViewSynthesisLoss(opt, deterministic=args.deterministic, noise_mode="device")
+        mod = ViewSynthesisLoss(opt, deterministic=args.deterministic, noise_mode="device", fused=False if args.no_fused else None)
         host_sets = []
         for (inputs, outputs, noise) in sets[:4]:
             t = tensors_of_step(inputs, outputs, noise, S, is_multi)

@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define PPEA_ABI_VERSION 3
+#define PPEA_ABI_VERSION 4
 
 /* error codes (negative) */
 #define PPEA_OK 0
@@ -72,6 +72,11 @@ extern "C" {
 #define PPEA_F_GRAD_POSE (1u << 7)     /* backward: also produce dL/dT (mono path) */
 #define PPEA_F_GRAD_PREZEROED (1u << 8) /* backward: every grad_disp was zero-filled by the forward (which does so when it is
                                            handed non-NULL grad_disp pointers); skips the backward's own zero-fill */
+
+#define PPEA_F_RAW_PREZEROED (1u << 9)  /* fused step: the coarse-scale raw gradient fields inside PpeaVslFused.workspace are zero on
+                                           entry of ppea_vsl_fused_forward (zero-filled once by the caller); ppea_vsl_fused_backward
+                                           then clears them again on its way out, so a replayed forward/backward pair needs no
+                                           memset.  Every fused_forward must be followed by exactly one fused_backward. */
 
 /* sel map (uint8 per full-res pixel, written by forward, read by backward):
  *   bits 0-1: source frame whose loss is propagated: 0 -> frame_ids[1] (-1),
@@ -165,6 +170,26 @@ size_t ppea_vsl_sums_floats(int batch, int num_scales);
 int ppea_vsl_forward(const PpeaVslParams* p, void* stream);
 /* `p` must describe the same call as the forward (same inputs, sel and sums as written by it) */
 int ppea_vsl_backward(const PpeaVslParams* p, const PpeaVslGrads* g, void* stream);
+
+/* ---- fused training step (mono path, non-deterministic backward) --------------------------------
+ * Same reference calls as ppea_vsl_forward + ppea_vsl_backward (Trainer.generate_images_pred
+ * trainer.py:871-918 + Trainer.compute_losses :1032-1160 + autograd of both), organised as ONE main
+ * launch: the masked-mean normaliser 1/(sum(mask_s) + 1e-7) (trainer.py:1113-1114) is the only global
+ * quantity of the path, so ppea_vsl_fused_forward evaluates the loss AND the un-normalised gradient
+ * fields (into `workspace`), and ppea_vsl_fused_backward only rescales them by the upstream gradient
+ * of `losses`, adds the smoothness gradient and reduces the pose gradient.  Outputs (depth, sel,
+ * loss_px, sums, losses, grad_disp, grad_T) are the same tensors, to the same tolerances, as the
+ * two-call path.  PPEA_F_MULTI / PPEA_F_DETERMINISTIC are refused (PPEA_E_FLAGS); pass PPEA_F_GRAD_POSE
+ * to BOTH calls if dL/dT is wanted. */
+typedef struct PpeaVslFused {
+  uint32_t struct_size;
+  void* workspace;        /* >= ppea_vsl_fused_workspace_bytes(p), 16-byte aligned; written by fused_forward,
+                             read by fused_backward (keep it untouched in between) */
+  size_t workspace_bytes;
+} PpeaVslFused;
+size_t ppea_vsl_fused_workspace_bytes(const PpeaVslParams* p);
+int ppea_vsl_fused_forward(const PpeaVslParams* p, const PpeaVslFused* f, void* stream);
+int ppea_vsl_fused_backward(const PpeaVslParams* p, const PpeaVslGrads* g, const PpeaVslFused* f, void* stream);
 
 /* ---- piecewise operators behind the reference's nn.Module / function API ---- */
 int ppea_ssim_forward(const float* x, const float* y, float* out, int n_planes, int height, int width, void* stream);

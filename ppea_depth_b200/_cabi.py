@@ -17,10 +17,10 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.environ.get("PPEA_LIB") or os.path.join(PKG_DIR, "libppea_vsl.so")
 INCLUDE_DIR = os.path.join(os.path.dirname(PKG_DIR), "include")
-SOURCES = ("api.cu", "vsl_fwd.cu", "vsl_bwd.cu", "smooth.cu", "ops.cu")
-HEADERS = ("vsl_common.cuh", "vsl_math.cuh")
+SOURCES = ("api.cu", "vsl_fwd.cu", "vsl_bwd.cu", "vsl_fused.cu", "smooth.cu", "ops.cu")
+HEADERS = ("vsl_common.cuh", "vsl_math.cuh", "vsl_gather.cuh", "smooth.cuh")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 TRACE_EVENTS = 5
 MAX_SCALES = 4
 SUMS_PER_SCALE = 8
@@ -35,6 +35,7 @@ F_MOTION_MASK = 1 << 5
 F_MATCH_AUG = 1 << 6
 F_GRAD_POSE = 1 << 7
 F_GRAD_PREZEROED = 1 << 8
+F_RAW_PREZEROED = 1 << 9
 
 SEL_SRC_MASK = 3
 SEL_AUTOMASK = 4
@@ -74,6 +75,13 @@ class PpeaVslGrads(ctypes.Structure):
     ]
 
 
+class PpeaVslFused(ctypes.Structure):
+    _fields_ = [
+        ("struct_size", ctypes.c_uint32),
+        ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
+    ]
+
+
 _I, _P, _F, _SZ, _U = ctypes.c_int, ctypes.c_void_p, ctypes.c_float, ctypes.c_size_t, ctypes.c_uint32
 
 # name -> (restype, argtypes); every symbol include/ppea_vsl.h declares
@@ -89,6 +97,9 @@ SIGNATURES = {
     "ppea_vsl_sums_floats": (_SZ, [_I, _I]),
     "ppea_vsl_forward": (_I, [ctypes.POINTER(PpeaVslParams), _P]),
     "ppea_vsl_backward": (_I, [ctypes.POINTER(PpeaVslParams), ctypes.POINTER(PpeaVslGrads), _P]),
+    "ppea_vsl_fused_workspace_bytes": (_SZ, [ctypes.POINTER(PpeaVslParams)]),
+    "ppea_vsl_fused_forward": (_I, [ctypes.POINTER(PpeaVslParams), ctypes.POINTER(PpeaVslFused), _P]),
+    "ppea_vsl_fused_backward": (_I, [ctypes.POINTER(PpeaVslParams), ctypes.POINTER(PpeaVslGrads), ctypes.POINTER(PpeaVslFused), _P]),
     "ppea_ssim_forward": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "ppea_ssim_backward": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "ppea_reprojection_forward": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),

@@ -78,6 +78,7 @@ void fill_args(const PpeaVslParams* p, VslArgs& a) {
     sc.sel = in.sel;
     sc.grad_disp = in.grad_disp;
     sc.grad_dup = nullptr;
+    sc.grad_raw = nullptr;
   }
   a.sums = p->sums;
   a.losses = p->losses;
@@ -217,6 +218,101 @@ int ppea_vsl_backward(const PpeaVslParams* p, const PpeaVslGrads* g, void* strea
   if (any_dup) PPEA_TRY(launch_upsample_gather(a, stream));
   PPEA_TRACE(p, 3);
   if (pose) PPEA_TRY(launch_pose_finish(a, bwd_blocks(a.B, a.H, a.W), stream));
+  PPEA_TRACE(p, 4);
+  return PPEA_OK;
+}
+
+// ---- fused training step (mono path): vsl_fused.cu -------------------------------------------------
+static_assert(kFusedTileWc == kFwdTileW && kFusedTileHc == kFwdTileH, "the fused step reuses the forward workspace layout");
+
+struct FusedWorkspace {
+  size_t off_pose, off_raw[kMaxScales], total_floats;
+};
+static FusedWorkspace fused_workspace(const PpeaVslParams* p) {
+  FusedWorkspace w;
+  w.off_pose = 0;
+  size_t off = align_up((size_t)fused_blocks(p->batch, p->height, p->width) * p->num_scales * 24, 4);
+  for (int s = 0; s < kMaxScales; ++s) {
+    w.off_raw[s] = off;
+    if (s < p->num_scales) off += align_up((size_t)p->batch * p->scales[s].disp_h * p->scales[s].disp_w, 4);
+  }
+  w.total_floats = off;
+  return w;
+}
+
+static int check_fused(const PpeaVslParams* p, const PpeaVslFused* f, bool backward) {
+  const int rc = check_params(p, backward);
+  if (rc != PPEA_OK) return rc;
+  if (!f) return PPEA_E_NULL;
+  if (f->struct_size != sizeof(PpeaVslFused)) return PPEA_E_VERSION;
+  if (p->flags & (PPEA_F_MULTI | PPEA_F_DETERMINISTIC)) return PPEA_E_FLAGS;   // mono path, atomics backward only
+  if (!f->workspace) return PPEA_E_NULL;
+  if (!aligned(f->workspace, 16) || f->workspace_bytes < fused_workspace(p).total_floats * sizeof(float)) return PPEA_E_WORKSPACE;
+  return PPEA_OK;
+}
+
+static void fused_args(const PpeaVslParams* p, const PpeaVslFused* f, VslArgs& a) {
+  fill_args(p, a);
+  const FusedWorkspace fw = fused_workspace(p);
+  const FwdWorkspace ws = fwd_workspace(p->batch, p->height, p->width, p->num_scales);
+  a.tiles_x = ceil_div(a.W, kFusedTileWc);
+  a.tiles_y = ceil_div(a.H, kFusedTileHc);
+  a.partials = (float*)p->workspace + ws.off_partials;
+  a.smooth_ws = (float*)p->workspace + ws.off_smooth;
+  a.pose_partials = (float*)f->workspace + fw.off_pose;
+  for (int s = 0; s < a.S; ++s) a.sc[s].grad_raw = (float*)f->workspace + fw.off_raw[s];
+}
+
+size_t ppea_vsl_fused_workspace_bytes(const PpeaVslParams* p) {
+  if (!p || p->struct_size != sizeof(PpeaVslParams) || p->batch <= 0 || p->height <= 0 || p->width <= 0 ||
+      p->num_scales < 1 || p->num_scales > PPEA_MAX_SCALES)
+    return 0;
+  return fused_workspace(p).total_floats * sizeof(float);
+}
+
+int ppea_vsl_fused_forward(const PpeaVslParams* p, const PpeaVslFused* f, void* stream_) {
+  const int rc = check_fused(p, f, false);
+  if (rc != PPEA_OK) return rc;
+  const FwdWorkspace ws = fwd_workspace(p->batch, p->height, p->width, p->num_scales);
+  if (!p->workspace) return PPEA_E_NULL;
+  if (!aligned(p->workspace, 16) || p->workspace_bytes < ws.total_floats * sizeof(float)) return PPEA_E_WORKSPACE;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  VslArgs a;
+  fused_args(p, f, a);
+  for (int s = 0; s < a.S; ++s) a.sc[s].grad_disp = nullptr;     // (the smoothness role would pre-zero it)
+  PPEA_TRACE(p, 0);
+  for (int s = 0; s < a.S; ++s)                                  // coarse scales accumulate atomically
+    if (!(p->flags & PPEA_F_RAW_PREZEROED) && (a.sc[s].hs != a.H || a.sc[s].ws != a.W))
+      PPEA_TRY(cudaMemsetAsync(a.sc[s].grad_raw, 0, sizeof(float) * (size_t)a.B * a.sc[s].hs * a.sc[s].ws, stream));
+  PPEA_TRACE(p, 1);
+  PPEA_TRY(launch_vsl_fused(a, stream));
+  PPEA_TRACE(p, 2);
+  PPEA_TRACE(p, 3);
+  PPEA_TRY(launch_vsl_finish(a, fused_blocks(a.B, a.H, a.W), stream));
+  PPEA_TRACE(p, 4);
+  return PPEA_OK;
+}
+
+int ppea_vsl_fused_backward(const PpeaVslParams* p, const PpeaVslGrads* g, const PpeaVslFused* f, void* stream_) {
+  const int rc = check_fused(p, f, true);
+  if (rc != PPEA_OK) return rc;
+  if (!g) return PPEA_E_NULL;
+  if (g->struct_size != sizeof(PpeaVslGrads)) return PPEA_E_VERSION;
+  if (!g->grad_losses) return PPEA_E_NULL;
+  const bool pose = p->flags & PPEA_F_GRAD_POSE;
+  if (pose && (!g->grad_T[0] || !g->grad_T[1])) return PPEA_E_NULL;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  VslArgs a;
+  fused_args(p, f, a);
+  a.grad_losses = g->grad_losses;
+  a.grad_T[0] = g->grad_T[0];
+  a.grad_T[1] = g->grad_T[1];
+  PPEA_TRACE(p, 0);
+  PPEA_TRACE(p, 1);
+  PPEA_TRY(launch_vsl_grad_finish(a, stream));
+  PPEA_TRACE(p, 2);
+  PPEA_TRACE(p, 3);
+  if (pose) PPEA_TRY(launch_pose_finish_fused(a, stream));
   PPEA_TRACE(p, 4);
   return PPEA_OK;
 }

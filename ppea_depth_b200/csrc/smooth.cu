@@ -7,7 +7,7 @@
 namespace ppea {
 
 __global__ void __launch_bounds__(kSmoothThreads) smooth_backward_kernel(const __grid_constant__ VslArgs a) {
-  smooth_backward_role<false>(a, blockIdx.x);
+  smooth_backward_role<0>(a, blockIdx.x);
 }
 
 cudaError_t launch_smooth_backward(const VslArgs& a, cudaStream_t stream) {

@@ -137,11 +137,12 @@ __device__ __forceinline__ void smooth_forward_role(const VslArgs& a, int role, 
   }
 }
 
-// Backward role: smoothness gradient of one chunk.  ACCUMULATE: atomically add into a zero-initialised
-// (and concurrently accumulated) grad_disp;  otherwise overwrite it.
+// Backward role: smoothness gradient of one chunk.  MODE 0: overwrite grad_disp;  1: atomically add into a
+// zero-initialised (and concurrently accumulated) grad_disp;  2 (fused step, vsl_fused.cu): grad_disp =
+// smoothness gradient + w_s * grad_raw with w_s = upstream(reproj_s) / (sum(mask_s) + 1e-7).
 //   grad(x,y) = inv * ( R(x,y) - R(x-1,y) + D(x,y) - D(x,y-1) - mean_term ),
 //   R = gx * sign(d - d_right) * e_right,  D = gy * sign(d - d_down) * e_down.
-template <bool ACCUMULATE>
+template <int MODE>
 __device__ __forceinline__ void smooth_backward_role(const VslArgs& a, int role) {
   int s, b, chunk;
   smooth_role_ids(a, role, s, b, chunk);
@@ -158,6 +159,8 @@ __device__ __forceinline__ void smooth_backward_role(const VslArgs& a, int role)
   const float* d = sc.disp + (size_t)b * n;
   const float* img = sc.color + (size_t)b * 3 * n;
   float* out = sc.grad_disp + (size_t)b * n;
+  const float* raw = (MODE == 2) ? sc.grad_raw + (size_t)b * n : nullptr;
+  const float w_raw = (MODE == 2) ? scale_grads(a, s).reproj / (a.sums[(size_t)s * sums_stride(a.B) + 1] + 1e-7f) : 0.f;
   const int lane = threadIdx.x & 31;
   const bool xin = ck.x < w, has_r = ck.x + 1 < w, has_l = xin && ck.x > 0;
   SmoothPx cur = smooth_load(d, img, n, (unsigned)(ck.y_lo * w + ck.x), xin);
@@ -184,8 +187,10 @@ __device__ __forceinline__ void smooth_backward_role(const VslArgs& a, int role)
     const float d_here = (xin && has_d) ? gy * sign_of(cur.d - nxt.d) * smooth_weight(cur, nxt) : 0.f;
     if (xin) {
       const float v = ((r_here - r_left) + (d_here - d_up) - mean_term) * inv;
-      if (ACCUMULATE)
+      if (MODE == 1)
         atomicAdd(out + o, v);
+      else if (MODE == 2)
+        out[o] = fmaf(w_raw, __ldg(raw + o), v);
       else
         out[o] = v;
     }

@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(NT, PPEA_BWD_CTAS) vsl_backward_kernel(const _
   // non-deterministic mode: the first CTAs of the grid add the smoothness gradient of every scale (smooth.cuh)
   const int n_smooth = (a.flags & PPEA_F_DETERMINISTIC) ? 0 : a.S * a.B * kSmoothChunks;
   if ((int)blockIdx.x < n_smooth) {
-    smooth_backward_role<true>(a, blockIdx.x);
+    smooth_backward_role<1>(a, blockIdx.x);
     return;
   }
   const int tid = threadIdx.x;

@@ -25,6 +25,7 @@ struct ScaleArgs {
   uint8_t* sel;
   float* grad_disp;
   float* grad_dup;      // deterministic mode: full-res dL/d disp_up scratch (scales with hs != H only)
+  float* grad_raw;      // fused step: un-normalised photometric gradient of disp_s (vsl_fused.cu)
 };
 
 // Kernel argument block (passed by value, lives in the constant bank).
@@ -99,12 +100,19 @@ inline BwdWorkspace bwd_workspace(int B, int H, int W, int S, unsigned flags) {
   return w;
 }
 
+// Fused-step workspace layout (floats): [pose partials: nblk*S*24][raw gradient of disp_s, s = 0..S-1]
+constexpr int kFusedTileWc = 32, kFusedTileHc = 16;
+inline int fused_blocks(int B, int H, int W) { return B * ceil_div(W, kFusedTileWc) * ceil_div(H, kFusedTileHc); }
+
 cudaError_t launch_vsl_forward(const VslArgs& a, cudaStream_t stream);
 cudaError_t launch_vsl_backward(const VslArgs& a, cudaStream_t stream);
 cudaError_t launch_vsl_finish(const VslArgs& a, int nblk_fwd, cudaStream_t stream);
 cudaError_t launch_smooth_backward(const VslArgs& a, cudaStream_t stream);
 cudaError_t launch_upsample_gather(const VslArgs& a, cudaStream_t stream);
 cudaError_t launch_pose_finish(const VslArgs& a, int nblk_bwd, cudaStream_t stream);
+cudaError_t launch_vsl_fused(const VslArgs& a, cudaStream_t stream);
+cudaError_t launch_vsl_grad_finish(const VslArgs& a, cudaStream_t stream);
+cudaError_t launch_pose_finish_fused(const VslArgs& a, cudaStream_t stream);
 
 // Opt a kernel into > 48 KB of dynamic shared memory once per device (the attribute is sticky per
 // function and device); keeping it out of the steady state also keeps it out of CUDA-graph capture.

@@ -1,0 +1,564 @@
+// vsl_fused.cu -- single-pass training step of the view-synthesis loss (mono path): the forward
+// products AND the un-normalised gradient fields of every pyramid scale in ONE launch.
+//
+// Why this is possible.  The only global quantity of the path is the masked-mean normaliser
+// 1/(sum(mask_s) + 1e-7) (trainer.py:1113-1114) -- a scalar per scale that multiplies the whole
+// photometric gradient field.  So the kernel that evaluates the loss of a tile can also push the
+// adjoint of that tile through SSIM, grid_sample, Project3D, BackprojectDepth, disp_to_depth and the
+// bilinear upsample with weight 1, and the backward proper shrinks to "multiply by
+// upstream / (sum(mask_s) + 1e-7) and add the smoothness gradient" (vsl_grad_finish_kernel).  Compared
+// with the forward + backward pair (vsl_fwd.cu / vsl_bwd.cu) the gather of both sources and the SSIM
+// window sums are evaluated once per step instead of twice, and the per-channel phase structure
+// (eight barriers per scale) becomes three phases per scale.
+//
+// A CTA owns a TW x TH tile of one image; lanes of an f2 are the two source frames.
+//   once     stage the target (2-pixel reflection halo) and the un-warped sources; identity loss
+//            (trainer.py:1060-1069) of every pixel q of the tile + 1-pixel halo.
+//   per scale
+//   gather   every cell of the tile + 2-pixel halo: upsample -> depth -> projection -> bilinear
+//            samples of both sources into shared memory; own pixels keep d warped / d(u,v) in
+//            registers and write depth.
+//   pass Q   every q of the tile + 1-pixel halo: 3x3 window sums of the three channels -> SSIM + L1
+//            loss of both sources -> min over sources / selec_reproj / automask (same arithmetic
+//            in every CTA that sees q, so halo decisions agree with the owner's) -> the SSIM
+//            adjoint coefficients (cA, cB, cC) of the SELECTED source only, as scalar planes, plus
+//            the per-source indicator  mask(q) * [sel(q) == lane]; owners also write sel /
+//            loss_px and the masked sums.
+//   fold     d L / d warped_c(p) = sum_{q in 3x3(p)} ind(q) * (cA + cB x(p) + cC y(p))(q) + L1 term,
+//            with the reflection multiplicities, by a sliding three-row window down the thread's
+//            column; folded into d L / d (u, v) with the kept derivatives.
+//   chain    projection / backprojection adjoint -> d L / d depth -> d L / d disp_up -> adjoint of
+//            the upsample into the raw gradient of disp_s (plain store at scale 0, float atomics
+//            above), pose partials.
+#include "vsl_common.cuh"
+#include <type_traits>
+
+#include "smooth.cuh"
+#include "vsl_gather.cuh"
+
+namespace ppea {
+
+template <int TW, int TH, int NT>
+struct FusedSmem {
+  static constexpr int RW = TW + 4, RH = TH + 4, RP = RW * RH;   // value region (2-pixel halo)
+  static constexpr int QW = TW + 2, QH = TH + 2, QP = QW * QH;   // decision / coefficient region (1-pixel halo)
+  float y[3][RP];       // target (broadcast into both lanes at use)
+  f2 x[3][RP];          // un-warped, then warped (source 0, source 1)
+  float cf[9][QP];      // [3 c + e]: cA, cB, cC of channel c for the source selected at q
+  f2 ind[QP];           // mask(q) * [sel(q) == lane]
+  float ident[QP];      // identity loss min_f photo(src_f, tgt)   (scale-invariant)
+  f2 G[12];             // per-source geometry (vsl_math.cuh Geom), lanes = sources
+  float redf[3][NT / 32];
+  float red[24][NT / 32];
+};
+
+struct PhotoQ {
+  f2 L;     // 0.85 mean_c SSIM + 0.15 mean_c |y - x|  (trainer.py:995-1007), both sources
+  f2 cs;    // sum_c x (selec_reproj's darkness test, trainer.py:1078-1079)
+};
+
+// Photometric loss of both sources at one pixel q from its 3x3 window (xq / yq point at the window's
+// top-left cell); with ADJ also the SSIM adjoint coefficients of the three channels (weight W_SSIM).
+template <bool ADJ, int RW, int RP>
+__device__ __forceinline__ PhotoQ photo_q(const f2* __restrict__ xq, const float* __restrict__ yq, bool no_ssim, float w_l1,
+                                          f2 (&co)[9]) {
+  PhotoQ o;
+  o.L = dup2(0.f);
+  o.cs = dup2(0.f);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const f2* xp = xq + c * RP;
+    const float* yp = yq + c * RP;
+    f2 Sx, Sxx, Sxy, Sy, Syy;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const f2 xa = xp[dy * RW], xb = xp[dy * RW + 1], xc = xp[dy * RW + 2];
+      const f2 ya = dup2(yp[dy * RW]), yb = dup2(yp[dy * RW + 1]), yc = dup2(yp[dy * RW + 2]);
+      f2 hx, hxx, hxy, hy, hyy;
+      row_sums_y<f2>(ya, yb, yc, hy, hyy);
+      row_sums_x<f2>(xa, xb, xc, ya, yb, yc, hx, hxx, hxy);
+      if (dy == 0) {
+        Sx = hx, Sxx = hxx, Sxy = hxy, Sy = hy, Syy = hyy;
+      } else {
+        Sx = vadd(Sx, hx), Sxx = vadd(Sxx, hxx), Sxy = vadd(Sxy, hxy), Sy = vadd(Sy, hy), Syy = vadd(Syy, hyy);
+      }
+      if (dy == 1) {
+        const f2 d = vsub(yb, xb);
+        o.L.x = fma_rn(w_l1, fabsf(d.x), o.L.x);
+        o.L.y = fma_rn(w_l1, fabsf(d.y), o.L.y);
+        o.cs = vadd(o.cs, xb);
+      }
+    }
+    if (!no_ssim) {
+      const SsimYT<f2> yst = ssim_y_stats<f2>(Sy, Syy);
+      const SsimTermsT<f2> t = ssim_terms<f2>(Sx, Sxx, Sxy, yst);
+      const f2 inv_d = vrcp(vmul(t.d1, t.d2));
+      const f2 R = vmul(vmul(t.n1, t.n2), inv_d);
+      const f2 v = vfma(dup2(-0.5f), R, dup2(0.5f));
+      o.L = vfma(dup2(PPEA_W_SSIM), mk2(clamp01(v.x), clamp01(v.y)), o.L);
+      if (ADJ) {
+        const f2 k = clamp_pass(v, vmul(dup2(-0.5f * PPEA_W_SSIM), inv_d));
+        const f2 p = vmul(vmul(dup2(2.f), yst.s), vsub(t.n2, t.n1));
+        const f2 q = vmul(vmul(vmul(dup2(2.f), R), Sx), vsub(t.d2, t.d1));
+        co[c * 3 + 0] = vmul(k, vsub(p, q));
+        co[c * 3 + 1] = vmul(k, vmul(vmul(dup2(-18.f), R), t.d1));
+        co[c * 3 + 2] = vmul(k, vmul(dup2(18.f), t.n1));
+      }
+    } else if (ADJ) {
+      co[c * 3 + 0] = co[c * 3 + 1] = co[c * 3 + 2] = dup2(0.f);
+    }
+  }
+  return o;
+}
+
+#ifndef PPEA_FUSED_CTAS
+#define PPEA_FUSED_CTAS 4
+#endif
+constexpr int kFusedTileW = 32;
+constexpr int kFusedTileH = 16;
+constexpr int kFusedThreads = 128;
+
+template <int TW, int TH, int NT, bool POSE>
+__global__ void __launch_bounds__(NT, PPEA_FUSED_CTAS) vsl_fused_kernel(const __grid_constant__ VslArgs a) {
+  using Smem = FusedSmem<TW, TH, NT>;
+  constexpr int RW = Smem::RW, RP = Smem::RP, QW = Smem::QW, QP = Smem::QP;
+  constexpr int R = (TW * TH) / NT;
+  static_assert(TW == 32 && (NT / 32) * R == TH && NT >= 128, "the gather/row mapping assumes lane == tile column and R rows per warp");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+
+  // the first CTAs of the grid collect the smoothness sums of every scale (smooth.cuh)
+  const int n_smooth = a.S * a.B * kSmoothChunks;
+  if ((int)blockIdx.x < n_smooth) {
+    smooth_forward_role(a, blockIdx.x, reinterpret_cast<float*>(smem_raw));
+    return;
+  }
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  int blk = blockIdx.x - n_smooth;
+  const int tile_id = blk;
+  const int tx = blk % a.tiles_x;
+  blk /= a.tiles_x;
+  const int ty = blk % a.tiles_y;
+  const int b = blk / a.tiles_y;
+  const int x0 = tx * TW, y0 = ty * TH;
+  const int H = a.H, W = a.W;
+  const size_t plane = (size_t)H * W;
+  const bool automask = a.flags & PPEA_F_AUTOMASK;
+  const bool no_ssim = a.flags & PPEA_F_NO_SSIM;
+  const bool selec = a.flags & PPEA_F_SELEC_REPROJ;
+  const float l1w = no_ssim ? (1.f / 3.f) : PPEA_W_L1;
+
+  if (tid < 24) {
+    const int f = tid / 12, e = tid % 12;
+    const float v = geom_entry(a.K + b * 16, a.T[f] + b * 16, a.inv_K + b * 16, e);
+    (f ? sm.G[e].y : sm.G[e].x) = v;
+  }
+
+  const float* tgt_b = a.tgt + (size_t)b * 3 * plane;
+  const float* src_b[2] = {a.src[0] + (size_t)b * 3 * plane, a.src[1] + (size_t)b * 3 * plane};
+
+  // ---- stage the target (+ the un-warped sources for the identity loss) with a 2-pixel reflection halo
+  for (int idx = tid; idx < RP; idx += NT) {
+    const int i = idx / RW, j = idx - i * RW;
+    const int py = reflect_index(y0 - 2 + i, H), px = reflect_index(x0 - 2 + j, W);
+    const size_t o = (size_t)py * W + px;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) sm.y[c][idx] = __ldg(tgt_b + c * plane + o);
+    if (automask) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) sm.x[c][idx] = mk2(__ldg(src_b[0] + c * plane + o), __ldg(src_b[1] + c * plane + o));
+    }
+  }
+  __syncthreads();
+
+  // ---- identity loss of every q of the tile + 1 halo (trainer.py:1060-1069), once for all scales
+  if (automask) {
+    for (int qi = tid; qi < QP; qi += NT) {
+      const int i = qi / QW, j = qi - i * QW;
+      const int qy = y0 - 1 + i, qx = x0 - 1 + j;
+      float idl = 0.f;
+      if (qy >= 0 && qy < H && qx >= 0 && qx < W) {
+        f2 unused[9];
+        const PhotoQ ph = photo_q<false, RW, RP>(&sm.x[0][i * RW + j], &sm.y[0][i * RW + j], no_ssim, l1w, unused);
+        idl = fminf(ph.L.x, ph.L.y);
+      }
+      sm.ident[qi] = idl;
+    }
+    __syncthreads();   // the x planes are rewritten by the first gather
+  }
+
+  const float wmax = coord_max(W), hmax = coord_max(H);
+  const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
+  const int col = tid % TW;
+  const int row0 = (tid / TW) * R;
+  const int gx_own = x0 + col;
+  const ColCtx col_own = make_col(sm.G, gx_own, W);              // this thread's tile column (reflect-clamped for partial tiles)
+  const int px_own = col_own.px;
+  const SrcPlanes sp = make_planes(src_b[0], src_b[1], plane);
+  // reflection multiplicities of the taps left/right of this thread's column
+  const f2 mL = dup2((gx_own == 1) ? 2.f : 1.f), mR = dup2((gx_own == W - 2) ? 2.f : 1.f);
+
+#pragma unroll 1
+  for (int s = 0; s < a.S; ++s) {
+    const ScaleArgs& sc = a.sc[s];
+    const float* disp_b = sc.disp + (size_t)b * sc.hs * sc.ws;
+    const bool same_res = (sc.hs == H && sc.ws == W);
+
+    float dep[R];
+    f2 ddx[R][3], ddy[R][3];     // d warped_c / d u, d warped_c / d v  (lanes = sources)
+    f2 gu[R], gv[R];
+
+    // ---- gather.  Warp w walks its own R tile rows (lane == tile column, derivatives kept) plus its share
+    // of the four halo rows; the four halo columns are a flat list of extra cells.
+    ColCtx cc = col_own;
+    if (!same_res) cc.cx = up_coef(cc.px, sc.ws, sc.up_sx);
+    auto gather_row = [&](int i, auto want_deriv, f2 (&dx)[3], f2 (&dy)[3]) -> float {
+      const int py = reflect_index(y0 - 2 + i, H);
+      UpCoef cy;
+      float d;
+      if (same_res) {
+        d = depth_of<true>(disp_b, W, sc.ws, py, cc, cy, a.disp_lo, a.disp_range);
+      } else {
+        cy = up_coef(py, sc.hs, sc.up_sy);
+        d = depth_of<false>(disp_b, W, sc.ws, py, cc, cy, a.disp_lo, a.disp_range);
+      }
+      f2 A[3], val[3];
+      const ProjT<f2> pr = project_cell(sm.G, cc, py, d, a.eps, wmax, hmax, A);
+      sample_sources<decltype(want_deriv)::value, false>(sp, W, pr, wm1, hm1, val, dx, dy);
+      const int ridx = i * RW + col + 2;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) sm.x[c][ridx] = val[c];
+      return d;
+    };
+    {
+      float* depth_b = sc.depth + (size_t)b * plane;
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        dep[k] = gather_row(row0 + k + 2, std::true_type{}, ddx[k], ddy[k]);
+        gu[k] = gv[k] = dup2(0.f);
+        const int gy = y0 + row0 + k;
+        if (gy < H && gx_own < W) depth_b[(unsigned)gy * (unsigned)W + (unsigned)gx_own] = dep[k];   // trainer.py:893
+      }
+    }
+    {
+      f2 u0[3], u1[3];
+      constexpr int NWB = NT / 32;
+      if (wid == 0 || wid == NWB - 1) {
+        const int base = (wid == 0) ? 0 : Smem::RH - 2;
+        gather_row(base, std::false_type{}, u0, u1);
+        gather_row(base + 1, std::false_type{}, u0, u1);
+      }
+      for (int e = tid - 32; e < 4 * Smem::RH && tid >= 32 && tid < NT - 32; e += NT - 64) {
+        const int i = e >> 2, jj = e & 3, j = jj < 2 ? jj : RW - 4 + jj;
+        const int py = reflect_index(y0 - 2 + i, H);
+        ColCtx ce = make_col(sm.G, x0 - 2 + j, W);
+        UpCoef cy;
+        float d;
+        if (same_res) {
+          d = depth_of<true>(disp_b, W, sc.ws, py, ce, cy, a.disp_lo, a.disp_range);
+        } else {
+          ce.cx = up_coef(ce.px, sc.ws, sc.up_sx);
+          cy = up_coef(py, sc.hs, sc.up_sy);
+          d = depth_of<false>(disp_b, W, sc.ws, py, ce, cy, a.disp_lo, a.disp_range);
+        }
+        f2 A[3], val[3];
+        const ProjT<f2> pr = project_cell(sm.G, ce, py, d, a.eps, wmax, hmax, A);
+        sample_sources<false, false>(sp, W, pr, wm1, hm1, val, u0, u1);
+        const int ridx = i * RW + j;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) sm.x[c][ridx] = val[c];
+      }
+    }
+    __syncthreads();
+
+    // ---- pass Q: loss, selection, mask and adjoint coefficients of every q of the tile + 1 halo
+    float s_rm = 0.f, s_m = 0.f;
+#pragma unroll 1
+    for (int qi = tid; qi < QP; qi += NT) {
+      const int i = qi / QW, j = qi - i * QW;
+      const int qy = y0 - 1 + i, qx = x0 - 1 + j;
+      f2 indv = dup2(0.f);
+      float cfo[9];
+#pragma unroll
+      for (int e = 0; e < 9; ++e) cfo[e] = 0.f;
+      if (qy >= 0 && qy < H && qx >= 0 && qx < W) {
+        const size_t o = (size_t)b * plane + (size_t)qy * W + qx;
+        float nz = 0.f;
+        if (automask && sc.noise) nz = __ldg(sc.noise + o);
+        f2 co[9];
+        const PhotoQ ph = photo_q<true, RW, RP>(&sm.x[0][i * RW + j], &sm.y[0][i * RW + j], no_ssim, l1w, co);
+        const Select sl = select_source(ph.L.x, ph.L.y, ph.cs.x, ph.cs.y, selec);
+        bool on = true;
+        if (automask) {
+          const float idl = sc.noise ? add_rn(sm.ident[qi], mul_rn(nz, 0.00001f)) : sm.ident[qi];   // trainer.py:1086-1087
+          on = sl.r <= idl;                                                                       // argmin([r, id]) == 0
+        }
+        if (on) indv = mk2(sl.src == 0 ? 1.f : 0.f, sl.src == 1 ? 1.f : 0.f);
+#pragma unroll
+        for (int e = 0; e < 9; ++e) cfo[e] = (sl.src == 1) ? co[e].y : co[e].x;
+        if (i >= 1 && i <= TH && j >= 1 && j <= TW) {      // owner of q: forward products
+          if (sc.loss_px) sc.loss_px[o] = sl.r;
+          sc.sel[o] = (uint8_t)((unsigned)sl.src | (on ? PPEA_SEL_AUTOMASK : 0u));
+          if (on) {
+            s_rm += sl.r;
+            s_m += 1.f;
+          }
+        }
+      }
+      sm.ind[qi] = indv;
+#pragma unroll
+      for (int e = 0; e < 9; ++e) sm.cf[e][qi] = cfo[e];
+    }
+    s_rm = warp_sum(s_rm);
+    s_m = warp_sum(s_m);
+    if (lane == 0) {
+      sm.redf[0][wid] = s_rm;
+      sm.redf[1][wid] = s_m;
+    }
+    __syncthreads();
+    if (tid < 3) {
+      float t = 0.f;
+      if (tid < 2)
+        for (int w = 0; w < NT / 32; ++w) t += sm.redf[tid][w];
+      a.partials[((size_t)tile_id * a.S + s) * 4 + tid] = t;
+    }
+
+    // ---- fold: box sums of the coefficients (sliding window down this thread's column) -> d L / d (u, v)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      f2 h[3][3];
+#pragma unroll
+      for (int i = 0; i < R + 2; ++i) {
+        const int sl = i % 3;
+        if (!no_ssim) {
+          const int qrow = (row0 + i) * QW + col;
+          const f2 i0 = vmul(mL, sm.ind[qrow]), i1 = sm.ind[qrow + 1], i2 = vmul(mR, sm.ind[qrow + 2]);
+#pragma unroll
+          for (int e = 0; e < 3; ++e) {
+            const float* cp = &sm.cf[c * 3 + e][qrow];
+            h[sl][e] = vfma(dup2(cp[2]), i2, vfma(dup2(cp[1]), i1, vmul(dup2(cp[0]), i0)));
+          }
+        }
+        if (i >= 2) {
+          const int k = i - 2;
+          const int gy = y0 + row0 + k;
+          const int ridx = (row0 + k + 2) * RW + col + 2;
+          const f2 xv = sm.x[c][ridx], yv = dup2(sm.y[c][ridx]);
+          const f2 wl = sm.ind[(row0 + k + 1) * QW + col + 1];
+          const f2 d = vsub(yv, xv);
+          // L1 term:  -ind * l1w * sign(y - x)
+          f2 G = mk2(-wl.x * l1w * sign_of(d.x), -wl.y * l1w * sign_of(d.y));
+          if (!no_ssim) {
+            const f2 mU = dup2((gy == 1) ? 2.f : 1.f), mD = dup2((gy == H - 2) ? 2.f : 1.f);
+            const int su = (i - 2) % 3, smid = (i - 1) % 3;
+            const f2 A = vfma(mU, h[su][0], vfma(mD, h[sl][0], h[smid][0]));
+            const f2 Bc = vfma(mU, h[su][1], vfma(mD, h[sl][1], h[smid][1]));
+            const f2 Cc = vfma(mU, h[su][2], vfma(mD, h[sl][2], h[smid][2]));
+            G = vadd(G, vfma(Bc, xv, vfma(Cc, yv, A)));               // d L / d warped_c(p), both sources
+          }
+          gu[k] = vfma(G, ddx[k][c], gu[k]);
+          gv[k] = vfma(G, ddy[k][c], gv[k]);
+        }
+      }
+    }
+
+    // ---- chain: projection adjoint, depth -> disp, adjoint of the bilinear upsample (weight 1: raw gradient)
+    float* gr_b = sc.grad_raw + (size_t)b * sc.hs * sc.ws;
+    f2 Sw[POSE ? 3 : 1], Swy[POSE ? 3 : 1], Sg[POSE ? 3 : 1];
+#pragma unroll
+    for (int e = 0; e < (POSE ? 3 : 1); ++e) Sw[e] = Swy[e] = Sg[e] = dup2(0.f);
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const int gy = y0 + row0 + k;
+      if (gy < H && gx_own < W) {
+        f2 A[3];
+        const ProjT<f2> pr = project_cell(sm.G, col_own, gy, dep[k], a.eps, wmax, hmax, A);
+        const f2 gc0 = vmul(gu[k], pr.rz), gc1 = vmul(gv[k], pr.rz);
+        const f2 gc2 = vneg(vmul(vfma(gu[k], pr.u, vmul(gv[k], pr.v)), pr.rz));
+        const f2 gd2 = vfma(gc2, A[2], vfma(gc1, A[1], vmul(gc0, A[0])));
+        const float g = gd2.x + gd2.y;
+        if (POSE) {
+          const f2 dk = dup2(dep[k]), fy = dup2(int_to_float(gy));
+          const f2 w0 = vmul(gc0, dk), w1 = vmul(gc1, dk), w2 = vmul(gc2, dk);
+          Sw[0] = vadd(Sw[0], w0);
+          Sw[1] = vadd(Sw[1], w1);
+          Sw[2] = vadd(Sw[2], w2);
+          Swy[0] = vfma(w0, fy, Swy[0]);
+          Swy[1] = vfma(w1, fy, Swy[1]);
+          Swy[2] = vfma(w2, fy, Swy[2]);
+          Sg[0] = vadd(Sg[0], gc0);
+          Sg[1] = vadd(Sg[1], gc1);
+          Sg[2] = vadd(Sg[2], gc2);
+        }
+        const float g_dup = g * ddepth_ddisp(dep[k], a.disp_range);
+        if (same_res) {
+          gr_b[(unsigned)gy * (unsigned)W + (unsigned)gx_own] = g_dup;     // sole owner: plain store, no pre-zero needed
+        } else if (g_dup != 0.f) {
+          const UpCoef cy = up_coef(gy, sc.hs, sc.up_sy), cx = up_coef(gx_own, sc.ws, sc.up_sx);
+          atomicAdd(gr_b + cy.i0 * sc.ws + cx.i0, g_dup * cy.l0 * cx.l0);
+          atomicAdd(gr_b + cy.i0 * sc.ws + cx.i1, g_dup * cy.l0 * cx.l1);
+          atomicAdd(gr_b + cy.i1 * sc.ws + cx.i0, g_dup * cy.l1 * cx.l0);
+          atomicAdd(gr_b + cy.i1 * sc.ws + cx.i1, g_dup * cy.l1 * cx.l1);
+        }
+      }
+    }
+    if (POSE) {
+      // per source f and row r of dL/dP: (sum gc_r*depth*x, sum gc_r*depth*y, sum gc_r*depth, sum gc_r)
+      const float fx = int_to_float(px_own);
+      float v[24];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        v[0 * 12 + r * 4 + 0] = Sw[r].x * fx;
+        v[0 * 12 + r * 4 + 1] = Swy[r].x;
+        v[0 * 12 + r * 4 + 2] = Sw[r].x;
+        v[0 * 12 + r * 4 + 3] = Sg[r].x;
+        v[1 * 12 + r * 4 + 0] = Sw[r].y * fx;
+        v[1 * 12 + r * 4 + 1] = Swy[r].y;
+        v[1 * 12 + r * 4 + 2] = Sw[r].y;
+        v[1 * 12 + r * 4 + 3] = Sg[r].y;
+      }
+#pragma unroll
+      for (int e = 0; e < 24; ++e) {
+        const float t = warp_sum(v[e]);
+        if (lane == 0) sm.red[e][wid] = t;
+      }
+    }
+    __syncthreads();   // fold is done with x / cf / ind: the next scale may overwrite them; red[] is complete
+    if (POSE && tid < 24) {
+      float t = 0.f;
+      for (int w = 0; w < NT / 32; ++w) t += sm.red[tid][w];
+      a.pose_partials[((size_t)tile_id * a.S + s) * 24 + tid] = t;
+    }
+    // (red[] is next written after two more barriers of the following scale)
+  }
+}
+
+cudaError_t launch_vsl_fused(const VslArgs& a, cudaStream_t stream) {
+  using Smem = FusedSmem<kFusedTileW, kFusedTileH, kFusedThreads>;
+  static_assert(sizeof(Smem) <= 227 * 1024, "shared memory tile too large");
+  const int nblk = a.B * a.tiles_x * a.tiles_y + a.S * a.B * kSmoothChunks;
+  cudaError_t e;
+  if (a.flags & PPEA_F_GRAD_POSE) {
+    auto kern = vsl_fused_kernel<kFusedTileW, kFusedTileH, kFusedThreads, true>;
+    e = ensure_dynamic_smem(kern, (int)sizeof(Smem));
+    if (e != cudaSuccess) return e;
+    kern<<<nblk, kFusedThreads, sizeof(Smem), stream>>>(a);
+  } else {
+    auto kern = vsl_fused_kernel<kFusedTileW, kFusedTileH, kFusedThreads, false>;
+    e = ensure_dynamic_smem(kern, (int)sizeof(Smem));
+    if (e != cudaSuccess) return e;
+    kern<<<nblk, kFusedThreads, sizeof(Smem), stream>>>(a);
+  }
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// Backward proper of the fused step, one thread per pixel of disp_s, every scale in one launch:
+//   grad_disp_s = w_s * raw_s + d(smoothness term)/d disp_s,
+//   w_s = (upstream of reproj_s) / (sum(mask_s) + 1e-7)          trainer.py:1113-1114
+// The smoothness gradient is the one of smooth.cuh (same formula, flat indexing instead of the
+// column walk: here the term has a launch of its own, so it is laid out for bandwidth):
+//   grad(x,y) = inv_b * ( R(x,y) - R(x-1,y) + D(x,y) - D(x,y-1) - mean_term_b ),
+//   R = gx * sign(d - d_right) * e_right,  D = gy * sign(d - d_down) * e_down.
+// With REZERO the raw field of the coarse scales (accumulated atomically by the next step) is
+// cleared on the way out, so a replayed plan needs no memset.
+// ---------------------------------------------------------------------------
+constexpr int kGradFinishThreads = 256;
+
+__device__ __forceinline__ float smooth_edge(const float* __restrict__ d, const float* __restrict__ img, unsigned n, unsigned i,
+                                             unsigned j, float gscale) {
+  // gscale * sign(d_i - d_j) * exp(-mean_c |I_i - I_j|)   (layers.py:214-221)
+  return gscale * sign_of(__ldg(d + i) - __ldg(d + j)) * smooth_edge_weight(img, n, i, j);
+}
+
+__global__ void __launch_bounds__(kGradFinishThreads) vsl_grad_finish_kernel(const __grid_constant__ VslArgs a, int4 blk_end) {
+  // scale of this CTA (blk_end.{x,y,z,w}: first block index past the blocks of scale 0..3)
+  const int blk = blockIdx.x;
+  const int s = (blk >= blk_end.x) + (blk >= blk_end.y) + (blk >= blk_end.z);
+  const int blk0 = s == 0 ? 0 : (s == 1 ? blk_end.x : (s == 2 ? blk_end.y : blk_end.z));
+  const ScaleArgs& sc = a.sc[s];
+  const int h = sc.hs, w = sc.ws;
+  const unsigned n = (unsigned)(h * w);
+  const unsigned idx = (unsigned)(blk - blk0) * kGradFinishThreads + threadIdx.x;
+  if (idx >= (unsigned)a.B * n) return;
+  const unsigned b = idx / n, o = idx - b * n;
+  const int y = (int)(o / (unsigned)w), x = (int)(o - (unsigned)y * (unsigned)w);
+  const float* row = a.sums + (size_t)s * sums_stride(a.B);
+  const float* img_sums = row + PPEA_SUMS_PER_SCALE + 4 * b;                                   // (sum d, X_b, Y_b)
+  const float inv = 1.f / (img_sums[0] / (float)n + 1e-7f);
+  const ScaleGrads sg = scale_grads(a, s);
+  const float gx = sg.smooth / ((float)a.B * h * (w - 1)), gy = sg.smooth / ((float)a.B * (h - 1) * w);
+  const float mean_term = inv * (gx * img_sums[1] + gy * img_sums[2]) / (float)n;
+  const float w_raw = sg.reproj / (row[1] + 1e-7f);
+  const float* d = sc.disp + (size_t)b * n;
+  const float* img = sc.color + (size_t)b * 3 * n;
+  const float r_here = (x + 1 < w) ? smooth_edge(d, img, n, o, o + 1u, gx) : 0.f;
+  const float r_left = (x > 0) ? smooth_edge(d, img, n, o - 1u, o, gx) : 0.f;
+  const float d_here = (y + 1 < h) ? smooth_edge(d, img, n, o, o + (unsigned)w, gy) : 0.f;
+  const float d_up = (y > 0) ? smooth_edge(d, img, n, o - (unsigned)w, o, gy) : 0.f;
+  const float v = ((r_here - r_left) + (d_here - d_up) - mean_term) * inv;
+  float* raw = sc.grad_raw + (size_t)b * n;
+  sc.grad_disp[(size_t)b * n + o] = fmaf(w_raw, raw[o], v);
+  if ((a.flags & PPEA_F_RAW_PREZEROED) && (h != a.H || w != a.W)) raw[o] = 0.f;
+}
+
+cudaError_t launch_vsl_grad_finish(const VslArgs& a, cudaStream_t stream) {
+  int end[4] = {0, 0, 0, 0};
+  int acc = 0;
+  for (int s = 0; s < 4; ++s) {
+    if (s < a.S) acc += ceil_div(a.B * a.sc[s].hs * a.sc[s].ws, kGradFinishThreads);
+    end[s] = acc;
+  }
+  vsl_grad_finish_kernel<<<acc, kGradFinishThreads, 0, stream>>>(a, make_int4(end[0], end[1], end[2], end[3]));
+  return cudaGetLastError();
+}
+
+// Pose gradient of the fused step: per-scale weighted, fixed-order reduction of the raw per-CTA
+// d L / d P_f partials of each image, then d L / d T_f = K[:3,:]^T @ dL/dP_f  (autograd of layers.py:185).
+__global__ void __launch_bounds__(32 * 24) pose_finish_fused_kernel(const __grid_constant__ VslArgs a, int tiles_per_image) {
+  __shared__ double Q[24];
+  __shared__ double gP[24];
+  __shared__ float wS[kMaxScales];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, e = tid >> 5;   // warp e reduces entry e
+  if (tid < a.S) wS[tid] = scale_grads(a, tid).reproj / (a.sums[(size_t)tid * sums_stride(a.B) + 1] + 1e-7f);
+  __syncthreads();
+  {
+    // entries of image b: [tile][scale][24]; every load is independent of the others
+    double t = 0;
+    const int S = a.S, items = tiles_per_image * S;
+    const float* p = a.pose_partials + (size_t)b * items * 24 + e;
+#pragma unroll 4
+    for (int i = lane; i < items; i += 32) t += (double)(wS[i % S] * p[(size_t)i * 24]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) Q[e] = t;
+  }
+  __syncthreads();
+  const float* K = a.K + b * 16;
+  const float* iK = a.inv_K + b * 16;
+  if (tid < 24) {
+    const int f = tid / 12, ee = tid % 12, r = ee / 4, j = ee % 4;
+    double t;
+    if (j == 3) {
+      t = Q[f * 12 + r * 4 + 3];
+    } else {
+      t = 0;
+      for (int k = 0; k < 3; ++k) t += Q[f * 12 + r * 4 + k] * (double)iK[j * 4 + k];
+    }
+    gP[tid] = t;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    const int f = tid / 16, ee = tid % 16, i = ee / 4, j = ee % 4;
+    double t = 0;
+    for (int r = 0; r < 3; ++r) t += (double)K[r * 4 + i] * gP[f * 12 + r * 4 + j];
+    a.grad_T[f][b * 16 + ee] = (float)t;
+  }
+}
+
+cudaError_t launch_pose_finish_fused(const VslArgs& a, cudaStream_t stream) {
+  pose_finish_fused_kernel<<<a.B, 32 * 24, 0, stream>>>(a, a.tiles_x * a.tiles_y);
+  return cudaGetLastError();
+}
+
+}  // namespace ppea

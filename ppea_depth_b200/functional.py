@@ -52,6 +52,14 @@ class VslConfig:
     first_scale: int = 0
     total_scales: Optional[int] = None
     want_loss_px: bool = False
+    fused: Optional[bool] = None     # single-launch training step (vsl_fused.cu); None = whenever it applies
+                                     # (mono path, atomics backward, some input requires grad)
+
+    def use_fused(self, needs_grad):
+        ok = (not self.is_multi) and (not self.deterministic)
+        if self.fused and not ok:
+            raise ValueError("the fused training step covers the mono path with the non-deterministic backward only")
+        return bool(needs_grad) and ok and (self.fused is None or self.fused)
 
     def flags(self, grad_pose):
         f = 0
@@ -149,6 +157,14 @@ def _fill_params(bundle, flags, T, disps, depth, loss_px, sel, grad_disp, sums, 
     return p
 
 
+def _fused_struct(ws):
+    f = C.PpeaVslFused()
+    f.struct_size = ctypes.sizeof(C.PpeaVslFused)
+    f.workspace = ws.data_ptr()
+    f.workspace_bytes = ws.numel() * 4
+    return f
+
+
 class _FusedViewSynthLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, bundle, T0, T1, *disps):
@@ -165,10 +181,22 @@ class _FusedViewSynthLoss(torch.autograd.Function):
             sums = torch.empty(lib.ppea_vsl_sums_floats(B, S), device=dev, dtype=torch.float32)
             losses = torch.empty(1 + C.LOSSES_PER_SCALE * S, device=dev, dtype=torch.float32)
             ws = torch.empty(lib.ppea_vsl_workspace_bytes(B, H, W, S) // 4, device=dev, dtype=torch.float32)
-            flags = bundle.cfg.flags(grad_pose=False)
-            p = _fill_params(bundle, flags, T, disps, depth, loss_px, sel, None, sums, losses, ws)
-            C.check(lib.ppea_vsl_forward(ctypes.byref(p), _stream()))
+            fused = bundle.cfg.use_fused(any(ctx.needs_input_grad))
+            fws = None
+            if fused:
+                # one launch evaluates the loss and the un-normalised gradient fields; backward() only rescales them
+                grad_pose = bool(ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
+                flags = bundle.cfg.flags(grad_pose=grad_pose)
+                p = _fill_params(bundle, flags, T, disps, depth, loss_px, sel, None, sums, losses, ws)
+                fws = torch.empty(max(lib.ppea_vsl_fused_workspace_bytes(ctypes.byref(p)) // 4, 4), device=dev, dtype=torch.float32)
+                C.check(lib.ppea_vsl_fused_forward(ctypes.byref(p), ctypes.byref(_fused_struct(fws)), _stream()))
+                ctx.fused_flags = flags
+            else:
+                flags = bundle.cfg.flags(grad_pose=False)
+                p = _fill_params(bundle, flags, T, disps, depth, loss_px, sel, None, sums, losses, ws)
+                C.check(lib.ppea_vsl_forward(ctypes.byref(p), _stream()))
         ctx.bundle = bundle
+        ctx.fused_ws = fws
         ctx.saved = (T, disps, depth, sel, loss_px, sums)
         ctx.mark_non_differentiable(*depth, *sel, *[t for t in loss_px if t is not None], sums)
         outs = [losses] + depth + sel + [sums] + [t for t in loss_px if t is not None]
@@ -186,9 +214,23 @@ class _FusedViewSynthLoss(torch.autograd.Function):
             if grad_losses is None:
                 grad_losses = torch.zeros(1 + C.LOSSES_PER_SCALE * S, device=dev, dtype=torch.float32)
             grad_losses = grad_losses.contiguous().float()
-            flags = bundle.cfg.flags(grad_pose=grad_pose)
+            if ctx.fused_ws is not None:
+                flags = ctx.fused_flags
+                grad_pose = bool(flags & C.F_GRAD_POSE)
+            else:
+                flags = bundle.cfg.flags(grad_pose=grad_pose)
             grad_disp = [torch.empty_like(d) for d in disps]
             gT = [torch.empty(B, 4, 4, device=dev, dtype=torch.float32) for _ in range(2)] if grad_pose else None
+            if ctx.fused_ws is not None:
+                scratch_fwd = torch.empty(4, device=dev, dtype=torch.float32)   # forward workspace is not used by backward
+                p = _fill_params(bundle, flags, T, disps, depth, loss_px, sel, grad_disp, sums, grad_losses, scratch_fwd)
+                g = C.PpeaVslGrads()
+                g.struct_size = ctypes.sizeof(C.PpeaVslGrads)
+                g.grad_losses = grad_losses.data_ptr()
+                if grad_pose:
+                    g.grad_T[0], g.grad_T[1] = gT[0].data_ptr(), gT[1].data_ptr()
+                C.check(lib.ppea_vsl_fused_backward(ctypes.byref(p), ctypes.byref(g), ctypes.byref(_fused_struct(ctx.fused_ws)), _stream()))
+                return (None, gT[0] if grad_pose else None, gT[1] if grad_pose else None, *grad_disp)
             ws_bytes = lib.ppea_vsl_backward_workspace_bytes(B, H, W, S, flags)
             ws = torch.empty(max(ws_bytes // 4, 4), device=dev, dtype=torch.float32)
             scratch_fwd = torch.empty(4, device=dev, dtype=torch.float32)   # forward workspace is not used by backward

@@ -53,6 +53,7 @@ def _config(self, is_multi, **kw):
         min_depth=float(o.min_depth), max_depth=float(o.max_depth),
         disparity_smoothness=float(_opt(self, "disparity_smoothness", 1e-3)),
         want_loss_px=bool(getattr(self, "ppea_keep_maps", False)),
+        fused=getattr(self, "ppea_fused", None),
         **kw)
 
 
@@ -170,7 +171,7 @@ def compute_losses(self, inputs, outputs, is_multi=False):
     return losses, []
 
 
-def install(trainer_cls, deterministic=False, noise_mode="reference"):
+def install(trainer_cls, deterministic=False, noise_mode="reference", fused=None):
     """Rebinds the reference Trainer's loss methods to the fused implementation."""
     trainer_cls.generate_images_pred = generate_images_pred
     trainer_cls.compute_reprojection_loss = compute_reprojection_loss
@@ -178,6 +179,7 @@ def install(trainer_cls, deterministic=False, noise_mode="reference"):
     trainer_cls.compute_losses = compute_losses
     trainer_cls.ppea_deterministic = deterministic
     trainer_cls.ppea_noise_mode = noise_mode
+    trainer_cls.ppea_fused = fused     # None: single-launch training step whenever it applies (functional.VslConfig.fused)
     return trainer_cls
 
 
@@ -185,8 +187,9 @@ class ViewSynthesisLoss:
     """Stand-alone holder of the four methods for callers without the reference Trainer
     (tests, bench.py): ``ViewSynthesisLoss(opt).generate_images_pred(inputs, outputs)`` etc."""
 
-    def __init__(self, opt, deterministic=False, noise_mode="reference", keep_maps=False):
+    def __init__(self, opt, deterministic=False, noise_mode="reference", keep_maps=False, fused=None):
         self.opt = opt
+        self.ppea_fused = fused
         self.ppea_deterministic = deterministic
         self.ppea_noise_mode = noise_mode
         self.ppea_keep_maps = keep_maps

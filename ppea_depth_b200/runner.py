@@ -25,7 +25,7 @@ class FusedPlan:
                  src: Sequence[torch.Tensor], K: torch.Tensor, inv_K: torch.Tensor, colors: Sequence[torch.Tensor],
                  noise: Optional[Sequence[torch.Tensor]] = None, cons_mask: Optional[torch.Tensor] = None,
                  aug_mask: Optional[torch.Tensor] = None, mono_depth: Optional[Sequence[torch.Tensor]] = None,
-                 grad_pose: Optional[bool] = None):
+                 grad_pose: Optional[bool] = None, fused: Optional[bool] = None):
         lib = C.lib()
         self.cfg = cfg
         self.tgt = _f32c(tgt, "tgt")
@@ -43,6 +43,11 @@ class FusedPlan:
         self.aug_mask = _f32c(aug_mask.reshape(-1)[:B], "aug_mask") if (cfg.is_multi and cfg.match_aug) else None
         self.mono_depth = [_f32c(m, "mono_depth") for m in mono_depth] if cfg.is_multi else None
         self.grad_pose = (not cfg.is_multi) if grad_pose is None else bool(grad_pose)
+        # single-launch training step (vsl_fused.cu) wherever it applies: mono path, atomics backward
+        can_fuse = (not cfg.is_multi) and (not cfg.deterministic)
+        if fused and not can_fuse:
+            raise ValueError("the fused training step covers the mono path with the non-deterministic backward only")
+        self.fused = can_fuse if fused is None else bool(fused)
         f32 = dict(device=dev, dtype=torch.float32)
         with torch.cuda.device(dev):
             self.depth = [torch.empty(B, 1, H, W, **f32) for _ in range(S)]
@@ -56,7 +61,11 @@ class FusedPlan:
             self.grad_T = [torch.empty(B, 4, 4, **f32) for _ in range(2)] if self.grad_pose else None
             self.flags_fwd = cfg.flags(grad_pose=False)
             self.flags_bwd = cfg.flags(grad_pose=self.grad_pose)
-            if not cfg.deterministic:     # the forward zero-fills the persistent grad buffers on the fly
+            if self.fused:
+                # the plan owns the fused workspace: zero-filled once here, kept clean by every backward
+                self.flags_bwd |= C.F_RAW_PREZEROED
+                self.flags_fwd = self.flags_bwd
+            elif not cfg.deterministic:   # the forward zero-fills the persistent grad buffers on the fly
                 self.flags_bwd |= C.F_GRAD_PREZEROED
             self.ws_fwd = torch.empty(max(lib.ppea_vsl_workspace_bytes(B, H, W, S) // 4, 4), **f32)
             self.ws_bwd = torch.empty(max(lib.ppea_vsl_backward_workspace_bytes(B, H, W, S, self.flags_bwd) // 4, 4), **f32)
@@ -72,14 +81,26 @@ class FusedPlan:
         self._g = g
         self._lib = lib
         self.graph = None
+        self._f = None
+        self._raw_pending = False
+        if self.fused:
+            with torch.cuda.device(dev):
+                self.ws_fused = torch.zeros(max(lib.ppea_vsl_fused_workspace_bytes(ctypes.byref(self._p_fwd)) // 4, 4), **f32)
+            f = C.PpeaVslFused()
+            f.struct_size = ctypes.sizeof(C.PpeaVslFused)
+            f.workspace = self.ws_fused.data_ptr()
+            f.workspace_bytes = self.ws_fused.numel() * 4
+            self._f = f
 
     # kernels launched by one forward / backward call (for bench.py's gpu_launches)
     @property
     def launches_forward(self):
-        return 2            # fused forward (tiles + smoothness CTAs), finish
+        return 2            # fused forward / fused step (tiles + smoothness CTAs), finish
 
     @property
     def launches_backward(self):
+        if self.fused:
+            return 1 + (1 if self.grad_pose else 0)     # gradient finish (rescale + smoothness), pose finish
         n = 1 + (1 if self.grad_pose else 0)     # fused backward (tiles + smoothness CTAs), pose finish
         if self.cfg.deterministic:               # + smoothness backward + one upsample gather per coarse scale
             n += 1 + sum(1 for d in self.disps if tuple(d.shape[-2:]) != (self.H, self.W))
@@ -124,11 +145,22 @@ class FusedPlan:
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def forward(self):
-        C.check(self._lib.ppea_vsl_forward(ctypes.byref(self._p_fwd), self._stream()))
+        if self.fused:
+            if self._raw_pending:         # a forward without its backward left the raw coarse-scale fields dirty
+                self.ws_fused.zero_()
+            self._raw_pending = True
+            C.check(self._lib.ppea_vsl_fused_forward(ctypes.byref(self._p_fwd), ctypes.byref(self._f), self._stream()))
+        else:
+            C.check(self._lib.ppea_vsl_forward(ctypes.byref(self._p_fwd), self._stream()))
         return self.losses
 
     def backward(self):
-        C.check(self._lib.ppea_vsl_backward(ctypes.byref(self._p_bwd), ctypes.byref(self._g), self._stream()))
+        if self.fused:
+            self._raw_pending = False
+            C.check(self._lib.ppea_vsl_fused_backward(ctypes.byref(self._p_bwd), ctypes.byref(self._g), ctypes.byref(self._f),
+                                                      self._stream()))
+        else:
+            C.check(self._lib.ppea_vsl_backward(ctypes.byref(self._p_bwd), ctypes.byref(self._g), self._stream()))
         return self.grad_disp, self.grad_T
 
     def step(self):
@@ -160,6 +192,8 @@ class FusedPlan:
     # ---- per-stage device timing (bench.py's roofline leg) -------------------
     FWD_STAGES = ("fwd_unused0", "vsl_forward_kernel", "fwd_unused1", "finish")
     BWD_STAGES = ("grad_init", "vsl_backward_kernel", "upsample_gather", "pose_finish")
+    FUSED_FWD_STAGES = ("grad_raw_zero", "vsl_fused_kernel", "fwd_unused1", "finish")
+    FUSED_BWD_STAGES = ("bwd_unused0", "vsl_grad_finish_kernel", "bwd_unused1", "pose_finish")
 
     def enable_trace(self):
         """Asks the library to record a CUDA event before/after every stage of forward and
@@ -186,7 +220,8 @@ class FusedPlan:
         """Stage durations (ms) of the most recent traced forward + backward."""
         out = {}
         ms = ctypes.c_float()
-        for arr, names in zip(self._ev, (self.FWD_STAGES, self.BWD_STAGES)):
+        stages = (self.FUSED_FWD_STAGES, self.FUSED_BWD_STAGES) if self.fused else (self.FWD_STAGES, self.BWD_STAGES)
+        for arr, names in zip(self._ev, stages):
             for i, name in enumerate(names):
                 C.check(self._lib.ppea_event_elapsed_ms(arr[i], arr[i + 1], ctypes.byref(ms)))
                 out[name] = ms.value

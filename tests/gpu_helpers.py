@@ -31,10 +31,10 @@ class FeedNoise:
         torch.randn = self.orig
 
 
-def run_cuda(inputs, outputs, opt, is_multi, noise, deterministic=False, backward=True, device="cuda"):
+def run_cuda(inputs, outputs, opt, is_multi, noise, deterministic=False, backward=True, device="cuda", fused=None):
     """Returns (losses, grads, maps) like oracle.run_fwd_bwd, computed by the CUDA path."""
     ins, outs = O.clone_batch(inputs, outputs, device=device)
-    mod = ViewSynthesisLoss(opt, deterministic=deterministic, keep_maps=True)
+    mod = ViewSynthesisLoss(opt, deterministic=deterministic, keep_maps=True, fused=fused)
     with FeedNoise(noise if noise is not None else []):
         mod.generate_images_pred(ins, outs, is_multi)
         losses, _ = mod.compute_losses(ins, outs, is_multi)

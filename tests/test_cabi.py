@@ -53,6 +53,7 @@ int main(void) {
   printf("%zu %zu %zu %zu %zu %zu\\n", offsetof(PpeaVslParams, tgt), offsetof(PpeaVslParams, scales), offsetof(PpeaVslParams, sums),
          offsetof(PpeaVslParams, workspace_bytes), offsetof(PpeaVslParams, trace_events), offsetof(PpeaVslScale, grad_disp));
   printf("%zu %zu\\n", offsetof(PpeaVslGrads, grad_T), offsetof(PpeaVslGrads, workspace_bytes));
+  printf("%zu %zu %zu\\n", sizeof(PpeaVslFused), offsetof(PpeaVslFused, workspace), offsetof(PpeaVslFused, workspace_bytes));
   return 0;
 }''')
     exe = tmp_path / "layout"
@@ -61,7 +62,8 @@ int main(void) {
     got = [int(x) for x in out]
     P, S, G = C.PpeaVslParams, C.PpeaVslScale, C.PpeaVslGrads
     want = [ctypes.sizeof(P), ctypes.sizeof(S), ctypes.sizeof(G), P.tgt.offset, P.scales.offset, P.sums.offset,
-            P.workspace_bytes.offset, P.trace_events.offset, S.grad_disp.offset, G.grad_T.offset, G.workspace_bytes.offset]
+            P.workspace_bytes.offset, P.trace_events.offset, S.grad_disp.offset, G.grad_T.offset, G.workspace_bytes.offset,
+            ctypes.sizeof(C.PpeaVslFused), C.PpeaVslFused.workspace.offset, C.PpeaVslFused.workspace_bytes.offset]
     assert got == want
 
 
@@ -88,6 +90,8 @@ def test_argument_validation_happens_on_the_host(lib):
     p.num_scales = 1
     p.flags = C.F_MULTI | C.F_GRAD_POSE
     assert lib.ppea_vsl_forward(ctypes.byref(p), None) == -4          # T is detached on the multi path
+    assert lib.ppea_vsl_fused_forward(ctypes.byref(p), None, None) == -4      # (the MULTI|GRAD_POSE contradiction is found first)
+    assert lib.ppea_vsl_fused_workspace_bytes(None) == 0
     assert lib.ppea_ssim_forward(None, None, None, 3, 8, 8, None) == -1
     assert lib.ppea_ssim_forward(1, 1, 1, 3, 0, 8, None) == -2
     assert lib.ppea_smooth_forward(None, None, None, None, 1, 8, 8, None) == -1
