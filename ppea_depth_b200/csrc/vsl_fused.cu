@@ -173,8 +173,17 @@ __global__ void __launch_bounds__(NT, PPEA_FUSED_CTAS) vsl_fused_kernel(const __
 
   // ---- identity loss of every q of the tile + 1 halo (trainer.py:1060-1069), once for all scales
   if (automask) {
-    for (int qi = tid; qi < QP; qi += NT) {
-      const int i = qi / QW, j = qi - i * QW;
+    constexpr int QH = Smem::QH, NEX = (2 * QH + 31) / 32;      // same work items as pass Q below
+#pragma unroll 1
+    for (int item = wid; item < QH + NEX; item += NT / 32) {
+      int i = item, j = lane;
+      if (item >= QH) {
+        const int e = (item - QH) * 32 + lane;
+        if (e >= 2 * QH) break;
+        i = e >> 1;
+        j = 32 + (e & 1);
+      }
+      const int qi = i * QW + j;
       const int qy = y0 - 1 + i, qx = x0 - 1 + j;
       float idl = 0.f;
       if (qy >= 0 && qy < H && qx >= 0 && qx < W) {
@@ -273,9 +282,19 @@ __global__ void __launch_bounds__(NT, PPEA_FUSED_CTAS) vsl_fused_kernel(const __
 
     // ---- pass Q: loss, selection, mask and adjoint coefficients of every q of the tile + 1 halo
     float s_rm = 0.f, s_m = 0.f;
+    // Work items: one Q row per warp (lane == column, so every shared-memory access of the warp is one
+    // contiguous, bank-conflict-free run), then the two right-most Q columns as a flat list of cells.
+    constexpr int QH = Smem::QH, NEX = (2 * QH + 31) / 32;
 #pragma unroll 1
-    for (int qi = tid; qi < QP; qi += NT) {
-      const int i = qi / QW, j = qi - i * QW;
+    for (int item = wid; item < QH + NEX; item += NT / 32) {
+      int i = item, j = lane;
+      if (item >= QH) {
+        const int e = (item - QH) * 32 + lane;
+        if (e >= 2 * QH) break;
+        i = e >> 1;
+        j = 32 + (e & 1);
+      }
+      const int qi = i * QW + j;
       const int qy = y0 - 1 + i, qx = x0 - 1 + j;
       f2 indv = dup2(0.f);
       float cfo[9];
