@@ -347,11 +347,9 @@ __global__ void __launch_bounds__(NT, PPEA_BWD_CTAS) vsl_backward_kernel(const _
         v[1 * 12 + r * 4 + 3] = Sg[r].y;
       }
       const int lane = tid & 31, wid = tid >> 5;
-  #pragma unroll
-      for (int e = 0; e < 24; ++e) {
-        const float t = warp_sum(v[e]);
-        if (lane == 0) sm.red[e][wid] = t;
-      }
+      const float t = warp_sum24(v, lane);
+      const int e = warp_sum24_index(lane);
+      if (e < 24) sm.red[e][wid] = t;
       __syncthreads();
       if (tid < 24) {
         float t = 0.f;

@@ -155,6 +155,34 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// Cross-lane sums of 24 per-lane values with 24 shuffles instead of 24 x 5: every step halves the
+// number of values a lane carries (the lane keeps the half selected by one bit of its id and hands the
+// other half to its partner), 24 -> 12 -> 6 -> 3(+1 pad) -> 2 -> 1.  Returns the total of entry
+// `warp_sum24_index(lane)`; lanes whose index is 24 or more hold padding.  Fixed summation order.
+template <int N>
+__device__ __forceinline__ void warp_halve(float (&v)[24], int lane, int o) {
+  const bool hi = lane & o;
+#pragma unroll
+  for (int k = 0; k < N / 2; ++k) {
+    const float send = hi ? v[k] : v[k + N / 2];
+    const float keep = hi ? v[k + N / 2] : v[k];
+    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+  }
+}
+__device__ __forceinline__ float warp_sum24(float (&v)[24], int lane) {
+  warp_halve<24>(v, lane, 16);
+  warp_halve<12>(v, lane, 8);
+  warp_halve<6>(v, lane, 4);
+  v[3] = 0.f;
+  warp_halve<4>(v, lane, 2);
+  warp_halve<2>(v, lane, 1);
+  return v[0];
+}
+__device__ __forceinline__ int warp_sum24_index(int lane) {
+  const int sub = lane & 3;                                  // 3 is the padding slot
+  return sub == 3 ? 24 : ((lane & 16) ? 12 : 0) + ((lane & 8) ? 6 : 0) + ((lane & 4) ? 3 : 0) + sub;
+}
+
 // Effective upstream weights of the three per-scale terms, from the gradient of the
 // `losses` vector (layout in ppea_vsl.h): losses[0] = sum_s loss_s / total_scales,
 // loss_s = reproj_s + cons_s + (disparity_smoothness / 2^s) * smooth_s.

@@ -221,16 +221,16 @@ __global__ void __launch_bounds__(NT, PPEA_FUSED_CTAS) vsl_fused_kernel(const __
     // of the four halo rows; the four halo columns are a flat list of extra cells.
     ColCtx cc = col_own;
     if (!same_res) cc.cx = up_coef(cc.px, sc.ws, sc.up_sx);
-    auto gather_row = [&](int i, auto want_deriv, f2 (&dx)[3], f2 (&dy)[3]) -> float {
+    // the (upsampled) disparity of region row i at this thread's column: loads only, so the rows of a
+    // thread can have them in flight together, ahead of the dependent source gathers
+    auto load_disp = [&](int i) -> float {
       const int py = reflect_index(y0 - 2 + i, H);
-      UpCoef cy;
-      float d;
-      if (same_res) {
-        d = depth_of<true>(disp_b, W, sc.ws, py, cc, cy, a.disp_lo, a.disp_range);
-      } else {
-        cy = up_coef(py, sc.hs, sc.up_sy);
-        d = depth_of<false>(disp_b, W, sc.ws, py, cc, cy, a.disp_lo, a.disp_range);
-      }
+      if (same_res) return __ldg(disp_b + ((unsigned)py * (unsigned)W + (unsigned)cc.px));
+      return up_sample(disp_b, sc.ws, up_coef(py, sc.hs, sc.up_sy), cc.cx);
+    };
+    auto gather_row = [&](int i, float dup, auto want_deriv, f2 (&dx)[3], f2 (&dy)[3]) -> float {
+      const int py = reflect_index(y0 - 2 + i, H);
+      const float d = depth_from_disp_fast(dup, a.disp_lo, a.disp_range);
       f2 A[3], val[3];
       const ProjT<f2> pr = project_cell(sm.G, cc, py, d, a.eps, wmax, hmax, A);
       sample_sources<decltype(want_deriv)::value, false>(sp, W, pr, wm1, hm1, val, dx, dy);
@@ -242,8 +242,10 @@ __global__ void __launch_bounds__(NT, PPEA_FUSED_CTAS) vsl_fused_kernel(const __
     {
       float* depth_b = sc.depth + (size_t)b * plane;
 #pragma unroll
+      for (int k = 0; k < R; ++k) dep[k] = load_disp(row0 + k + 2);
+#pragma unroll
       for (int k = 0; k < R; ++k) {
-        dep[k] = gather_row(row0 + k + 2, std::true_type{}, ddx[k], ddy[k]);
+        dep[k] = gather_row(row0 + k + 2, dep[k], std::true_type{}, ddx[k], ddy[k]);
         gu[k] = gv[k] = dup2(0.f);
         const int gy = y0 + row0 + k;
         if (gy < H && gx_own < W) depth_b[(unsigned)gy * (unsigned)W + (unsigned)gx_own] = dep[k];   // trainer.py:893
@@ -254,8 +256,9 @@ __global__ void __launch_bounds__(NT, PPEA_FUSED_CTAS) vsl_fused_kernel(const __
       constexpr int NWB = NT / 32;
       if (wid == 0 || wid == NWB - 1) {
         const int base = (wid == 0) ? 0 : Smem::RH - 2;
-        gather_row(base, std::false_type{}, u0, u1);
-        gather_row(base + 1, std::false_type{}, u0, u1);
+        const float da = load_disp(base), db = load_disp(base + 1);
+        gather_row(base, da, std::false_type{}, u0, u1);
+        gather_row(base + 1, db, std::false_type{}, u0, u1);
       }
       for (int e = tid - 32; e < 4 * Smem::RH && tid >= 32 && tid < NT - 32; e += NT - 64) {
         const int i = e >> 2, jj = e & 3, j = jj < 2 ? jj : RW - 4 + jj;
@@ -436,11 +439,9 @@ __global__ void __launch_bounds__(NT, PPEA_FUSED_CTAS) vsl_fused_kernel(const __
         v[1 * 12 + r * 4 + 2] = Sw[r].y;
         v[1 * 12 + r * 4 + 3] = Sg[r].y;
       }
-#pragma unroll
-      for (int e = 0; e < 24; ++e) {
-        const float t = warp_sum(v[e]);
-        if (lane == 0) sm.red[e][wid] = t;
-      }
+      const float t = warp_sum24(v, lane);
+      const int e = warp_sum24_index(lane);
+      if (e < 24) sm.red[e][wid] = t;
     }
     __syncthreads();   // fold is done with x / cf / ind: the next scale may overwrite them; red[] is complete
     if (POSE && tid < 24) {

@@ -228,8 +228,10 @@ PPEA_HD UpCoef up_coef(int dst, int in_size, float scale) {
 PPEA_HD float up_sample(const float* __restrict__ d, int w_s, const UpCoef& cy, const UpCoef& cx) {
   // 32-bit element offsets from one base pointer: one IMAD.WIDE.U32 per address on the device
   const unsigned r0 = (unsigned)cy.i0 * (unsigned)w_s, r1 = (unsigned)cy.i1 * (unsigned)w_s;
-  return cy.l0 * (cx.l0 * d[r0 + (unsigned)cx.i0] + cx.l1 * d[r0 + (unsigned)cx.i1]) +
-         cy.l1 * (cx.l0 * d[r1 + (unsigned)cx.i0] + cx.l1 * d[r1 + (unsigned)cx.i1]);
+  // explicit roundings (mul, fma per lerp) so that every kernel that inlines this gets the same bits
+  const float top = fma_rn(cx.l1, d[r0 + (unsigned)cx.i1], mul_rn(cx.l0, d[r0 + (unsigned)cx.i0]));
+  const float bot = fma_rn(cx.l1, d[r1 + (unsigned)cx.i1], mul_rn(cx.l0, d[r1 + (unsigned)cx.i0]));
+  return fma_rn(cy.l1, bot, mul_rn(cy.l0, top));
 }
 
 // ---------------------------------------------------------------- depth
