@@ -226,7 +226,7 @@ int ppea_vsl_backward(const PpeaVslParams* p, const PpeaVslGrads* g, void* strea
 static_assert(kFusedTileWc == kFwdTileW && kFusedTileHc == kFwdTileH, "the fused step reuses the forward workspace layout");
 
 struct FusedWorkspace {
-  size_t off_pose, off_raw[kMaxScales], total_floats;
+  size_t off_pose, off_raw[kMaxScales], off_st[kMaxScales], total_floats;
 };
 static FusedWorkspace fused_workspace(const PpeaVslParams* p) {
   FusedWorkspace w;
@@ -234,6 +234,10 @@ static FusedWorkspace fused_workspace(const PpeaVslParams* p) {
   size_t off = align_up((size_t)fused_blocks(p->batch, p->height, p->width) * p->num_scales * 24, 4);
   for (int s = 0; s < kMaxScales; ++s) {
     w.off_raw[s] = off;
+    if (s < p->num_scales) off += align_up((size_t)p->batch * p->scales[s].disp_h * p->scales[s].disp_w, 4);
+  }
+  for (int s = 0; s < kMaxScales; ++s) {
+    w.off_st[s] = off;
     if (s < p->num_scales) off += align_up((size_t)p->batch * p->scales[s].disp_h * p->scales[s].disp_w, 4);
   }
   w.total_floats = off;
@@ -260,7 +264,10 @@ static void fused_args(const PpeaVslParams* p, const PpeaVslFused* f, VslArgs& a
   a.partials = (float*)p->workspace + ws.off_partials;
   a.smooth_ws = (float*)p->workspace + ws.off_smooth;
   a.pose_partials = (float*)f->workspace + fw.off_pose;
-  for (int s = 0; s < a.S; ++s) a.sc[s].grad_raw = (float*)f->workspace + fw.off_raw[s];
+  for (int s = 0; s < a.S; ++s) {
+    a.sc[s].grad_raw = (float*)f->workspace + fw.off_raw[s];
+    a.sc[s].grad_st = (float*)f->workspace + fw.off_st[s];
+  }
 }
 
 size_t ppea_vsl_fused_workspace_bytes(const PpeaVslParams* p) {

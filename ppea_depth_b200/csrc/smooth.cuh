@@ -137,6 +137,76 @@ __device__ __forceinline__ void smooth_forward_role(const VslArgs& a, int role, 
   }
 }
 
+// Fused-step role (vsl_fused.cu): the forward sums of one chunk AND the un-normalised stencil field
+//   st(x,y) = ( R(x,y) - R(x-1,y) ) / N_x + ( D(x,y) - D(x,y-1) ) / N_y,
+//   R = sign(d - d_right) * e_right,  D = sign(d - d_down) * e_down,
+// from the same column walk (the edge weights are the forward's own), so that the backward proper is
+// elementwise:  d smooth / d d_j = inv_b * ( st_j - inv_b * (X_b / N_x + Y_b / N_y) / (h*w) )  (times upstream).
+__device__ __forceinline__ void smooth_fused_role(const VslArgs& a, int role, float* red) {
+  int s, b, chunk;
+  smooth_role_ids(a, role, s, b, chunk);
+  const ScaleArgs& sc = a.sc[s];
+  const int h = sc.hs, w = sc.ws;
+  const unsigned n = (unsigned)(h * w);
+  const float* d = sc.disp + (size_t)b * n;
+  const float* img = sc.color + (size_t)b * 3 * n;
+  float* st = sc.grad_st + (size_t)b * n;
+  const SmoothChunk ck = smooth_chunk(w, h, chunk);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float cx = w > 1 ? 1.f / ((float)a.B * h * (w - 1)) : 0.f, cy = h > 1 ? 1.f / ((float)a.B * (h - 1) * w) : 0.f;
+  float sd = 0.f, sx = 0.f, sy = 0.f;
+  if (ck.active) {
+    const bool xin = ck.x < w, has_r = ck.x + 1 < w, has_l = xin && ck.x > 0;
+    SmoothPx cur = smooth_load(d, img, n, (unsigned)(ck.y_lo * w + ck.x), xin);
+    float d_up = 0.f;                      // D(x, y-1)
+    if (ck.y_lo > 0 && xin) {
+      const SmoothPx up = smooth_load(d, img, n, (unsigned)((ck.y_lo - 1) * w + ck.x), true);
+      d_up = sign_of(up.d - cur.d) * smooth_weight(up, cur);
+    }
+    for (int y = ck.y_lo; y < ck.y_hi; ++y) {
+      const unsigned o = (unsigned)(y * w + ck.x);
+      const bool has_d = y + 1 < h;
+      const SmoothPx nxt = smooth_load(d, img, n, o + (unsigned)w, xin && has_d);
+      SmoothPx rgt = smooth_shfl_down(cur);
+      if (lane == 31) rgt = smooth_load(d, img, n, o + 1u, has_r);     // the neighbour lives in the next warp / strip
+      const float dr = cur.d - rgt.d, dd = cur.d - nxt.d;
+      const float er = (xin && has_r) ? smooth_weight(cur, rgt) : 0.f;
+      const float ed = (xin && has_d) ? smooth_weight(cur, nxt) : 0.f;
+      const float r_here = sign_of(dr) * er, d_here = sign_of(dd) * ed;
+      float r_left = __shfl_up_sync(0xffffffffu, r_here, 1);
+      if (lane == 0) {
+        r_left = 0.f;
+        if (has_l) {
+          const SmoothPx lft = smooth_load(d, img, n, o - 1u, true);
+          r_left = sign_of(lft.d - cur.d) * smooth_weight(lft, cur);
+        }
+      }
+      if (xin) {
+        sd += cur.d;
+        sx += fabsf(dr) * er;
+        sy += fabsf(dd) * ed;
+        st[o] = (r_here - r_left) * cx + (d_here - d_up) * cy;
+      }
+      d_up = d_here;
+      cur = nxt;
+    }
+  }
+  sd = warp_sum(sd);
+  sx = warp_sum(sx);
+  sy = warp_sum(sy);
+  if (lane == 0) {
+    red[wid] = sd;
+    red[nw + wid] = sx;
+    red[2 * nw + wid] = sy;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float t = 0.f;
+    for (int k = 0; k < nw; ++k) t += red[threadIdx.x * nw + k];
+    a.smooth_ws[(((size_t)s * a.B + b) * kSmoothChunks + chunk) * 3 + threadIdx.x] = t;
+  }
+}
+
 // Backward role: smoothness gradient of one chunk.  MODE 0: overwrite grad_disp;  1: atomically add into a
 // zero-initialised (and concurrently accumulated) grad_disp;  2 (fused step, vsl_fused.cu): grad_disp =
 // smoothness gradient + w_s * grad_raw with w_s = upstream(reproj_s) / (sum(mask_s) + 1e-7).

@@ -26,6 +26,7 @@ struct ScaleArgs {
   float* grad_disp;
   float* grad_dup;      // deterministic mode: full-res dL/d disp_up scratch (scales with hs != H only)
   float* grad_raw;      // fused step: un-normalised photometric gradient of disp_s (vsl_fused.cu)
+  float* grad_st;       // fused step: un-normalised smoothness stencil field of disp_s (smooth.cuh)
 };
 
 // Kernel argument block (passed by value, lives in the constant bank).
@@ -100,7 +101,7 @@ inline BwdWorkspace bwd_workspace(int B, int H, int W, int S, unsigned flags) {
   return w;
 }
 
-// Fused-step workspace layout (floats): [pose partials: nblk*S*24][raw gradient of disp_s, s = 0..S-1]
+// Fused-step workspace layout (floats): [pose partials: nblk*S*24][raw photometric gradient of disp_s, s = 0..S-1][smoothness stencil field of disp_s, s = 0..S-1]
 constexpr int kFusedTileWc = 32, kFusedTileHc = 16;
 inline int fused_blocks(int B, int H, int W) { return B * ceil_div(W, kFusedTileWc) * ceil_div(H, kFusedTileHc); }
 

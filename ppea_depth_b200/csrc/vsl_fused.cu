@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(NT, PPEA_FUSED_CTAS) vsl_fused_kernel(const __
   // the first CTAs of the grid collect the smoothness sums of every scale (smooth.cuh)
   const int n_smooth = a.S * a.B * kSmoothChunks;
   if ((int)blockIdx.x < n_smooth) {
-    smooth_forward_role(a, blockIdx.x, reinterpret_cast<float*>(smem_raw));
+    smooth_fused_role(a, blockIdx.x, reinterpret_cast<float*>(smem_raw));
     return;
   }
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -473,24 +473,19 @@ cudaError_t launch_vsl_fused(const VslArgs& a, cudaStream_t stream) {
 }
 
 // ---------------------------------------------------------------------------
-// Backward proper of the fused step, one thread per pixel of disp_s, every scale in one launch:
-//   grad_disp_s = w_s * raw_s + d(smoothness term)/d disp_s,
-//   w_s = (upstream of reproj_s) / (sum(mask_s) + 1e-7)          trainer.py:1113-1114
-// The smoothness gradient is the one of smooth.cuh (same formula, flat indexing instead of the
-// column walk: here the term has a launch of its own, so it is laid out for bandwidth):
-//   grad(x,y) = inv_b * ( R(x,y) - R(x-1,y) + D(x,y) - D(x,y-1) - mean_term_b ),
-//   R = gx * sign(d - d_right) * e_right,  D = gy * sign(d - d_down) * e_down.
-// With REZERO the raw field of the coarse scales (accumulated atomically by the next step) is
-// cleared on the way out, so a replayed plan needs no memset.
+// Backward proper of the fused step, one thread per pixel of disp_s, every scale in one launch --
+// elementwise, because both gradient fields were laid down un-normalised by the forward launch:
+//   grad_disp_s = w_s * raw_s + g_s * inv_b * ( st_s - inv_b * (X_b / N_x + Y_b / N_y) / (h*w) ),
+//   w_s = (upstream of reproj_s) / (sum(mask_s) + 1e-7)                    trainer.py:1113-1114
+//   g_s = upstream of the smoothness term, inv_b = 1 / (mean(disp_s[b]) + 1e-7)   trainer.py:1147-1149
+// (st: smooth.cuh smooth_fused_role).  With REZERO the raw field of the coarse scales (accumulated
+// atomically by the next step) is cleared on the way out, so a replayed plan needs no memset.
 // ---------------------------------------------------------------------------
 constexpr int kGradFinishThreads = 256;
 
-__device__ __forceinline__ float smooth_edge(const float* __restrict__ d, const float* __restrict__ img, unsigned n, unsigned i,
-                                             unsigned j, float gscale) {
-  // gscale * sign(d_i - d_j) * exp(-mean_c |I_i - I_j|)   (layers.py:214-221)
-  return gscale * sign_of(__ldg(d + i) - __ldg(d + j)) * smooth_edge_weight(img, n, i, j);
-}
-
+// VEC = 4: four consecutive pixels per thread through 128-bit accesses (needs h*w % 4 == 0 for every scale,
+// so that the four share an image, and 16-byte aligned grad_disp); VEC = 1 otherwise.
+template <int VEC>
 __global__ void __launch_bounds__(kGradFinishThreads) vsl_grad_finish_kernel(const __grid_constant__ VslArgs a, int4 blk_end) {
   // scale of this CTA (blk_end.{x,y,z,w}: first block index past the blocks of scale 0..3)
   const int blk = blockIdx.x;
@@ -499,37 +494,50 @@ __global__ void __launch_bounds__(kGradFinishThreads) vsl_grad_finish_kernel(con
   const ScaleArgs& sc = a.sc[s];
   const int h = sc.hs, w = sc.ws;
   const unsigned n = (unsigned)(h * w);
-  const unsigned idx = (unsigned)(blk - blk0) * kGradFinishThreads + threadIdx.x;
+  const unsigned idx = ((unsigned)(blk - blk0) * kGradFinishThreads + threadIdx.x) * VEC;
   if (idx >= (unsigned)a.B * n) return;
-  const unsigned b = idx / n, o = idx - b * n;
-  const int y = (int)(o / (unsigned)w), x = (int)(o - (unsigned)y * (unsigned)w);
+  const unsigned b = idx / n;
   const float* row = a.sums + (size_t)s * sums_stride(a.B);
   const float* img_sums = row + PPEA_SUMS_PER_SCALE + 4 * b;                                   // (sum d, X_b, Y_b)
   const float inv = 1.f / (img_sums[0] / (float)n + 1e-7f);
   const ScaleGrads sg = scale_grads(a, s);
-  const float gx = sg.smooth / ((float)a.B * h * (w - 1)), gy = sg.smooth / ((float)a.B * (h - 1) * w);
-  const float mean_term = inv * (gx * img_sums[1] + gy * img_sums[2]) / (float)n;
+  const float cx = w > 1 ? 1.f / ((float)a.B * h * (w - 1)) : 0.f, cy = h > 1 ? 1.f / ((float)a.B * (h - 1) * w) : 0.f;
+  const float mean_term = inv * (cx * img_sums[1] + cy * img_sums[2]) / (float)n;
+  const float w_st = sg.smooth * inv;
   const float w_raw = sg.reproj / (row[1] + 1e-7f);
-  const float* d = sc.disp + (size_t)b * n;
-  const float* img = sc.color + (size_t)b * 3 * n;
-  const float r_here = (x + 1 < w) ? smooth_edge(d, img, n, o, o + 1u, gx) : 0.f;
-  const float r_left = (x > 0) ? smooth_edge(d, img, n, o - 1u, o, gx) : 0.f;
-  const float d_here = (y + 1 < h) ? smooth_edge(d, img, n, o, o + (unsigned)w, gy) : 0.f;
-  const float d_up = (y > 0) ? smooth_edge(d, img, n, o - (unsigned)w, o, gy) : 0.f;
-  const float v = ((r_here - r_left) + (d_here - d_up) - mean_term) * inv;
-  float* raw = sc.grad_raw + (size_t)b * n;
-  sc.grad_disp[(size_t)b * n + o] = fmaf(w_raw, raw[o], v);
-  if ((a.flags & PPEA_F_RAW_PREZEROED) && (h != a.H || w != a.W)) raw[o] = 0.f;
+  const bool rezero = (a.flags & PPEA_F_RAW_PREZEROED) && (h != a.H || w != a.W);
+  if (VEC == 4) {
+    const float4 st = __ldg(reinterpret_cast<const float4*>(sc.grad_st + idx));
+    const float4 raw = *reinterpret_cast<const float4*>(sc.grad_raw + idx);
+    float4 o;
+    o.x = fmaf(w_raw, raw.x, w_st * (st.x - mean_term));
+    o.y = fmaf(w_raw, raw.y, w_st * (st.y - mean_term));
+    o.z = fmaf(w_raw, raw.z, w_st * (st.z - mean_term));
+    o.w = fmaf(w_raw, raw.w, w_st * (st.w - mean_term));
+    *reinterpret_cast<float4*>(sc.grad_disp + idx) = o;
+    if (rezero) *reinterpret_cast<float4*>(sc.grad_raw + idx) = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    sc.grad_disp[idx] = fmaf(w_raw, sc.grad_raw[idx], w_st * (__ldg(sc.grad_st + idx) - mean_term));
+    if (rezero) sc.grad_raw[idx] = 0.f;
+  }
 }
 
 cudaError_t launch_vsl_grad_finish(const VslArgs& a, cudaStream_t stream) {
+  bool vec = true;
+  for (int s = 0; s < a.S; ++s)
+    vec = vec && (a.sc[s].hs * a.sc[s].ws) % 4 == 0 && (reinterpret_cast<uintptr_t>(a.sc[s].grad_disp) & 15) == 0;
+  const int per = kGradFinishThreads * (vec ? 4 : 1);
   int end[4] = {0, 0, 0, 0};
   int acc = 0;
   for (int s = 0; s < 4; ++s) {
-    if (s < a.S) acc += ceil_div(a.B * a.sc[s].hs * a.sc[s].ws, kGradFinishThreads);
+    if (s < a.S) acc += ceil_div(a.B * a.sc[s].hs * a.sc[s].ws, per);
     end[s] = acc;
   }
-  vsl_grad_finish_kernel<<<acc, kGradFinishThreads, 0, stream>>>(a, make_int4(end[0], end[1], end[2], end[3]));
+  const int4 be = make_int4(end[0], end[1], end[2], end[3]);
+  if (vec)
+    vsl_grad_finish_kernel<4><<<acc, kGradFinishThreads, 0, stream>>>(a, be);
+  else
+    vsl_grad_finish_kernel<1><<<acc, kGradFinishThreads, 0, stream>>>(a, be);
   return cudaGetLastError();
 }
 
