@@ -171,16 +171,19 @@ int ppea_vsl_forward(const PpeaVslParams* p, void* stream);
 /* `p` must describe the same call as the forward (same inputs, sel and sums as written by it) */
 int ppea_vsl_backward(const PpeaVslParams* p, const PpeaVslGrads* g, void* stream);
 
-/* ---- fused training step (mono path, non-deterministic backward) --------------------------------
+/* ---- fused training step (mono and multi path, atomic or deterministic backward) -----------------
  * Same reference calls as ppea_vsl_forward + ppea_vsl_backward (Trainer.generate_images_pred
  * trainer.py:871-918 + Trainer.compute_losses :1032-1160 + autograd of both), organised as ONE main
  * launch: the masked-mean normaliser 1/(sum(mask_s) + 1e-7) (trainer.py:1113-1114) is the only global
  * quantity of the path, so ppea_vsl_fused_forward evaluates the loss AND the un-normalised gradient
- * fields (into `workspace`), and ppea_vsl_fused_backward only rescales them by the upstream gradient
- * of `losses`, adds the smoothness gradient and reduces the pose gradient.  Outputs (depth, sel,
- * loss_px, sums, losses, grad_disp, grad_T) are the same tensors, to the same tolerances, as the
- * two-call path.  PPEA_F_MULTI / PPEA_F_DETERMINISTIC are refused (PPEA_E_FLAGS); pass PPEA_F_GRAD_POSE
- * to BOTH calls if dL/dT is wanted. */
+ * fields (into `workspace`: photometric term, smoothness stencil, and on the multi path the consistency
+ * term trainer.py:1128-1132), and ppea_vsl_fused_backward only combines them with the upstream gradient
+ * of `losses` and reduces the pose gradient.  Outputs (depth, sel, loss_px, sums, losses, grad_disp,
+ * grad_T) are the same tensors, to the same tolerances, as the two-call path.
+ * PPEA_F_DETERMINISTIC: the coarse-scale fields are accumulated as 64-bit fixed-point integers (2^-40
+ * resolution, contributions clamped to +-8.3e6), so the gradients are bit-reproducible without a
+ * full-resolution scratch field or a second pass.  Pass PPEA_F_GRAD_POSE to BOTH calls if dL/dT is
+ * wanted (ignored with PPEA_F_MULTI: T is detached there, trainer.py:900-902). */
 typedef struct PpeaVslFused {
   uint32_t struct_size;
   void* workspace;        /* >= ppea_vsl_fused_workspace_bytes(p), 16-byte aligned; written by fused_forward,

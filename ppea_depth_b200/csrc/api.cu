@@ -79,6 +79,8 @@ void fill_args(const PpeaVslParams* p, VslArgs& a) {
     sc.grad_disp = in.grad_disp;
     sc.grad_dup = nullptr;
     sc.grad_raw = nullptr;
+    sc.grad_raw2 = nullptr;
+    sc.grad_st = nullptr;
   }
   a.sums = p->sums;
   a.losses = p->losses;
@@ -226,15 +228,30 @@ int ppea_vsl_backward(const PpeaVslParams* p, const PpeaVslGrads* g, void* strea
 static_assert(kFusedTileWc == kFwdTileW && kFusedTileHc == kFwdTileH, "the fused step reuses the forward workspace layout");
 
 struct FusedWorkspace {
-  size_t off_pose, off_raw[kMaxScales], off_st[kMaxScales], total_floats;
+  size_t off_pose, off_raw[kMaxScales], off_raw2[kMaxScales], off_st[kMaxScales], raw_floats[kMaxScales], total_floats;
 };
+// Layout (floats): [pose partials: nblk*S*24][raw photometric gradient of disp_s][multi path: raw consistency
+// gradient of disp_s][smoothness stencil field of disp_s].  A coarse-scale raw field takes 2 floats per pixel:
+// with PPEA_F_DETERMINISTIC it is an array of 64-bit fixed-point accumulators.
 static FusedWorkspace fused_workspace(const PpeaVslParams* p) {
   FusedWorkspace w;
   w.off_pose = 0;
   size_t off = align_up((size_t)fused_blocks(p->batch, p->height, p->width) * p->num_scales * 24, 4);
   for (int s = 0; s < kMaxScales; ++s) {
+    w.raw_floats[s] = 0;
+    if (s < p->num_scales) {
+      const size_t n = (size_t)p->batch * p->scales[s].disp_h * p->scales[s].disp_w;
+      const bool coarse = p->scales[s].disp_h != p->height || p->scales[s].disp_w != p->width;
+      w.raw_floats[s] = align_up(coarse ? 2 * n : n, 4);
+    }
+  }
+  for (int s = 0; s < kMaxScales; ++s) {
     w.off_raw[s] = off;
-    if (s < p->num_scales) off += align_up((size_t)p->batch * p->scales[s].disp_h * p->scales[s].disp_w, 4);
+    off += w.raw_floats[s];
+  }
+  for (int s = 0; s < kMaxScales; ++s) {
+    w.off_raw2[s] = off;
+    if (p->flags & PPEA_F_MULTI) off += w.raw_floats[s];
   }
   for (int s = 0; s < kMaxScales; ++s) {
     w.off_st[s] = off;
@@ -249,7 +266,6 @@ static int check_fused(const PpeaVslParams* p, const PpeaVslFused* f, bool backw
   if (rc != PPEA_OK) return rc;
   if (!f) return PPEA_E_NULL;
   if (f->struct_size != sizeof(PpeaVslFused)) return PPEA_E_VERSION;
-  if (p->flags & (PPEA_F_MULTI | PPEA_F_DETERMINISTIC)) return PPEA_E_FLAGS;   // mono path, atomics backward only
   if (!f->workspace) return PPEA_E_NULL;
   if (!aligned(f->workspace, 16) || f->workspace_bytes < fused_workspace(p).total_floats * sizeof(float)) return PPEA_E_WORKSPACE;
   return PPEA_OK;
@@ -266,6 +282,7 @@ static void fused_args(const PpeaVslParams* p, const PpeaVslFused* f, VslArgs& a
   a.pose_partials = (float*)f->workspace + fw.off_pose;
   for (int s = 0; s < a.S; ++s) {
     a.sc[s].grad_raw = (float*)f->workspace + fw.off_raw[s];
+    a.sc[s].grad_raw2 = (p->flags & PPEA_F_MULTI) ? (float*)f->workspace + fw.off_raw2[s] : nullptr;
     a.sc[s].grad_st = (float*)f->workspace + fw.off_st[s];
   }
 }
@@ -288,9 +305,14 @@ int ppea_vsl_fused_forward(const PpeaVslParams* p, const PpeaVslFused* f, void* 
   fused_args(p, f, a);
   for (int s = 0; s < a.S; ++s) a.sc[s].grad_disp = nullptr;     // (the smoothness role would pre-zero it)
   PPEA_TRACE(p, 0);
-  for (int s = 0; s < a.S; ++s)                                  // coarse scales accumulate atomically
-    if (!(p->flags & PPEA_F_RAW_PREZEROED) && (a.sc[s].hs != a.H || a.sc[s].ws != a.W))
-      PPEA_TRY(cudaMemsetAsync(a.sc[s].grad_raw, 0, sizeof(float) * (size_t)a.B * a.sc[s].hs * a.sc[s].ws, stream));
+  if (!(p->flags & PPEA_F_RAW_PREZEROED)) {                      // coarse scales accumulate atomically
+    const FusedWorkspace fw = fused_workspace(p);
+    for (int s = 0; s < a.S; ++s)
+      if (a.sc[s].hs != a.H || a.sc[s].ws != a.W) {
+        PPEA_TRY(cudaMemsetAsync(a.sc[s].grad_raw, 0, sizeof(float) * fw.raw_floats[s], stream));
+        if (a.sc[s].grad_raw2) PPEA_TRY(cudaMemsetAsync(a.sc[s].grad_raw2, 0, sizeof(float) * fw.raw_floats[s], stream));
+      }
+  }
   PPEA_TRACE(p, 1);
   PPEA_TRY(launch_vsl_fused(a, stream));
   PPEA_TRACE(p, 2);
@@ -306,7 +328,7 @@ int ppea_vsl_fused_backward(const PpeaVslParams* p, const PpeaVslGrads* g, const
   if (!g) return PPEA_E_NULL;
   if (g->struct_size != sizeof(PpeaVslGrads)) return PPEA_E_VERSION;
   if (!g->grad_losses) return PPEA_E_NULL;
-  const bool pose = p->flags & PPEA_F_GRAD_POSE;
+  const bool pose = (p->flags & PPEA_F_GRAD_POSE) && !(p->flags & PPEA_F_MULTI);   // T is detached on the multi path
   if (pose && (!g->grad_T[0] || !g->grad_T[1])) return PPEA_E_NULL;
   cudaStream_t stream = (cudaStream_t)stream_;
   VslArgs a;

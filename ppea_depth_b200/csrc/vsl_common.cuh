@@ -26,6 +26,7 @@ struct ScaleArgs {
   float* grad_disp;
   float* grad_dup;      // deterministic mode: full-res dL/d disp_up scratch (scales with hs != H only)
   float* grad_raw;      // fused step: un-normalised photometric gradient of disp_s (vsl_fused.cu)
+  float* grad_raw2;     // fused step, multi path: un-normalised gradient of the consistency term
   float* grad_st;       // fused step: un-normalised smoothness stencil field of disp_s (smooth.cuh)
 };
 

@@ -111,6 +111,25 @@ __device__ __forceinline__ PhotoQ photo_q(const f2* __restrict__ xq, const float
   return o;
 }
 
+// Deterministic mode: the coarse-scale gradient fields are accumulated as 64-bit fixed-point integers
+// (2^-40 resolution, +-8.3e6 range): integer addition commutes, so the result does not depend on the
+// order in which the atomics land, and no full-resolution scratch field / second pass is needed.
+constexpr float kFixScale = 1099511627776.f;          // 2^40 (a power of two: the scaling itself is exact)
+__device__ __forceinline__ void fixed_add(float* field, int idx, float v) {
+  const long long q = __float2ll_rn(fminf(fmaxf(v, -8.3e6f), 8.3e6f) * kFixScale);
+  atomicAdd(reinterpret_cast<unsigned long long*>(field) + idx, (unsigned long long)q);
+}
+__device__ __forceinline__ void scatter_fixed(float* field, float g, UpCoef cy, UpCoef cx, int ws) {
+  if (g == 0.f) return;
+  fixed_add(field, cy.i0 * ws + cx.i0, g * cy.l0 * cx.l0);
+  fixed_add(field, cy.i0 * ws + cx.i1, g * cy.l0 * cx.l1);
+  fixed_add(field, cy.i1 * ws + cx.i0, g * cy.l1 * cx.l0);
+  fixed_add(field, cy.i1 * ws + cx.i1, g * cy.l1 * cx.l1);
+}
+__device__ __forceinline__ float fixed_value(unsigned long long acc) {
+  return (float)((double)(long long)acc * (1.0 / (double)kFixScale));
+}
+
 #ifndef PPEA_FUSED_CTAS
 #define PPEA_FUSED_CTAS 4
 #endif
@@ -118,23 +137,24 @@ constexpr int kFusedTileW = 32;
 constexpr int kFusedTileH = 16;
 constexpr int kFusedThreads = 128;
 
-template <int TW, int TH, int NT, bool POSE>
+template <int TW, int TH, int NT, bool POSE, bool MULTI, bool DET>
 __global__ void __launch_bounds__(NT, PPEA_FUSED_CTAS) vsl_fused_kernel(const __grid_constant__ VslArgs a) {
   using Smem = FusedSmem<TW, TH, NT>;
-  constexpr int RW = Smem::RW, RP = Smem::RP, QW = Smem::QW, QP = Smem::QP;
+  constexpr int RW = Smem::RW, RP = Smem::RP, QW = Smem::QW;
   constexpr int R = (TW * TH) / NT;
   static_assert(TW == 32 && (NT / 32) * R == TH && NT >= 128, "the gather/row mapping assumes lane == tile column and R rows per warp");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
 
-  // the first CTAs of the grid collect the smoothness sums of every scale (smooth.cuh)
-  const int n_smooth = a.S * a.B * kSmoothChunks;
-  if ((int)blockIdx.x < n_smooth) {
-    smooth_fused_role(a, blockIdx.x, reinterpret_cast<float*>(smem_raw));
+  // The smoothness roles are the LAST CTAs of the grid: they are short and fill the tail of the last
+  // wave of tile CTAs (measured: -19 us against running them first).
+  const int n_tiles_all = a.B * a.tiles_x * a.tiles_y;
+  if ((int)blockIdx.x >= n_tiles_all) {
+    smooth_fused_role(a, blockIdx.x - n_tiles_all, reinterpret_cast<float*>(smem_raw));
     return;
   }
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  int blk = blockIdx.x - n_smooth;
+  int blk = blockIdx.x;
   const int tile_id = blk;
   const int tx = blk % a.tiles_x;
   blk /= a.tiles_x;
@@ -143,7 +163,11 @@ __global__ void __launch_bounds__(NT, PPEA_FUSED_CTAS) vsl_fused_kernel(const __
   const int x0 = tx * TW, y0 = ty * TH;
   const int H = a.H, W = a.W;
   const size_t plane = (size_t)H * W;
-  const bool automask = a.flags & PPEA_F_AUTOMASK;
+  const bool automask = !MULTI && (a.flags & PPEA_F_AUTOMASK);   // the multi path masks by consistency / augmentation instead
+  constexpr bool det = DET;     // coarse-scale fields as 64-bit fixed-point accumulators (PPEA_F_DETERMINISTIC)
+  // multi path (trainer.py:1101-1141): mask = consistency_mask * (1 - augmentation_mask[b])
+  const bool motion = MULTI && (a.flags & PPEA_F_MOTION_MASK);
+  const float one_minus_aug = (MULTI && (a.flags & PPEA_F_MATCH_AUG)) ? 1.f - a.aug_mask[b] : 1.f;
   const bool no_ssim = a.flags & PPEA_F_NO_SSIM;
   const bool selec = a.flags & PPEA_F_SELEC_REPROJ;
   const float l1w = no_ssim ? (1.f / 3.f) : PPEA_W_L1;
@@ -311,17 +335,27 @@ __global__ void __launch_bounds__(NT, PPEA_FUSED_CTAS) vsl_fused_kernel(const __
         const PhotoQ ph = photo_q<true, RW, RP>(&sm.x[0][i * RW + j], &sm.y[0][i * RW + j], no_ssim, l1w, co);
         const Select sl = select_source(ph.L.x, ph.L.y, ph.cs.x, ph.cs.y, selec);
         bool on = true;
-        if (automask) {
+        float mq = 1.f;
+        if (MULTI) {
+          mq = (motion ? __ldg(a.cons_mask + o) : 1.f) * one_minus_aug;
+        } else if (automask) {
           const float idl = sc.noise ? add_rn(sm.ident[qi], mul_rn(nz, 0.00001f)) : sm.ident[qi];   // trainer.py:1086-1087
           on = sl.r <= idl;                                                                       // argmin([r, id]) == 0
+          mq = on ? 1.f : 0.f;
         }
-        if (on) indv = mk2(sl.src == 0 ? 1.f : 0.f, sl.src == 1 ? 1.f : 0.f);
+        if (MULTI)
+          indv = mk2(sl.src == 0 ? mq : 0.f, sl.src == 1 ? mq : 0.f);
+        else if (on)
+          indv = mk2(sl.src == 0 ? 1.f : 0.f, sl.src == 1 ? 1.f : 0.f);
 #pragma unroll
         for (int e = 0; e < 9; ++e) cfo[e] = (sl.src == 1) ? co[e].y : co[e].x;
         if (i >= 1 && i <= TH && j >= 1 && j <= TW) {      // owner of q: forward products
           if (sc.loss_px) sc.loss_px[o] = sl.r;
           sc.sel[o] = (uint8_t)((unsigned)sl.src | (on ? PPEA_SEL_AUTOMASK : 0u));
-          if (on) {
+          if (MULTI) {
+            s_rm = fmaf(sl.r, mq, s_rm);
+            s_m += mq;
+          } else if (on) {
             s_rm += sl.r;
             s_m += 1.f;
           }
@@ -338,7 +372,7 @@ __global__ void __launch_bounds__(NT, PPEA_FUSED_CTAS) vsl_fused_kernel(const __
       sm.redf[1][wid] = s_m;
     }
     __syncthreads();
-    if (tid < 3) {
+    if (tid < (MULTI ? 2 : 3)) {          // (multi path: entry 2, the consistency sum, follows the chain phase)
       float t = 0.f;
       if (tid < 2)
         for (int w = 0; w < NT / 32; ++w) t += sm.redf[tid][w];
@@ -385,7 +419,10 @@ __global__ void __launch_bounds__(NT, PPEA_FUSED_CTAS) vsl_fused_kernel(const __
     }
 
     // ---- chain: projection adjoint, depth -> disp, adjoint of the bilinear upsample (weight 1: raw gradient)
-    float* gr_b = sc.grad_raw + (size_t)b * sc.hs * sc.ws;
+    const size_t img_off = (size_t)b * sc.hs * sc.ws;
+    float* gr_b = sc.grad_raw + (det && !same_res ? 2 * img_off : img_off);          // (fixed-point fields: 8 bytes per pixel)
+    float* gc_b = MULTI ? sc.grad_raw2 + (det && !same_res ? 2 * img_off : img_off) : nullptr;
+    float s_c = 0.f;
     f2 Sw[POSE ? 3 : 1], Swy[POSE ? 3 : 1], Sg[POSE ? 3 : 1];
 #pragma unroll
     for (int e = 0; e < (POSE ? 3 : 1); ++e) Sw[e] = Swy[e] = Sg[e] = dup2(0.f);
@@ -412,17 +449,47 @@ __global__ void __launch_bounds__(NT, PPEA_FUSED_CTAS) vsl_fused_kernel(const __
           Sg[1] = vadd(Sg[1], gc1);
           Sg[2] = vadd(Sg[2], gc2);
         }
-        const float g_dup = g * ddepth_ddisp(dep[k], a.disp_range);
+        const float dd = ddepth_ddisp(dep[k], a.disp_range);
+        const float g_dup = g * dd;
+        float c_dup = 0.f;
+        if (MULTI) {
+          // consistency term mean(|depth - mono_depth| * (1 - mask))  (trainer.py:1128-1132): its un-normalised
+          // gradient goes to a field of its own (its upstream weight differs from the photometric one)
+          const size_t o = (size_t)b * plane + (size_t)gy * W + gx_own;
+          const float om = 1.f - (motion ? __ldg(a.cons_mask + o) : 1.f) * one_minus_aug;
+          const float dm = dep[k] - __ldg(sc.mono_depth + o);
+          s_c = fmaf(fabsf(dm), om, s_c);
+          c_dup = sign_of(dm) * om * dd;
+        }
         if (same_res) {
-          gr_b[(unsigned)gy * (unsigned)W + (unsigned)gx_own] = g_dup;     // sole owner: plain store, no pre-zero needed
-        } else if (g_dup != 0.f) {
+          const unsigned o0 = (unsigned)gy * (unsigned)W + (unsigned)gx_own;
+          gr_b[o0] = g_dup;     // sole owner: plain store, no pre-zero needed
+          if (MULTI) gc_b[o0] = c_dup;
+        } else if (g_dup != 0.f || (MULTI && c_dup != 0.f)) {
           const UpCoef cy = up_coef(gy, sc.hs, sc.up_sy), cx = up_coef(gx_own, sc.ws, sc.up_sx);
-          atomicAdd(gr_b + cy.i0 * sc.ws + cx.i0, g_dup * cy.l0 * cx.l0);
-          atomicAdd(gr_b + cy.i0 * sc.ws + cx.i1, g_dup * cy.l0 * cx.l1);
-          atomicAdd(gr_b + cy.i1 * sc.ws + cx.i0, g_dup * cy.l1 * cx.l0);
-          atomicAdd(gr_b + cy.i1 * sc.ws + cx.i1, g_dup * cy.l1 * cx.l1);
+          if (!det) {
+            if (!MULTI || g_dup != 0.f) {
+              atomicAdd(gr_b + cy.i0 * sc.ws + cx.i0, g_dup * cy.l0 * cx.l0);
+              atomicAdd(gr_b + cy.i0 * sc.ws + cx.i1, g_dup * cy.l0 * cx.l1);
+              atomicAdd(gr_b + cy.i1 * sc.ws + cx.i0, g_dup * cy.l1 * cx.l0);
+              atomicAdd(gr_b + cy.i1 * sc.ws + cx.i1, g_dup * cy.l1 * cx.l1);
+            }
+            if (MULTI && c_dup != 0.f) {
+              atomicAdd(gc_b + cy.i0 * sc.ws + cx.i0, c_dup * cy.l0 * cx.l0);
+              atomicAdd(gc_b + cy.i0 * sc.ws + cx.i1, c_dup * cy.l0 * cx.l1);
+              atomicAdd(gc_b + cy.i1 * sc.ws + cx.i0, c_dup * cy.l1 * cx.l0);
+              atomicAdd(gc_b + cy.i1 * sc.ws + cx.i1, c_dup * cy.l1 * cx.l1);
+            }
+          } else {
+            scatter_fixed(gr_b, g_dup, cy, cx, sc.ws);
+            if (MULTI) scatter_fixed(gc_b, c_dup, cy, cx, sc.ws);
+          }
         }
       }
+    }
+    if (MULTI) {
+      s_c = warp_sum(s_c);
+      if (lane == 0) sm.redf[2][wid] = s_c;
     }
     if (POSE) {
       // per source f and row r of dL/dP: (sum gc_r*depth*x, sum gc_r*depth*y, sum gc_r*depth, sum gc_r)
@@ -449,27 +516,34 @@ __global__ void __launch_bounds__(NT, PPEA_FUSED_CTAS) vsl_fused_kernel(const __
       for (int w = 0; w < NT / 32; ++w) t += sm.red[tid][w];
       a.pose_partials[((size_t)tile_id * a.S + s) * 24 + tid] = t;
     }
+    if (MULTI && tid == 32) {
+      float t = 0.f;
+      for (int w = 0; w < NT / 32; ++w) t += sm.redf[2][w];
+      a.partials[((size_t)tile_id * a.S + s) * 4 + 2] = t;
+    }
     // (red[] is next written after two more barriers of the following scale)
   }
 }
 
-cudaError_t launch_vsl_fused(const VslArgs& a, cudaStream_t stream) {
+template <bool POSE, bool MULTI, bool DET>
+static cudaError_t launch_vsl_fused_as(const VslArgs& a, cudaStream_t stream) {
   using Smem = FusedSmem<kFusedTileW, kFusedTileH, kFusedThreads>;
   static_assert(sizeof(Smem) <= 227 * 1024, "shared memory tile too large");
   const int nblk = a.B * a.tiles_x * a.tiles_y + a.S * a.B * kSmoothChunks;
-  cudaError_t e;
-  if (a.flags & PPEA_F_GRAD_POSE) {
-    auto kern = vsl_fused_kernel<kFusedTileW, kFusedTileH, kFusedThreads, true>;
-    e = ensure_dynamic_smem(kern, (int)sizeof(Smem));
-    if (e != cudaSuccess) return e;
-    kern<<<nblk, kFusedThreads, sizeof(Smem), stream>>>(a);
-  } else {
-    auto kern = vsl_fused_kernel<kFusedTileW, kFusedTileH, kFusedThreads, false>;
-    e = ensure_dynamic_smem(kern, (int)sizeof(Smem));
-    if (e != cudaSuccess) return e;
-    kern<<<nblk, kFusedThreads, sizeof(Smem), stream>>>(a);
-  }
+  auto kern = vsl_fused_kernel<kFusedTileW, kFusedTileH, kFusedThreads, POSE, MULTI, DET>;
+  const cudaError_t e = ensure_dynamic_smem(kern, (int)sizeof(Smem));
+  if (e != cudaSuccess) return e;
+  kern<<<nblk, kFusedThreads, sizeof(Smem), stream>>>(a);
   return cudaGetLastError();
+}
+
+cudaError_t launch_vsl_fused(const VslArgs& a, cudaStream_t stream) {
+  const bool det = a.flags & PPEA_F_DETERMINISTIC;
+  if (a.flags & PPEA_F_MULTI)      // T is detached on the multi path (trainer.py:900-902)
+    return det ? launch_vsl_fused_as<false, true, true>(a, stream) : launch_vsl_fused_as<false, true, false>(a, stream);
+  if (a.flags & PPEA_F_GRAD_POSE)
+    return det ? launch_vsl_fused_as<true, false, true>(a, stream) : launch_vsl_fused_as<true, false, false>(a, stream);
+  return det ? launch_vsl_fused_as<false, false, true>(a, stream) : launch_vsl_fused_as<false, false, false>(a, stream);
 }
 
 // ---------------------------------------------------------------------------
@@ -485,6 +559,49 @@ constexpr int kGradFinishThreads = 256;
 
 // VEC = 4: four consecutive pixels per thread through 128-bit accesses (needs h*w % 4 == 0 for every scale,
 // so that the four share an image, and 16-byte aligned grad_disp); VEC = 1 otherwise.
+template <int VEC>
+struct RawVec {
+  float v[VEC];
+};
+// one un-normalised field at pixels idx .. idx+VEC-1; `fixed`: 64-bit fixed-point accumulators (deterministic
+// mode, coarse scales)
+template <int VEC>
+__device__ __forceinline__ RawVec<VEC> load_raw(const float* field, unsigned idx, bool fixed) {
+  RawVec<VEC> r;
+  if (fixed) {
+    const unsigned long long* f = reinterpret_cast<const unsigned long long*>(field) + idx;
+    if (VEC == 4) {
+      const ulonglong2 lo = *reinterpret_cast<const ulonglong2*>(f), hi = *reinterpret_cast<const ulonglong2*>(f + 2);
+      r.v[0] = fixed_value(lo.x), r.v[1 % VEC] = fixed_value(lo.y), r.v[2 % VEC] = fixed_value(hi.x), r.v[3 % VEC] = fixed_value(hi.y);
+    } else {
+      r.v[0] = fixed_value(*f);
+    }
+  } else if (VEC == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(field + idx);
+    r.v[0] = t.x, r.v[1 % VEC] = t.y, r.v[2 % VEC] = t.z, r.v[3 % VEC] = t.w;
+  } else {
+    r.v[0] = field[idx];
+  }
+  return r;
+}
+// clear what was read: the next step of a replayed plan accumulates into it again (PPEA_F_RAW_PREZEROED)
+template <int VEC>
+__device__ __forceinline__ void zero_raw(float* field, unsigned idx, bool fixed) {
+  if (fixed) {
+    unsigned long long* f = reinterpret_cast<unsigned long long*>(field) + idx;
+    if (VEC == 4) {
+      *reinterpret_cast<ulonglong2*>(f) = make_ulonglong2(0ull, 0ull);
+      *reinterpret_cast<ulonglong2*>(f + 2) = make_ulonglong2(0ull, 0ull);
+    } else {
+      *f = 0ull;
+    }
+  } else if (VEC == 4) {
+    *reinterpret_cast<float4*>(field + idx) = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    field[idx] = 0.f;
+  }
+}
+
 template <int VEC>
 __global__ void __launch_bounds__(kGradFinishThreads) vsl_grad_finish_kernel(const __grid_constant__ VslArgs a, int4 blk_end) {
   // scale of this CTA (blk_end.{x,y,z,w}: first block index past the blocks of scale 0..3)
@@ -505,20 +622,33 @@ __global__ void __launch_bounds__(kGradFinishThreads) vsl_grad_finish_kernel(con
   const float mean_term = inv * (cx * img_sums[1] + cy * img_sums[2]) / (float)n;
   const float w_st = sg.smooth * inv;
   const float w_raw = sg.reproj / (row[1] + 1e-7f);
-  const bool rezero = (a.flags & PPEA_F_RAW_PREZEROED) && (h != a.H || w != a.W);
+  const bool multi = a.flags & PPEA_F_MULTI;
+  const float w_cons = multi ? sg.cons / ((float)a.B * (float)a.H * (float)a.W) : 0.f;        // plain mean (trainer.py:1132)
+  const bool coarse = (h != a.H || w != a.W);
+  const bool fixed = coarse && (a.flags & PPEA_F_DETERMINISTIC);
+  const bool rezero = coarse && (a.flags & PPEA_F_RAW_PREZEROED);
+  // every load is issued before the first use (the kernel is latency-bound: one DRAM round trip, not three)
+  RawVec<VEC> o;
   if (VEC == 4) {
     const float4 st = __ldg(reinterpret_cast<const float4*>(sc.grad_st + idx));
-    const float4 raw = *reinterpret_cast<const float4*>(sc.grad_raw + idx);
-    float4 o;
-    o.x = fmaf(w_raw, raw.x, w_st * (st.x - mean_term));
-    o.y = fmaf(w_raw, raw.y, w_st * (st.y - mean_term));
-    o.z = fmaf(w_raw, raw.z, w_st * (st.z - mean_term));
-    o.w = fmaf(w_raw, raw.w, w_st * (st.w - mean_term));
-    *reinterpret_cast<float4*>(sc.grad_disp + idx) = o;
-    if (rezero) *reinterpret_cast<float4*>(sc.grad_raw + idx) = make_float4(0.f, 0.f, 0.f, 0.f);
+    o.v[0] = st.x, o.v[1 % VEC] = st.y, o.v[2 % VEC] = st.z, o.v[3 % VEC] = st.w;
   } else {
-    sc.grad_disp[idx] = fmaf(w_raw, sc.grad_raw[idx], w_st * (__ldg(sc.grad_st + idx) - mean_term));
-    if (rezero) sc.grad_raw[idx] = 0.f;
+    o.v[0] = __ldg(sc.grad_st + idx);
+  }
+  const RawVec<VEC> raw = load_raw<VEC>(sc.grad_raw, idx, fixed);
+  RawVec<VEC> rc;
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) rc.v[k] = 0.f;
+  if (multi) rc = load_raw<VEC>(sc.grad_raw2, idx, fixed);
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) o.v[k] = fmaf(w_cons, rc.v[k], fmaf(w_raw, raw.v[k], w_st * (o.v[k] - mean_term)));
+  if (VEC == 4)
+    *reinterpret_cast<float4*>(sc.grad_disp + idx) = make_float4(o.v[0], o.v[1 % VEC], o.v[2 % VEC], o.v[3 % VEC]);
+  else
+    sc.grad_disp[idx] = o.v[0];
+  if (rezero) {
+    zero_raw<VEC>(sc.grad_raw, idx, fixed);
+    if (multi) zero_raw<VEC>(sc.grad_raw2, idx, fixed);
   }
 }
 

@@ -52,14 +52,11 @@ class VslConfig:
     first_scale: int = 0
     total_scales: Optional[int] = None
     want_loss_px: bool = False
-    fused: Optional[bool] = None     # single-launch training step (vsl_fused.cu); None = whenever it applies
-                                     # (mono path, atomics backward, some input requires grad)
+    fused: Optional[bool] = None     # single-launch training step (vsl_fused.cu); None = whenever some input
+                                     # requires grad (False: forward + backward kernel pair)
 
     def use_fused(self, needs_grad):
-        ok = (not self.is_multi) and (not self.deterministic)
-        if self.fused and not ok:
-            raise ValueError("the fused training step covers the mono path with the non-deterministic backward only")
-        return bool(needs_grad) and ok and (self.fused is None or self.fused)
+        return bool(needs_grad) and (self.fused is None or self.fused)
 
     def flags(self, grad_pose):
         f = 0

@@ -43,11 +43,8 @@ class FusedPlan:
         self.aug_mask = _f32c(aug_mask.reshape(-1)[:B], "aug_mask") if (cfg.is_multi and cfg.match_aug) else None
         self.mono_depth = [_f32c(m, "mono_depth") for m in mono_depth] if cfg.is_multi else None
         self.grad_pose = (not cfg.is_multi) if grad_pose is None else bool(grad_pose)
-        # single-launch training step (vsl_fused.cu) wherever it applies: mono path, atomics backward
-        can_fuse = (not cfg.is_multi) and (not cfg.deterministic)
-        if fused and not can_fuse:
-            raise ValueError("the fused training step covers the mono path with the non-deterministic backward only")
-        self.fused = can_fuse if fused is None else bool(fused)
+        # single-launch training step (vsl_fused.cu) unless the forward + backward kernel pair is asked for
+        self.fused = True if fused is None else bool(fused)
         f32 = dict(device=dev, dtype=torch.float32)
         with torch.cuda.device(dev):
             self.depth = [torch.empty(B, 1, H, W, **f32) for _ in range(S)]

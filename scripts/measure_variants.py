@@ -9,11 +9,17 @@ def bench(*args):
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "100", "--warmup", "10", "--no-cpu-baseline", "--no-e2e", *args],
                          capture_output=True, text=True).stdout.strip().splitlines()[-1]
     d = json.loads(out)
-    st = d["roofline"]["stage_ms"]
-    print("bench %-40s ms/step %.4f  Mpix/s %.0f  fwd %.4f bwd %.4f frac_step %.4f" % (" ".join(args), d["ms_per_step"], d["value"], st["vsl_forward_kernel"], st["vsl_backward_kernel"], d["roofline"]["step_frac_of_peak"]))
+    st = {k: round(v, 4) for k, v in d["roofline"]["stage_ms"].items() if "unused" not in k}
+    print("bench %-48s ms/step %.4f  Mpix/s %.0f  frac_step %.4f  %s" % (" ".join(args), d["ms_per_step"], d["value"], d["roofline"]["step_frac_of_peak"], st), flush=True)
 
-for a in ([], ["--path", "multi"], ["--deterministic"], ["--workload", "cityscapes"], ["--workload", "hires", "--deterministic"], ["--workload", "sweep96"]):
+MODES = ([], ["--path", "multi"], ["--deterministic"], ["--path", "multi", "--deterministic"], ["--workload", "cityscapes"],
+         ["--workload", "cityscapes", "--path", "multi"], ["--workload", "hires", "--deterministic"], ["--workload", "sweep96"])
+for a in MODES:
     bench(*a)
+    if "--pair" in sys.argv:
+        bench(*a, "--no-fused")
+if "--bench-only" in sys.argv:
+    sys.exit(0)
 
 # public API, inputs resident
 from types import SimpleNamespace

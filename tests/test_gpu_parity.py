@@ -12,15 +12,13 @@ from ppea_depth_b200.synth import CITYSCAPES_K, SynthConfig, make_batch, make_no
 pytestmark = pytest.mark.gpu
 
 
-# fused: None = the single-launch training step (vsl_fused.cu) wherever it applies (mono path);
+# fused: None = the single-launch training step (vsl_fused.cu: mono and multi path, atomic or deterministic);
 #        False = the forward + backward kernel pair (vsl_fwd.cu / vsl_bwd.cu)
 @pytest.mark.parametrize("fused", [None, False])
 @pytest.mark.parametrize("name", golden_names())
 def test_cuda_matches_golden(name, fused):
     fx = load_golden(name)
     opt, multi = fx["opt"], fx["is_multi"]
-    if multi and fused is None:
-        pytest.skip("the multi path always runs the kernel pair")
     noise = fx["noise"] if not multi else None
     losses, grads, maps = run_cuda(fx["inputs"], fx["outputs"], opt, multi, noise, fused=fused)
     for s, ref in fx["ref_maps"].items():
@@ -37,9 +35,10 @@ def test_cuda_matches_golden(name, fused):
         assert abs(float(losses[k]) - float(v)) <= tol * abs(float(v)) + 1e-8, (k, float(losses[k]), float(v))
 
 
-@pytest.mark.parametrize("multi,fused", [(False, None), (False, False), (True, False)])
+@pytest.mark.parametrize("det", [False, True])
+@pytest.mark.parametrize("multi,fused", [(False, None), (False, False), (True, None), (True, False)])
 @pytest.mark.parametrize("shape", [(2, 64, 96, 4), (1, 50, 70, 3), (3, 33, 47, 1)])
-def test_cuda_matches_oracle_synthetic(shape, multi, fused):
+def test_cuda_matches_oracle_synthetic(shape, multi, fused, det):
     B, H, W, S = shape
     cfg = SynthConfig(batch=B, height=H, width=W, num_scales=S, seed=21 + H)
     inputs, outputs = make_batch(cfg)
@@ -51,18 +50,19 @@ def test_cuda_matches_oracle_synthetic(shape, multi, fused):
             inputs[("color", 0, s)] = inputs[("color", 0, s)][..., :hs, :ws].contiguous()
     noise = make_noise(cfg, S)
     opt = O.default_opt(sclm=S - 1, height=H, width=W, batch_size=B)
-    losses, grads, maps = run_cuda(inputs, outputs, opt, multi, None if multi else noise, fused=fused)
+    losses, grads, maps = run_cuda(inputs, outputs, opt, multi, None if multi else noise, fused=fused, deterministic=det)
     check_against_oracle(inputs, outputs, opt, multi, noise, losses, grads, maps)
 
 
-def test_fused_step_equals_kernel_pair():
+@pytest.mark.parametrize("multi", [False, True])
+def test_fused_step_equals_kernel_pair(multi):
     """Same selection maps bit for bit, same losses, gradients equal up to summation order."""
     cfg = SynthConfig(batch=2, height=80, width=112, num_scales=4, seed=37)
     inputs, outputs = make_batch(cfg)
-    noise = make_noise(cfg, 4)
+    noise = None if multi else make_noise(cfg, 4)
     opt = O.default_opt(sclm=3, height=80, width=112, batch_size=2)
-    l_a, g_a, m_a = run_cuda(inputs, outputs, opt, False, noise, fused=True)
-    l_b, g_b, m_b = run_cuda(inputs, outputs, opt, False, noise, fused=False)
+    l_a, g_a, m_a = run_cuda(inputs, outputs, opt, multi, noise, fused=True)
+    l_b, g_b, m_b = run_cuda(inputs, outputs, opt, multi, noise, fused=False)
     # (the two kernels add the three window rows in different orders: last-ulp differences, so a handful of
     # exact near-ties may fall the other way)
     for s in range(4):
@@ -79,19 +79,22 @@ def test_fused_step_equals_kernel_pair():
             assert float((g_a[k] - g_b[k]).abs().max()) <= 2e-5 * scale + 1e-12, k
 
 
-def test_cuda_deterministic_backward_matches_and_repeats():
+@pytest.mark.parametrize("multi,fused", [(False, None), (False, False), (True, None), (True, False)])
+def test_cuda_deterministic_backward_matches_and_repeats(multi, fused):
+    """fused step: 64-bit fixed-point accumulation of the coarse-scale fields; kernel pair: scratch field +
+    fixed-order gather.  Both must repeat bit for bit and agree with the float-atomics backward."""
     cfg = SynthConfig(batch=2, height=64, width=96, num_scales=4, seed=31)
     inputs, outputs = make_batch(cfg)
-    noise = make_noise(cfg, 4)
+    noise = None if multi else make_noise(cfg, 4)
     opt = O.default_opt(sclm=3, height=64, width=96, batch_size=2)
-    _, g_atomic, _ = run_cuda(inputs, outputs, opt, False, noise, fused=False)
-    l_det, g_det1, maps = run_cuda(inputs, outputs, opt, False, noise, deterministic=True)
-    _, g_det2, _ = run_cuda(inputs, outputs, opt, False, noise, deterministic=True)
+    _, g_atomic, _ = run_cuda(inputs, outputs, opt, multi, noise, fused=fused)     # same kernels, float atomics
+    l_det, g_det1, maps = run_cuda(inputs, outputs, opt, multi, noise, deterministic=True, fused=fused)
+    _, g_det2, _ = run_cuda(inputs, outputs, opt, multi, noise, deterministic=True, fused=fused)
     for k in g_det1:
         assert torch.equal(g_det1[k], g_det2[k]), k                      # bit-reproducible
         scale = float(g_det1[k].abs().max())
         assert float((g_det1[k] - g_atomic[k]).abs().max()) <= 2e-6 * scale + 1e-12, k
-    check_against_oracle(inputs, outputs, opt, False, noise, l_det, g_det1, maps)
+    check_against_oracle(inputs, outputs, opt, multi, make_noise(cfg, 4), l_det, g_det1, maps)
 
 
 @pytest.mark.parametrize("fused", [None, False])
@@ -131,7 +134,7 @@ FULL = {
 }
 
 
-@pytest.mark.parametrize("multi,fused", [(False, None), (False, False), (True, False)])
+@pytest.mark.parametrize("multi,fused", [(False, None), (False, False), (True, None), (True, False)])
 def test_full_size_kitti_against_oracle(multi, fused):
     """BASELINE.json configs[0]/[1]: the whole 12x3x192x640, 4-scale batch against the oracle
     (a few seconds of CPU)."""
