@@ -225,7 +225,7 @@ int ppea_vsl_backward(const PpeaVslParams* p, const PpeaVslGrads* g, void* strea
 }
 
 // ---- fused training step (mono path): vsl_fused.cu -------------------------------------------------
-static_assert(kFusedTileWc == kFwdTileW && kFusedTileHc == kFwdTileH, "the fused step reuses the forward workspace layout");
+static_assert(kFusedTileWc == kFwdTileW && kFusedTileHc >= kFwdTileH, "the fused step reuses the forward workspace layout (never more tiles than the forward)");
 
 struct FusedWorkspace {
   size_t off_pose, off_raw[kMaxScales], off_raw2[kMaxScales], off_st[kMaxScales], raw_floats[kMaxScales], total_floats;

@@ -103,7 +103,13 @@ inline BwdWorkspace bwd_workspace(int B, int H, int W, int S, unsigned flags) {
 }
 
 // Fused-step workspace layout (floats): [pose partials: nblk*S*24][raw photometric gradient of disp_s, s = 0..S-1][smoothness stencil field of disp_s, s = 0..S-1]
-constexpr int kFusedTileWc = 32, kFusedTileHc = 16;
+#ifndef PPEA_FUSED_TILE_H
+#define PPEA_FUSED_TILE_H 16
+#endif
+#ifndef PPEA_FUSED_THREADS
+#define PPEA_FUSED_THREADS 128
+#endif
+constexpr int kFusedTileWc = 32, kFusedTileHc = PPEA_FUSED_TILE_H;
 inline int fused_blocks(int B, int H, int W) { return B * ceil_div(W, kFusedTileWc) * ceil_div(H, kFusedTileHc); }
 
 cudaError_t launch_vsl_forward(const VslArgs& a, cudaStream_t stream);

@@ -134,8 +134,8 @@ __device__ __forceinline__ float fixed_value(unsigned long long acc) {
 #define PPEA_FUSED_CTAS 4
 #endif
 constexpr int kFusedTileW = 32;
-constexpr int kFusedTileH = 16;
-constexpr int kFusedThreads = 128;
+constexpr int kFusedTileH = kFusedTileHc;
+constexpr int kFusedThreads = PPEA_FUSED_THREADS;
 
 template <int TW, int TH, int NT, bool POSE, bool MULTI, bool DET>
 __global__ void __launch_bounds__(NT, PPEA_FUSED_CTAS) vsl_fused_kernel(const __grid_constant__ VslArgs a) {
