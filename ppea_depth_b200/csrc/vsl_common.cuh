@@ -122,6 +122,31 @@ cudaError_t launch_vsl_fused(const VslArgs& a, cudaStream_t stream);
 cudaError_t launch_vsl_grad_finish(const VslArgs& a, cudaStream_t stream);
 cudaError_t launch_pose_finish_fused(const VslArgs& a, cudaStream_t stream);
 
+// Programmatic dependent launch (sm_90+): a kernel launched with launch_pdl may become resident while its
+// predecessor in the stream is still running; it must call grid_dependency_wait() before touching anything
+// the predecessor writes.  A predecessor that calls grid_launch_dependents() early lets the dependent's CTAs
+// take their place ahead of time (only worth it when those CTAs are few or the predecessor leaves SMs idle).
+// Captured by stream capture as a programmatic graph edge.  Used for the small tail kernels of a step, whose
+// cost is launch latency and ramp, not work.
+#if defined(__CUDACC__)
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+#endif
+
 // Opt a kernel into > 48 KB of dynamic shared memory once per device (the attribute is sticky per
 // function and device); keeping it out of the steady state also keeps it out of CUDA-graph capture.
 struct SmemAttrCache {

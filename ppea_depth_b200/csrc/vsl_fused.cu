@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(NT, PPEA_FUSED_CTAS) vsl_fused_kernel(const __
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
 
+  grid_launch_dependents();      // the dependent is the one-CTA finish kernel: let it take its place early
   // The smoothness roles are the LAST CTAs of the grid: they are short and fill the tail of the last
   // wave of tile CTAs (measured: -19 us against running them first).
   const int n_tiles_all = a.B * a.tiles_x * a.tiles_y;
@@ -604,6 +605,8 @@ __device__ __forceinline__ void zero_raw(float* field, unsigned idx, bool fixed)
 
 template <int VEC>
 __global__ void __launch_bounds__(kGradFinishThreads) vsl_grad_finish_kernel(const __grid_constant__ VslArgs a, int4 blk_end) {
+  grid_dependency_wait();        // sums of the finish kernel (and, transitively, the fields of the main launch)
+  grid_launch_dependents();      // the pose-gradient kernel (B CTAs) may take its place; it waits for this grid to drain
   // scale of this CTA (blk_end.{x,y,z,w}: first block index past the blocks of scale 0..3)
   const int blk = blockIdx.x;
   const int s = (blk >= blk_end.x) + (blk >= blk_end.y) + (blk >= blk_end.z);
@@ -664,11 +667,8 @@ cudaError_t launch_vsl_grad_finish(const VslArgs& a, cudaStream_t stream) {
     end[s] = acc;
   }
   const int4 be = make_int4(end[0], end[1], end[2], end[3]);
-  if (vec)
-    vsl_grad_finish_kernel<4><<<acc, kGradFinishThreads, 0, stream>>>(a, be);
-  else
-    vsl_grad_finish_kernel<1><<<acc, kGradFinishThreads, 0, stream>>>(a, be);
-  return cudaGetLastError();
+  if (vec) return launch_pdl(vsl_grad_finish_kernel<4>, dim3(acc), dim3(kGradFinishThreads), 0, stream, a, be);
+  return launch_pdl(vsl_grad_finish_kernel<1>, dim3(acc), dim3(kGradFinishThreads), 0, stream, a, be);
 }
 
 // Pose gradient of the fused step: per-scale weighted, fixed-order reduction of the raw per-CTA
@@ -678,6 +678,7 @@ __global__ void __launch_bounds__(32 * 24) pose_finish_fused_kernel(const __grid
   __shared__ double gP[24];
   __shared__ float wS[kMaxScales];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, e = tid >> 5;   // warp e reduces entry e
+  grid_dependency_wait();        // (launched programmatically behind the gradient finish: sums + partials are complete)
   if (tid < a.S) wS[tid] = scale_grads(a, tid).reproj / (a.sums[(size_t)tid * sums_stride(a.B) + 1] + 1e-7f);
   __syncthreads();
   {
@@ -715,8 +716,7 @@ __global__ void __launch_bounds__(32 * 24) pose_finish_fused_kernel(const __grid
 }
 
 cudaError_t launch_pose_finish_fused(const VslArgs& a, cudaStream_t stream) {
-  pose_finish_fused_kernel<<<a.B, 32 * 24, 0, stream>>>(a, a.tiles_x * a.tiles_y);
-  return cudaGetLastError();
+  return launch_pdl(pose_finish_fused_kernel, dim3(a.B), dim3(32 * 24), 0, stream, a, a.tiles_x * a.tiles_y);
 }
 
 }  // namespace ppea

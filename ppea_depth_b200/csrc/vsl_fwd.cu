@@ -306,6 +306,8 @@ __global__ void __launch_bounds__(kFinishThreads) vsl_finish_kernel(const __grid
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int s = wid / kFinishWarps, w = wid % kFinishWarps;
   const int stride = sums_stride(a.B);
+  grid_dependency_wait();        // the partial sums of the main launch
+  grid_launch_dependents();      // one CTA: the next kernel's CTAs may take the idle SMs now (they wait for our sums)
   if (s < a.S) {
     // tile partials of scale s: 256 threads, independent loads (4 in flight per thread)
     double v0 = 0, v1 = 0, v2 = 0;
@@ -397,8 +399,7 @@ __global__ void __launch_bounds__(kFinishThreads) vsl_finish_kernel(const __grid
 }
 
 cudaError_t launch_vsl_finish(const VslArgs& a, int nblk_fwd, cudaStream_t stream) {
-  vsl_finish_kernel<<<1, kFinishThreads, 0, stream>>>(a, nblk_fwd);
-  return cudaGetLastError();
+  return launch_pdl(vsl_finish_kernel, dim3(1), dim3(kFinishThreads), 0, stream, a, nblk_fwd);
 }
 
 }  // namespace ppea

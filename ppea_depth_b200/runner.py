@@ -97,7 +97,7 @@ class FusedPlan:
     @property
     def launches_backward(self):
         if self.fused:
-            return 1 + (1 if self.grad_pose else 0)     # gradient finish (rescale + smoothness), pose finish
+            return 1 + (1 if self.grad_pose else 0)     # gradient finish (combines the un-normalised fields), pose finish
         n = 1 + (1 if self.grad_pose else 0)     # fused backward (tiles + smoothness CTAs), pose finish
         if self.cfg.deterministic:               # + smoothness backward + one upsample gather per coarse scale
             n += 1 + sum(1 for d in self.disps if tuple(d.shape[-2:]) != (self.H, self.W))
