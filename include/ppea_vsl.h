@@ -223,6 +223,14 @@ int ppea_smooth_forward(const float* disp, const float* img, float* out_scalar, 
 int ppea_smooth_backward(const float* disp, const float* img, const float* grad_scalar, float* grad_disp,
                          int batch, int height, int width, void* stream);
 
+/* ---- input format: uint8 images expanded on the device --------------------
+ * The loss reads the un-augmented ("color", f, s) frames, which the reference produces on the CPU as
+ * torchvision ToTensor of a uint8 PIL image (datasets/mono_dataset.py:62, :106): float32(k) / 255,
+ * one correctly rounded division.  Shipping the uint8 planes and expanding them here gives the loss
+ * bit-identical inputs for a quarter of the host->device bytes.  Any layout: `count` bytes in,
+ * `count` floats out, same order. */
+int ppea_images_u8_to_f32(const uint8_t* src, float* dst, size_t count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -44,6 +44,12 @@ def default_opt(**kw):
 # --------------------------------------------------------------------------
 # per-op restatements
 # --------------------------------------------------------------------------
+def images_from_u8(img_u8):
+    """torchvision ToTensor on a uint8 image (datasets/mono_dataset.py:62, :106; torchvision functional.to_tensor:
+    ``img.to(float32).div(255)``): the float frames the loss reads are exactly k/255."""
+    return img_u8.to(torch.float32).div(255)
+
+
 def disp_to_depth(disp, min_depth, max_depth):
     # layers.py:14-23 -- scaled = 1/max + (1/min - 1/max) * disp ; depth = 1/scaled
     lo = 1.0 / max_depth

@@ -32,6 +32,7 @@ import torch
 
 from . import functional as Fn
 from .functional import VslConfig
+from .images import FrameCache
 
 _RESULT_KEY = "_ppea_vsl_result"
 
@@ -81,11 +82,12 @@ def _run_fused(self, inputs, outputs, is_multi):
     else:
         groups.append((0, S, 0))                     # all scales share source_scale 0 (trainer.py:886-888)
     results = []
+    frame = FrameCache()          # uint8 frames are expanded on the device, once each (images.py)
     for first, n, ss in groups:
         scales = range(first, first + n)
         disps = [outputs[("disp", s)] for s in scales]
-        colors = [inputs[("color", 0, s)] for s in scales]
-        tgt = inputs[("color", 0, ss)]
+        colors = [frame(inputs[("color", 0, s)]) for s in scales]
+        tgt = frame(inputs[("color", 0, ss)])
         kw = {}
         cfg = _config(self, is_multi, first_scale=first, total_scales=S)
         if is_multi:
@@ -96,7 +98,7 @@ def _run_fused(self, inputs, outputs, is_multi):
                 kw["aug_mask"] = kw["aug_mask"][:o.batch_size]
         elif not _opt(self, "disable_automasking", False):    # the flag only removes the noise (trainer.py:1084-1087)
             kw["noise"] = [_draw_noise(self, (tgt.shape[0], 1, tgt.shape[2], tgt.shape[3]), dev) for _ in scales]
-        res = Fn.view_synthesis_loss(disps, T, tgt, (inputs[("color", f0, ss)], inputs[("color", f1, ss)]),
+        res = Fn.view_synthesis_loss(disps, T, tgt, (frame(inputs[("color", f0, ss)]), frame(inputs[("color", f1, ss)])),
                                      inputs[("K", ss)], inputs[("inv_K", ss)], colors, cfg, **kw)
         results.append((first, n, res))
     return results

@@ -165,3 +165,52 @@ def test_modules_against_reference_classes():
     sd, dp = P.disp_to_depth(d, 0.1, 100.0)
     sd_r, dp_r = L.disp_to_depth(d, 0.1, 100.0)
     assert torch.equal(sd, sd_r) and torch.equal(dp, dp_r)
+
+
+@pytest.mark.parametrize("n", [256, 3 * 37 * 53, 12 * 3 * 192 * 640 + 5])
+def test_images_u8_to_f32_is_totensor(n):
+    """uint8 frames expanded on the device == torchvision ToTensor (oracle.images_from_u8), bit for bit; odd sizes and
+    unaligned views take the scalar tail / scalar path."""
+    from oracle import vsl_oracle as O
+    from ppea_depth_b200 import images_to_float
+    g = torch.Generator().manual_seed(n)
+    u8 = torch.randint(0, 256, (n + 3,), dtype=torch.uint8, generator=g)
+    for off in (0, 3):
+        view = u8[off:off + n]
+        got = images_to_float(view.cuda()) if off == 0 else images_to_float(u8.cuda()[off:off + n])
+        assert got.dtype == torch.float32 and torch.equal(got.cpu(), O.images_from_u8(view))
+    with pytest.raises(RuntimeError):
+        images_to_float(u8)                                   # no CPU path
+
+
+def test_loss_accepts_uint8_frames():
+    """The loss methods fed uint8 colour frames give bit-identical results to the float frames (k/255)."""
+    from gpu_helpers import FeedNoise
+    from oracle import vsl_oracle as O
+    from ppea_depth_b200.loss import ViewSynthesisLoss
+    from ppea_depth_b200.synth import SynthConfig, make_batch, make_noise
+    cfg = SynthConfig(batch=2, height=64, width=96, num_scales=4, seed=5)
+    inputs, outputs = make_batch(cfg)
+    noise = make_noise(cfg, 4)
+    opt = O.default_opt(sclm=3, height=64, width=96, batch_size=2)
+
+    def run(as_u8):
+        ins, outs = O.clone_batch(inputs, outputs, device="cuda")
+        if as_u8:
+            for k in list(ins):
+                if k[0] == "color":
+                    ins[k] = torch.round(ins[k] * 255).to(torch.uint8)
+        mod = ViewSynthesisLoss(opt)
+        with FeedNoise(noise):
+            mod.generate_images_pred(ins, outs, False)
+            losses, _ = mod.compute_losses(ins, outs, False)
+        losses["loss"].backward()
+        return float(losses["loss"]), [outs[("disp", s)].grad.cpu() for s in range(4)]
+
+    la, ga = run(False)
+    lb, gb = run(True)
+    assert la == lb
+    # (coarse-scale gradients are float atomics: equal up to summation order)
+    assert torch.equal(ga[0], gb[0])
+    for a, b in zip(ga[1:], gb[1:]):
+        assert float((a - b).abs().max()) <= 2e-6 * float(a.abs().max())

@@ -125,3 +125,15 @@ def test_gradcheck_fp64_small():
     h = 1e-7
     fd = (f(d0 + h * direction, *args[1:]) - f(d0 - h * direction, *args[1:])) / (2 * h)
     assert math.isclose(float(fd), float((an[0] * direction).sum()), rel_tol=2e-2, abs_tol=1e-7)
+
+
+def test_images_from_u8_is_the_synthetic_quantisation():
+    """The synthetic frames are exact k/255 (what ToTensor gives the reference): the uint8 round trip is the identity."""
+    from ppea_depth_b200.synth import SynthConfig, make_batch
+    inputs, _ = make_batch(SynthConfig(batch=1, height=32, width=64, num_scales=2, seed=3))
+    for f in (0, -1, 1):
+        img = inputs[("color", f, 0)]
+        u8 = torch.round(img * 255).to(torch.uint8)
+        assert torch.equal(O.images_from_u8(u8), img)
+    k = torch.arange(256, dtype=torch.uint8)
+    assert torch.equal(O.images_from_u8(k).double(), (k.double() / 255).float().double())     # correctly rounded k/255
