@@ -131,6 +131,13 @@ def make_sets(wl, n_sets, seed0, device, is_multi):
     return sets
 
 
+def _nbytes(shape, dtype):
+    n = 1
+    for d in shape:
+        n *= d
+    return n * torch.empty((), dtype=dtype).element_size()
+
+
 def tensors_of_step(inputs, outputs, noise, S, is_multi):
     """The tensors one step reads (what the e2e leg copies host->device every step)."""
     t = {("in",) + k: v for k, v in inputs.items() if k[0] in ("K", "inv_K") and k[1] == 0}
@@ -349,29 +356,56 @@ def main():
                               disable_motion_masking=False, no_matching_augmentation=False, batch_size=B,
                               disparity_smoothness=1e-3)
         mod = ViewSynthesisLoss(opt, deterministic=args.deterministic, noise_mode="device", fused=False if args.no_fused else None)
-        host_sets = []
+        def collate(t):
+            """One pinned arena per batch (what a collate_fn writing into a pinned buffer gives): a step's inputs cross
+            PCIe as ONE copy.  Returns (arena, layout) with layout[key] = (byte offset, shape, dtype); uint8 frames first,
+            contiguous, so that they can be expanded on the device by one call."""
+            layout, off = {}, 0
+            for k in sorted(t, key=lambda k: (t[k].dtype != torch.uint8, str(k))):
+                v = t[k]
+                off = (off + 255) // 256 * 256
+                layout[k] = (off, tuple(v.shape), v.dtype)
+                off += v.numel() * v.element_size()
+            arena = torch.empty(off, dtype=torch.uint8).pin_memory()
+            for k, (o, shape, dt) in layout.items():
+                arena[o:o + t[k].numel() * t[k].element_size()].view(dt).view(shape).copy_(t[k])
+            return arena, layout
+
+        step_tensors = []
         for (inputs, outputs, noise) in sets[:4]:
             t = tensors_of_step(inputs, outputs, noise, S, is_multi)
-            t = {k: v for k, v in t.items() if k[0] != "noise"}       # e2e draws the noise on the device (noise_mode="device")
-            host_sets.append({k: v.pin_memory() for k, v in t.items()})
-        h2d = sum(v.numel() * v.element_size() for v in host_sets[0].values())
+            step_tensors.append({k: v for k, v in t.items() if k[0] != "noise"})   # e2e draws the noise on the device (noise_mode="device")
+        host_sets = [collate(t) for t in step_tensors]
+        h2d = sum(v.numel() * v.element_size() for v in step_tensors[0].values())
         Ke = args.e2e_steps or min(K, 50)
 
         copy_stream = torch.cuda.Stream(device=device)
 
         def start_h2d(hs):
-            """Enqueues the step's host->device copies on the copy stream (as a pin_memory dataloader does one
-            batch ahead); returns the device tensors and the event that marks their arrival."""
+            """Enqueues the step's host->device copy on the copy stream (as a pin_memory dataloader does ahead of
+            the step); returns the device tensors (views of the device arena) and the event that marks their arrival."""
+            arena, layout = hs
             with torch.cuda.stream(copy_stream):
-                dev = {k: v.to(device, non_blocking=True) for k, v in hs.items()}
+                d_arena = arena.to(device, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
-            return dev, ev
+            return (d_arena, layout), ev
 
         def e2e_compute(dev, ev):
+            from ppea_depth_b200 import images_to_float
+            d_arena, layout = dev
             torch.cuda.current_stream().wait_event(ev)
-            for v in dev.values():
-                v.record_stream(torch.cuda.current_stream())
+            d_arena.record_stream(torch.cuda.current_stream())
+            dev = {k: d_arena[o:o + _nbytes(shape, dt)].view(dt).view(shape) for k, (o, shape, dt) in layout.items()}
+            u8 = [k for k, (o, shape, dt) in layout.items() if dt == torch.uint8]
+            if u8:
+                # uint8 frames: one expansion call over their contiguous block (public API: images_to_float)
+                lo = min(layout[k][0] for k in u8)
+                hi = max(layout[k][0] + _nbytes(layout[k][1], layout[k][2]) for k in u8)
+                f32 = images_to_float(d_arena[lo:hi])
+                for k in u8:
+                    o, shape, _ = layout[k]
+                    dev[k] = f32[o - lo:o - lo + _nbytes(shape, torch.uint8)].view(shape)
             ins = {k[1:]: v for k, v in dev.items() if k[0] == "in"}
             outs = {(k[1] if len(k) == 2 else k[1:]): v for k, v in dev.items() if k[0] == "out"}
             for s in range(S):
@@ -384,6 +418,8 @@ def main():
             losses["loss"].backward()
             return losses["loss"]
 
+        loss_host = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+        loss_ev = [torch.cuda.Event() for _ in range(2)]
         DEPTH = 2     # batches in flight on the copy stream (a pin_memory DataLoader's prefetch_factor)
 
         def e2e_run(n):
@@ -398,8 +434,16 @@ def main():
                 if i + DEPTH < n:
                     q.append(start_h2d(host_sets[(i + DEPTH) % len(host_sets)]))
                 loss = e2e_compute(*cur)
-                last = float(loss.item())            # D2H of the step's result (synchronises the compute stream)
-            return last
+                # D2H of the step's result into pinned memory, every step; the host looks at it one step later (as a
+                # training loop logs its loss), so the GPU is not left idle while the host enqueues the next step
+                slot = i % 2
+                loss_host[slot].copy_(loss.detach().reshape(1), non_blocking=True)
+                loss_ev[slot].record()
+                if i >= 1:
+                    loss_ev[1 - slot].synchronize()
+                    last = float(loss_host[1 - slot][0])
+            loss_ev[(n - 1) % 2].synchronize()
+            return float(loss_host[(n - 1) % 2][0])
 
         def time_e2e():
             e2e_run(3)
@@ -415,15 +459,18 @@ def main():
         e2e = {"value": world * B * H * W / (ms_e2e * 1e-3) / 1e6, "unit": "Mpixels/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e, "steps": Ke,
                "api": "ppea_depth_b200.loss.ViewSynthesisLoss.generate_images_pred + compute_losses + backward (noise_mode=device); "
-                      "inputs of the next two steps are copied on a second stream while step i computes"}
+                      "a step's inputs sit in one pinned arena and cross PCIe as one copy; the next two steps are copied on a second "
+                      "stream while step i computes; the loss is copied "
+                      "to pinned host memory every step and read by the host one step later"}
         # Same call, colour frames handed over as the dataset's uint8 planes and expanded on the device
         # (ppea_images_u8_to_f32, bit-identical to ToTensor): a quarter of the image bytes cross PCIe.  Reported beside the
         # reference-facing float32 number, not instead of it.
-        for hs in host_sets:
-            for k in list(hs):
+        for t in step_tensors:
+            for k in list(t):
                 if k[0] == "in" and k[1] == "color":
-                    hs[k] = torch.round(hs[k] * 255).to(torch.uint8).pin_memory()
-        h2d_u8 = sum(v.numel() * v.element_size() for v in host_sets[0].values())
+                    t[k] = torch.round(t[k] * 255).to(torch.uint8)
+        host_sets = [collate(t) for t in step_tensors]
+        h2d_u8 = sum(v.numel() * v.element_size() for v in step_tensors[0].values())
         ms_u8 = time_e2e()
         e2e["uint8_frames"] = {"value": world * B * H * W / (ms_u8 * 1e-3) / 1e6, "unit": "Mpixels/s", "h2d_bytes_per_step": h2d_u8,
                                "d2h_bytes_per_step": 4, "ms_per_step": ms_u8, "steps": Ke}
