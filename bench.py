@@ -269,7 +269,7 @@ def main():
     sets = probe + make_sets(wl, n_sets - 1, 1000 * rank + 1, device, is_multi)
     plans = [build_plan(t, wl, device, is_multi, args.deterministic, fused=False if args.no_fused else None) for t in sets]
     fused = plans[0].fused
-    cfg_desc["kernels"] = ("single-launch fused step (vsl_fused_kernel) + finish + gradient finish + pose finish" if fused
+    cfg_desc["kernels"] = ("single-launch fused step (vsl_fused_kernel) + finish + gradient finish + pose finish (tail kernels launched programmatically)" if fused
                            else "vsl_forward_kernel + finish + vsl_backward_kernel + pose finish")
     for p in plans:
         p.capture()
@@ -327,15 +327,16 @@ def main():
         if fused:
             # The fused launch does the forward AND the backward work of every pixel.scale but has to move less than the
             # two-launch figure of SURVEY.md §8d: target/sources are read once, sel never round-trips.  Its own compulsory
-            # bytes: tgt 12 + src 24 + noise 4 + depth 4 + sel 1 + loss 4 + (disp 4 + colour 12 + raw grad 4)/4^s.
+            # bytes: tgt 12 + src 24 + noise 4 + depth 4 + sel 1 + loss 4 + (disp 4 + colour 12 + raw grad 4 + stencil 4)/4^s;
+            # multi path: cons_mask 4 + mono_depth 4 instead of the noise, + consistency field 4/4^s.
             dom = "vsl_fused_kernel"
-            dom_bytes = sum(49.0 + 20.0 / 4 ** s for s in range(S)) * n_px
+            dom_bytes = sum((53.0 if is_multi else 49.0) + (28.0 if is_multi else 24.0) / 4 ** s for s in range(S)) * n_px
         else:
             dom = "vsl_backward_kernel" if stage_ms["vsl_backward_kernel"] >= stage_ms["vsl_forward_kernel"] else "vsl_forward_kernel"
             dom_bytes = bwd_b if dom == "vsl_backward_kernel" else fwd_b
         achieved = dom_bytes / (stage_ms[dom] * 1e-3) / 1e9
         traffic = None            # DRAM bytes of one launch of that kernel from the committed ncu capture (same workload only)
-        tpath = os.path.join(ROOT, "profiles", "r1g_traffic.json" if fused else "r1f_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r1i_traffic.json" if fused else "r1f_traffic.json")
         if os.path.exists(tpath) and args.workload == "kitti" and not is_multi and not args.deterministic:
             traffic = json.load(open(tpath)).get(dom)
         roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define PPEA_ABI_VERSION 4
+#define PPEA_ABI_VERSION 5
 
 /* error codes (negative) */
 #define PPEA_OK 0

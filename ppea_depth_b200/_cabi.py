@@ -20,7 +20,7 @@ INCLUDE_DIR = os.path.join(os.path.dirname(PKG_DIR), "include")
 SOURCES = ("api.cu", "vsl_fwd.cu", "vsl_bwd.cu", "vsl_fused.cu", "smooth.cu", "ops.cu")
 HEADERS = ("vsl_common.cuh", "vsl_math.cuh", "vsl_gather.cuh", "smooth.cuh")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 TRACE_EVENTS = 5
 MAX_SCALES = 4
 SUMS_PER_SCALE = 8
