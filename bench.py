@@ -256,6 +256,8 @@ def main():
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner out of stdout: rank 0 prints ONE JSON line
         torch.distributed.init_process_group("nccl", device_id=device)
     from ppea_depth_b200 import _cabi
     from ppea_depth_b200.synth import algorithmic_bytes
