@@ -271,8 +271,42 @@ static int check_fused(const PpeaVslParams* p, const PpeaVslFused* f, bool backw
   return PPEA_OK;
 }
 
+// TMA descriptor of one colour frame batch viewed as a (B*3, H, W) fp32 tensor, box = 3 planes x (TH+4) rows x (TW+8)
+// columns (the fused kernel's staging tile; TMA wants a 16-byte aligned start, so two unused columns on each side).  The encoder is a driver entry point (no libcuda link: fetched through the
+// statically linked runtime).  Returns false when the tensor cannot be described (row pitch not a multiple of 16 bytes,
+// unaligned base, driver without the entry point): the kernel then stages every tile with its reflecting loop.
+typedef CUresult (*TensorMapEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                           const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                           CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeTiledFn tensor_map_encoder() {
+  static std::once_flag once;
+  static TensorMapEncodeTiledFn fn = nullptr;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<TensorMapEncodeTiledFn>(sym);
+    (void)cudaGetLastError();
+  });
+  return fn;
+}
+static bool frame_tensor_map(CUtensorMap* tm, const float* base, int B, int H, int W) {
+  TensorMapEncodeTiledFn enc = tensor_map_encoder();
+  if (!enc || (W % 4) != 0 || !aligned(base, 16)) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B * 3};
+  const cuuint64_t strides[2] = {(cuuint64_t)W * sizeof(float), (cuuint64_t)W * H * sizeof(float)};
+  const cuuint32_t box[3] = {(cuuint32_t)kFusedTileWc + 8, (cuuint32_t)kFusedTileHc + 4, 3};   // starts at the aligned column x0 - 4
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static void fused_args(const PpeaVslParams* p, const PpeaVslFused* f, VslArgs& a) {
   fill_args(p, a);
+  a.use_tma = (frame_tensor_map(&a.tm_tgt, a.tgt, a.B, a.H, a.W) && frame_tensor_map(&a.tm_src[0], a.src[0], a.B, a.H, a.W) &&
+               frame_tensor_map(&a.tm_src[1], a.src[1], a.B, a.H, a.W))
+                  ? 1
+                  : 0;
   const FusedWorkspace fw = fused_workspace(p);
   const FwdWorkspace ws = fwd_workspace(p->batch, p->height, p->width, p->num_scales);
   a.tiles_x = ceil_div(a.W, kFusedTileWc);

@@ -1,6 +1,7 @@
 // vsl_common.cuh -- launch-side structures shared by the view-synthesis-loss kernels.
 #pragma once
 
+#include <cuda.h>            // CUtensorMap (type only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -54,6 +55,11 @@ struct VslArgs {
   const float* grad_losses;
   float* pose_partials; // [nblk_bwd][S][24]
   float* grad_T[2];
+  // fused step: TMA descriptors of the colour frames viewed as (B*3, H, W) fp32 tensors, box 3 x (TH+4) x (TW+8)
+  // (valid when use_tma; interior tiles are staged by cp.async.bulk.tensor, border tiles by the reflecting loop)
+  int use_tma;
+  alignas(64) CUtensorMap tm_tgt;
+  alignas(64) CUtensorMap tm_src[2];
 };
 
 constexpr int kFwdTileW = 32;

@@ -42,15 +42,53 @@ template <int TW, int TH, int NT>
 struct FusedSmem {
   static constexpr int RW = TW + 4, RH = TH + 4, RP = RW * RH;   // value region (2-pixel halo)
   static constexpr int QW = TW + 2, QH = TH + 2, QP = QW * QH;   // decision / coefficient region (1-pixel halo)
-  float y[3][RP];       // target (broadcast into both lanes at use)
-  f2 x[3][RP];          // un-warped, then warped (source 0, source 1)
+  // TMA needs a 16-byte aligned global start: the staged target / source tiles are YW = RW + 4 columns wide (two unused
+  // columns on each side), region column j sits at tile column j + 2.
+  static constexpr int YW = RW + 4, YP = YW * RH;
+  f2 x[3][RP];          // warped samples (source 0, source 1).  Before the first gather the un-warped sources live here as
+                        // two scalar plane triples [source][c][YP] (identity loss), spilling into cf (idle until pass Q)
   float cf[9][QP];      // [3 c + e]: cA, cB, cC of channel c for the source selected at q
+  alignas(128) float y[3][YP];       // target (broadcast into both lanes at use)
   f2 ind[QP];           // mask(q) * [sel(q) == lane]
   float ident[QP];      // identity loss min_f photo(src_f, tgt)   (scale-invariant)
   f2 G[12];             // per-source geometry (vsl_math.cuh Geom), lanes = sources
   float redf[3][NT / 32];
   float red[24][NT / 32];
+  unsigned long long mbar;                                   // arrival barrier of the TMA tile loads
+  static constexpr int kSplit = 3 * YP;                      // second source's plane triple (floats)
+  static_assert((kSplit * 4) % 128 == 0, "TMA destinations are 128-byte aligned");
+  static_assert(2 * kSplit * 4 <= (int)(sizeof(f2) * 3 * RP + sizeof(float) * 9 * QP), "split source planes must fit in x + cf");
 };
+
+// ---- TMA / mbarrier primitives (PTX: cp.async.bulk.tensor, mbarrier)
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// box at (x, y, plane) of a (planes, H, W) tensor -> dense [plane][row][col] tile in shared memory; out-of-range cells read 0
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int x, int y, int z, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                   smem_u32(dst)),
+               "l"(reinterpret_cast<unsigned long long>(tm)), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+               : "memory");
+}
 
 struct PhotoQ {
   f2 L;     // 0.85 mean_c SSIM + 0.15 mean_c |y - x|  (trainer.py:995-1007), both sources
@@ -59,7 +97,9 @@ struct PhotoQ {
 
 // Photometric loss of both sources at one pixel q from its 3x3 window (xq / yq point at the window's
 // top-left cell); with ADJ also the SSIM adjoint coefficients of the three channels (weight W_SSIM).
-template <bool ADJ, int RW, int RP>
+// Row / plane strides: XW, XP of the samples, YW, YP of the target.
+// XSPLIT > 0: the two sources are scalar planes (xq viewed as float*, second source XSPLIT floats further).
+template <bool ADJ, int XW, int XP, int YW, int YP, int XSPLIT = 0>
 __device__ __forceinline__ PhotoQ photo_q(const f2* __restrict__ xq, const float* __restrict__ yq, bool no_ssim, float w_l1,
                                           f2 (&co)[9]) {
   PhotoQ o;
@@ -67,13 +107,21 @@ __device__ __forceinline__ PhotoQ photo_q(const f2* __restrict__ xq, const float
   o.cs = dup2(0.f);
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const f2* xp = xq + c * RP;
-    const float* yp = yq + c * RP;
+    const f2* xp = xq + c * XP;
+    const float* x0p = reinterpret_cast<const float*>(xq) + c * XP;
+    const float* yp = yq + c * YP;
     f2 Sx, Sxx, Sxy, Sy, Syy;
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy) {
-      const f2 xa = xp[dy * RW], xb = xp[dy * RW + 1], xc = xp[dy * RW + 2];
-      const f2 ya = dup2(yp[dy * RW]), yb = dup2(yp[dy * RW + 1]), yc = dup2(yp[dy * RW + 2]);
+      f2 xa, xb, xc;
+      if (XSPLIT > 0) {
+        xa = mk2(x0p[dy * XW], x0p[XSPLIT + dy * XW]);
+        xb = mk2(x0p[dy * XW + 1], x0p[XSPLIT + dy * XW + 1]);
+        xc = mk2(x0p[dy * XW + 2], x0p[XSPLIT + dy * XW + 2]);
+      } else {
+        xa = xp[dy * XW], xb = xp[dy * XW + 1], xc = xp[dy * XW + 2];
+      }
+      const f2 ya = dup2(yp[dy * YW]), yb = dup2(yp[dy * YW + 1]), yc = dup2(yp[dy * YW + 2]);
       f2 hx, hxx, hxy, hy, hyy;
       row_sums_y<f2>(ya, yb, yc, hy, hyy);
       row_sums_x<f2>(xa, xb, xc, ya, yb, yc, hx, hxx, hxy);
@@ -140,10 +188,10 @@ constexpr int kFusedThreads = PPEA_FUSED_THREADS;
 template <int TW, int TH, int NT, bool POSE, bool MULTI, bool DET>
 __global__ void __launch_bounds__(NT, PPEA_FUSED_CTAS) vsl_fused_kernel(const __grid_constant__ VslArgs a) {
   using Smem = FusedSmem<TW, TH, NT>;
-  constexpr int RW = Smem::RW, RP = Smem::RP, QW = Smem::QW;
+  constexpr int RW = Smem::RW, RP = Smem::RP, QW = Smem::QW, YW = Smem::YW, YP = Smem::YP;
   constexpr int R = (TW * TH) / NT;
   static_assert(TW == 32 && (NT / 32) * R == TH && NT >= 128, "the gather/row mapping assumes lane == tile column and R rows per warp");
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
 
   grid_launch_dependents();      // the dependent is the one-CTA finish kernel: let it take its place early
@@ -182,19 +230,45 @@ __global__ void __launch_bounds__(NT, PPEA_FUSED_CTAS) vsl_fused_kernel(const __
   const float* tgt_b = a.tgt + (size_t)b * 3 * plane;
   const float* src_b[2] = {a.src[0] + (size_t)b * 3 * plane, a.src[1] + (size_t)b * 3 * plane};
 
-  // ---- stage the target (+ the un-warped sources for the identity loss) with a 2-pixel reflection halo
-  for (int idx = tid; idx < RP; idx += NT) {
-    const int i = idx / RW, j = idx - i * RW;
-    const int py = reflect_index(y0 - 2 + i, H), px = reflect_index(x0 - 2 + j, W);
-    const size_t o = (size_t)py * W + px;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) sm.y[c][idx] = __ldg(tgt_b + c * plane + o);
-    if (automask) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) sm.x[c][idx] = mk2(__ldg(src_b[0] + c * plane + o), __ldg(src_b[1] + c * plane + o));
+  // ---- stage the target (+ the un-warped sources for the identity loss) with a 2-pixel reflection halo.
+  // Interior tiles: three TMA tile loads (cp.async.bulk.tensor.3d, box 3 planes x RH rows x YW columns starting at the
+  // 16-byte aligned column x0 - 4) issued by one thread and awaited on an mbarrier; tiles that touch the image border:
+  // the reflecting loop, into the same layout.
+  float* const xs = reinterpret_cast<float*>(&sm.x[0][0]);       // identity-loss view of x (+ cf): [source][c][YP] scalars
+  constexpr int kSplit = Smem::kSplit;
+  const bool by_tma = a.use_tma && x0 >= 2 && y0 >= 2 && x0 + TW + 2 <= W && y0 + TH + 2 <= H;      // (block-uniform)
+  if (by_tma) {
+    if (tid == 0) mbar_init(&sm.mbar, 1);
+    __syncthreads();
+    if (tid == 0) {
+      constexpr unsigned kTileBytes = 3 * YP * sizeof(float);
+      mbar_expect_tx(&sm.mbar, automask ? 3 * kTileBytes : kTileBytes);
+      tma_load_3d(&sm.y[0][0], &a.tm_tgt, x0 - 4, y0 - 2, b * 3, &sm.mbar);
+      if (automask) {
+        tma_load_3d(xs, &a.tm_src[0], x0 - 4, y0 - 2, b * 3, &sm.mbar);
+        tma_load_3d(xs + kSplit, &a.tm_src[1], x0 - 4, y0 - 2, b * 3, &sm.mbar);
+      }
     }
+    mbar_wait(&sm.mbar, 0);
+    __syncthreads();             // (the geometry block above is read by every thread)
+  } else {
+    for (int idx = tid; idx < RP; idx += NT) {
+      const int i = idx / RW, j = idx - i * RW;
+      const int py = reflect_index(y0 - 2 + i, H), px = reflect_index(x0 - 2 + j, W);
+      const size_t o = (size_t)py * W + px;
+      const int yi = i * YW + j + 2;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) sm.y[c][yi] = __ldg(tgt_b + c * plane + o);
+      if (automask) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          xs[c * YP + yi] = __ldg(src_b[0] + c * plane + o);
+          xs[kSplit + c * YP + yi] = __ldg(src_b[1] + c * plane + o);
+        }
+      }
+    }
+    __syncthreads();
   }
-  __syncthreads();
 
   // ---- identity loss of every q of the tile + 1 halo (trainer.py:1060-1069), once for all scales
   if (automask) {
@@ -213,7 +287,7 @@ __global__ void __launch_bounds__(NT, PPEA_FUSED_CTAS) vsl_fused_kernel(const __
       float idl = 0.f;
       if (qy >= 0 && qy < H && qx >= 0 && qx < W) {
         f2 unused[9];
-        const PhotoQ ph = photo_q<false, RW, RP>(&sm.x[0][i * RW + j], &sm.y[0][i * RW + j], no_ssim, l1w, unused);
+        const PhotoQ ph = photo_q<false, YW, YP, YW, YP, kSplit>(reinterpret_cast<const f2*>(xs + i * YW + j + 2), &sm.y[0][i * YW + j + 2], no_ssim, l1w, unused);
         idl = fminf(ph.L.x, ph.L.y);
       }
       sm.ident[qi] = idl;
@@ -333,7 +407,7 @@ __global__ void __launch_bounds__(NT, PPEA_FUSED_CTAS) vsl_fused_kernel(const __
         float nz = 0.f;
         if (automask && sc.noise) nz = __ldg(sc.noise + o);
         f2 co[9];
-        const PhotoQ ph = photo_q<true, RW, RP>(&sm.x[0][i * RW + j], &sm.y[0][i * RW + j], no_ssim, l1w, co);
+        const PhotoQ ph = photo_q<true, RW, RP, YW, YP>(&sm.x[0][i * RW + j], &sm.y[0][i * YW + j + 2], no_ssim, l1w, co);
         const Select sl = select_source(ph.L.x, ph.L.y, ph.cs.x, ph.cs.y, selec);
         bool on = true;
         float mq = 1.f;
@@ -400,7 +474,7 @@ __global__ void __launch_bounds__(NT, PPEA_FUSED_CTAS) vsl_fused_kernel(const __
           const int k = i - 2;
           const int gy = y0 + row0 + k;
           const int ridx = (row0 + k + 2) * RW + col + 2;
-          const f2 xv = sm.x[c][ridx], yv = dup2(sm.y[c][ridx]);
+          const f2 xv = sm.x[c][ridx], yv = dup2(sm.y[c][(row0 + k + 2) * YW + col + 4]);
           const f2 wl = sm.ind[(row0 + k + 1) * QW + col + 1];
           const f2 d = vsub(yv, xv);
           // L1 term:  -ind * l1w * sign(y - x)
