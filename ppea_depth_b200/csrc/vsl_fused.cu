@@ -231,13 +231,13 @@ __global__ void __launch_bounds__(NT, PPEA_FUSED_CTAS) vsl_fused_kernel(const __
   const float* src_b[2] = {a.src[0] + (size_t)b * 3 * plane, a.src[1] + (size_t)b * 3 * plane};
 
   // ---- stage the target (+ the un-warped sources for the identity loss) with a 2-pixel reflection halo.
-  // Interior tiles: three TMA tile loads (cp.async.bulk.tensor.3d, box 3 planes x RH rows x YW columns starting at the
-  // 16-byte aligned column x0 - 4) issued by one thread and awaited on an mbarrier; tiles that touch the image border:
-  // the reflecting loop, into the same layout.
+  // Three TMA tile loads (cp.async.bulk.tensor.3d, box 3 planes x RH rows x YW columns starting at the 16-byte aligned
+  // column x0 - 4) issued by one thread and awaited on an mbarrier; border tiles then patch their reflected halo.
+  // Tensors TMA cannot describe (row pitch not a multiple of 16 bytes): the reflecting loop, into the same layout.
   float* const xs = reinterpret_cast<float*>(&sm.x[0][0]);       // identity-loss view of x (+ cf): [source][c][YP] scalars
   constexpr int kSplit = Smem::kSplit;
-  const bool by_tma = a.use_tma && x0 >= 2 && y0 >= 2 && x0 + TW + 2 <= W && y0 + TH + 2 <= H;      // (block-uniform)
-  if (by_tma) {
+  const bool interior = x0 >= 2 && y0 >= 2 && x0 + TW + 2 <= W && y0 + TH + 2 <= H;      // (block-uniform)
+  if (a.use_tma) {
     if (tid == 0) mbar_init(&sm.mbar, 1);
     __syncthreads();
     if (tid == 0) {
@@ -251,6 +251,28 @@ __global__ void __launch_bounds__(NT, PPEA_FUSED_CTAS) vsl_fused_kernel(const __
     }
     mbar_wait(&sm.mbar, 0);
     __syncthreads();             // (the geometry block above is read by every thread)
+    if (!interior) {
+      // TMA zero-fills what lies outside the image: the reflected halo (layers.py:238) of a border tile is copied from
+      // the in-image cell it mirrors, which is part of the same tile (cells further out than the halo stay zero)
+      for (int idx = tid; idx < RP; idx += NT) {
+        const int i = idx / RW, j = idx - i * RW;
+        const int gy = y0 - 2 + i, gx = x0 - 2 + j;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) continue;
+        const int si = reflect_index(gy, H) - (y0 - 2), sj = reflect_index(gx, W) - (x0 - 2);
+        if (si < 0 || si >= Smem::RH || sj < 0 || sj >= RW) continue;
+        const int dst = i * YW + j + 2, src = si * YW + sj + 2;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) sm.y[c][dst] = sm.y[c][src];
+        if (automask) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            xs[c * YP + dst] = xs[c * YP + src];
+            xs[kSplit + c * YP + dst] = xs[kSplit + c * YP + src];
+          }
+        }
+      }
+      __syncthreads();
+    }
   } else {
     for (int idx = tid; idx < RP; idx += NT) {
       const int i = idx / RW, j = idx - i * RW;
