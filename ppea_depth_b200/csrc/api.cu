@@ -228,15 +228,17 @@ int ppea_vsl_backward(const PpeaVslParams* p, const PpeaVslGrads* g, void* strea
 static_assert(kFusedTileWc == kFwdTileW && kFusedTileHc >= kFwdTileH, "the fused step reuses the forward workspace layout (never more tiles than the forward)");
 
 struct FusedWorkspace {
-  size_t off_pose, off_raw[kMaxScales], off_raw2[kMaxScales], off_st[kMaxScales], raw_floats[kMaxScales], total_floats;
+  size_t off_pose, off_pose_sums, off_raw[kMaxScales], off_raw2[kMaxScales], off_st[kMaxScales], raw_floats[kMaxScales], total_floats;
 };
-// Layout (floats): [pose partials: nblk*S*24][raw photometric gradient of disp_s][multi path: raw consistency
+// Layout (floats): [pose partials: nblk*S*24][per-image pose sums: B*S*24 doubles][raw photometric gradient of disp_s][multi path: raw consistency
 // gradient of disp_s][smoothness stencil field of disp_s].  A coarse-scale raw field takes 2 floats per pixel:
 // with PPEA_F_DETERMINISTIC it is an array of 64-bit fixed-point accumulators.
 static FusedWorkspace fused_workspace(const PpeaVslParams* p) {
   FusedWorkspace w;
   w.off_pose = 0;
   size_t off = align_up((size_t)fused_blocks(p->batch, p->height, p->width) * p->num_scales * 24, 4);
+  w.off_pose_sums = off;                                             // [B][S][24] doubles
+  off += align_up((size_t)p->batch * p->num_scales * 24 * 2, 4);
   for (int s = 0; s < kMaxScales; ++s) {
     w.raw_floats[s] = 0;
     if (s < p->num_scales) {
@@ -314,6 +316,7 @@ static void fused_args(const PpeaVslParams* p, const PpeaVslFused* f, VslArgs& a
   a.partials = (float*)p->workspace + ws.off_partials;
   a.smooth_ws = (float*)p->workspace + ws.off_smooth;
   a.pose_partials = (float*)f->workspace + fw.off_pose;
+  a.pose_sums = reinterpret_cast<double*>((float*)f->workspace + fw.off_pose_sums);
   for (int s = 0; s < a.S; ++s) {
     a.sc[s].grad_raw = (float*)f->workspace + fw.off_raw[s];
     a.sc[s].grad_raw2 = (p->flags & PPEA_F_MULTI) ? (float*)f->workspace + fw.off_raw2[s] : nullptr;
@@ -351,7 +354,7 @@ int ppea_vsl_fused_forward(const PpeaVslParams* p, const PpeaVslFused* f, void* 
   PPEA_TRY(launch_vsl_fused(a, stream));
   PPEA_TRACE(p, 2);
   PPEA_TRACE(p, 3);
-  PPEA_TRY(launch_vsl_finish(a, fused_blocks(a.B, a.H, a.W), stream));
+  PPEA_TRY(launch_vsl_finish(a, fused_blocks(a.B, a.H, a.W), stream, (p->flags & PPEA_F_GRAD_POSE) && !(p->flags & PPEA_F_MULTI)));
   PPEA_TRACE(p, 4);
   return PPEA_OK;
 }
@@ -375,7 +378,6 @@ int ppea_vsl_fused_backward(const PpeaVslParams* p, const PpeaVslGrads* g, const
   PPEA_TRY(launch_vsl_grad_finish(a, stream));
   PPEA_TRACE(p, 2);
   PPEA_TRACE(p, 3);
-  if (pose) PPEA_TRY(launch_pose_finish_fused(a, stream));
   PPEA_TRACE(p, 4);
   return PPEA_OK;
 }

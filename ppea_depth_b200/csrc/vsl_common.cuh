@@ -54,6 +54,7 @@ struct VslArgs {
   // backward only
   const float* grad_losses;
   float* pose_partials; // [nblk_bwd][S][24]
+  double* pose_sums;    // fused step: [B][S][24] per-image, per-scale sums of the pose partials (finish launch -> gradient finish)
   float* grad_T[2];
   // fused step: TMA descriptors of the colour frames viewed as (B*3, H, W) fp32 tensors, box 3 x (TH+4) x (TW+8)
   // (valid when use_tma; interior tiles are staged by cp.async.bulk.tensor, border tiles by the reflecting loop)
@@ -120,13 +121,12 @@ inline int fused_blocks(int B, int H, int W) { return B * ceil_div(W, kFusedTile
 
 cudaError_t launch_vsl_forward(const VslArgs& a, cudaStream_t stream);
 cudaError_t launch_vsl_backward(const VslArgs& a, cudaStream_t stream);
-cudaError_t launch_vsl_finish(const VslArgs& a, int nblk_fwd, cudaStream_t stream);
+cudaError_t launch_vsl_finish(const VslArgs& a, int nblk_fwd, cudaStream_t stream, bool pose_sums = false);
 cudaError_t launch_smooth_backward(const VslArgs& a, cudaStream_t stream);
 cudaError_t launch_upsample_gather(const VslArgs& a, cudaStream_t stream);
 cudaError_t launch_pose_finish(const VslArgs& a, int nblk_bwd, cudaStream_t stream);
 cudaError_t launch_vsl_fused(const VslArgs& a, cudaStream_t stream);
 cudaError_t launch_vsl_grad_finish(const VslArgs& a, cudaStream_t stream);
-cudaError_t launch_pose_finish_fused(const VslArgs& a, cudaStream_t stream);
 
 // Programmatic dependent launch (sm_90+): a kernel launched with launch_pdl may become resident while its
 // predecessor in the stream is still running; it must call grid_dependency_wait() before touching anything

@@ -654,6 +654,44 @@ cudaError_t launch_vsl_fused(const VslArgs& a, cudaStream_t stream) {
 // ---------------------------------------------------------------------------
 constexpr int kGradFinishThreads = 256;
 
+// Pose gradient of the fused step (a role of the gradient-finish launch, its last B CTAs, one per image): the per-scale
+// sums of the raw d L / d P_f partials (finish launch, vsl_fwd.cu pose_sums_role) weighted by
+// w_s = upstream(reproj_s) / (sum(mask_s) + 1e-7), then d L / d T_f = K[:3,:]^T @ dL/dP_f  (autograd of layers.py:185).
+__device__ __forceinline__ void pose_combine_role(const VslArgs& a, int b) {
+  __shared__ double Q[24];
+  __shared__ double gP[24];
+  const int tid = threadIdx.x;
+  if (tid < 24) {
+    double t = 0;
+    for (int s = 0; s < a.S; ++s) {
+      const float w = scale_grads(a, s).reproj / (a.sums[(size_t)s * sums_stride(a.B) + 1] + 1e-7f);
+      t += (double)w * a.pose_sums[((size_t)b * a.S + s) * 24 + tid];
+    }
+    Q[tid] = t;
+  }
+  __syncthreads();
+  const float* K = a.K + b * 16;
+  const float* iK = a.inv_K + b * 16;
+  if (tid < 24) {
+    const int f = tid / 12, ee = tid % 12, r = ee / 4, j = ee % 4;
+    double t;
+    if (j == 3) {
+      t = Q[f * 12 + r * 4 + 3];
+    } else {
+      t = 0;
+      for (int k = 0; k < 3; ++k) t += Q[f * 12 + r * 4 + k] * (double)iK[j * 4 + k];
+    }
+    gP[tid] = t;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    const int f = tid / 16, ee = tid % 16, i = ee / 4, j = ee % 4;
+    double t = 0;
+    for (int r = 0; r < 3; ++r) t += (double)K[r * 4 + i] * gP[f * 12 + r * 4 + j];
+    a.grad_T[f][b * 16 + ee] = (float)t;
+  }
+}
+
 // VEC = 4: four consecutive pixels per thread through 128-bit accesses (needs h*w % 4 == 0 for every scale,
 // so that the four share an image, and 16-byte aligned grad_disp); VEC = 1 otherwise.
 template <int VEC>
@@ -702,9 +740,12 @@ __device__ __forceinline__ void zero_raw(float* field, unsigned idx, bool fixed)
 template <int VEC>
 __global__ void __launch_bounds__(kGradFinishThreads) vsl_grad_finish_kernel(const __grid_constant__ VslArgs a, int4 blk_end) {
   grid_dependency_wait();        // sums of the finish kernel (and, transitively, the fields of the main launch)
-  grid_launch_dependents();      // the pose-gradient kernel (B CTAs) may take its place; it waits for this grid to drain
   // scale of this CTA (blk_end.{x,y,z,w}: first block index past the blocks of scale 0..3)
   const int blk = blockIdx.x;
+  if (blk >= blk_end.w) {        // the last B CTAs combine the pose gradient of one image each (tiny)
+    pose_combine_role(a, blk - blk_end.w);
+    return;
+  }
   const int s = (blk >= blk_end.x) + (blk >= blk_end.y) + (blk >= blk_end.z);
   const int blk0 = s == 0 ? 0 : (s == 1 ? blk_end.x : (s == 2 ? blk_end.y : blk_end.z));
   const ScaleArgs& sc = a.sc[s];
@@ -763,56 +804,10 @@ cudaError_t launch_vsl_grad_finish(const VslArgs& a, cudaStream_t stream) {
     end[s] = acc;
   }
   const int4 be = make_int4(end[0], end[1], end[2], end[3]);
-  if (vec) return launch_pdl(vsl_grad_finish_kernel<4>, dim3(acc), dim3(kGradFinishThreads), 0, stream, a, be);
-  return launch_pdl(vsl_grad_finish_kernel<1>, dim3(acc), dim3(kGradFinishThreads), 0, stream, a, be);
-}
-
-// Pose gradient of the fused step: per-scale weighted, fixed-order reduction of the raw per-CTA
-// d L / d P_f partials of each image, then d L / d T_f = K[:3,:]^T @ dL/dP_f  (autograd of layers.py:185).
-__global__ void __launch_bounds__(32 * 24) pose_finish_fused_kernel(const __grid_constant__ VslArgs a, int tiles_per_image) {
-  __shared__ double Q[24];
-  __shared__ double gP[24];
-  __shared__ float wS[kMaxScales];
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, e = tid >> 5;   // warp e reduces entry e
-  grid_dependency_wait();        // (launched programmatically behind the gradient finish: sums + partials are complete)
-  if (tid < a.S) wS[tid] = scale_grads(a, tid).reproj / (a.sums[(size_t)tid * sums_stride(a.B) + 1] + 1e-7f);
-  __syncthreads();
-  {
-    // entries of image b: [tile][scale][24]; every load is independent of the others
-    double t = 0;
-    const int S = a.S, items = tiles_per_image * S;
-    const float* p = a.pose_partials + (size_t)b * items * 24 + e;
-#pragma unroll 4
-    for (int i = lane; i < items; i += 32) t += (double)(wS[i % S] * p[(size_t)i * 24]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    if (lane == 0) Q[e] = t;
-  }
-  __syncthreads();
-  const float* K = a.K + b * 16;
-  const float* iK = a.inv_K + b * 16;
-  if (tid < 24) {
-    const int f = tid / 12, ee = tid % 12, r = ee / 4, j = ee % 4;
-    double t;
-    if (j == 3) {
-      t = Q[f * 12 + r * 4 + 3];
-    } else {
-      t = 0;
-      for (int k = 0; k < 3; ++k) t += Q[f * 12 + r * 4 + k] * (double)iK[j * 4 + k];
-    }
-    gP[tid] = t;
-  }
-  __syncthreads();
-  if (tid < 32) {
-    const int f = tid / 16, ee = tid % 16, i = ee / 4, j = ee % 4;
-    double t = 0;
-    for (int r = 0; r < 3; ++r) t += (double)K[r * 4 + i] * gP[f * 12 + r * 4 + j];
-    a.grad_T[f][b * 16 + ee] = (float)t;
-  }
-}
-
-cudaError_t launch_pose_finish_fused(const VslArgs& a, cudaStream_t stream) {
-  return launch_pdl(pose_finish_fused_kernel, dim3(a.B), dim3(32 * 24), 0, stream, a, a.tiles_x * a.tiles_y);
+  const bool pose = (a.flags & PPEA_F_GRAD_POSE) && !(a.flags & PPEA_F_MULTI);
+  const int nblk = acc + (pose ? a.B : 0);
+  if (vec) return launch_pdl(vsl_grad_finish_kernel<4>, dim3(nblk), dim3(kGradFinishThreads), 0, stream, a, be);
+  return launch_pdl(vsl_grad_finish_kernel<1>, dim3(nblk), dim3(kGradFinishThreads), 0, stream, a, be);
 }
 
 }  // namespace ppea

@@ -300,6 +300,28 @@ cudaError_t launch_vsl_forward(const VslArgs& a, cudaStream_t stream) {
 constexpr int kFinishWarps = 8;                          // warps per scale
 constexpr int kFinishThreads = 32 * kFinishWarps * kMaxScales;
 
+// Fused step: CTAs 1..B of the finish launch reduce the per-tile pose partials of one image each to per-scale sums
+// (fixed order, double), so that the backward only has to weight S x 24 numbers per image (vsl_fused.cu pose_combine_role).
+__device__ __forceinline__ void pose_sums_role(const VslArgs& a, int b, int tiles_per_image) {
+  const int tid = threadIdx.x, lane = tid & 31, e = tid >> 5;      // warp e reduces entry e of every scale
+  if (e >= 24) return;
+  const int S = a.S;
+  double t[kMaxScales] = {0, 0, 0, 0};
+  const float* p = a.pose_partials + (size_t)b * tiles_per_image * S * 24 + e;
+#pragma unroll 2
+  for (int i = lane; i < tiles_per_image; i += 32) {
+#pragma unroll
+    for (int s = 0; s < kMaxScales; ++s)
+      if (s < S) t[s] += (double)__ldg(p + ((size_t)i * S + s) * 24);
+  }
+#pragma unroll
+  for (int s = 0; s < kMaxScales; ++s) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t[s] += __shfl_xor_sync(0xffffffffu, t[s], o);
+    if (lane == 0 && s < S) a.pose_sums[((size_t)b * S + s) * 24 + e] = t[s];
+  }
+}
+
 __global__ void __launch_bounds__(kFinishThreads) vsl_finish_kernel(const __grid_constant__ VslArgs a, int nblk) {
   __shared__ double part[kMaxScales][kFinishWarps][3];
   __shared__ double tot[kMaxScales][4];     // sum r*mask, sum mask, sum cons, normalised smoothness
@@ -307,7 +329,11 @@ __global__ void __launch_bounds__(kFinishThreads) vsl_finish_kernel(const __grid
   const int s = wid / kFinishWarps, w = wid % kFinishWarps;
   const int stride = sums_stride(a.B);
   grid_dependency_wait();        // the partial sums of the main launch
-  grid_launch_dependents();      // one CTA: the next kernel's CTAs may take the idle SMs now (they wait for our sums)
+  grid_launch_dependents();      // few CTAs: the next kernel's CTAs may take the idle SMs now (they wait for our sums)
+  if (blockIdx.x > 0) {
+    pose_sums_role(a, blockIdx.x - 1, a.tiles_x * a.tiles_y);
+    return;
+  }
   if (s < a.S) {
     // tile partials of scale s: 256 threads, independent loads (4 in flight per thread)
     double v0 = 0, v1 = 0, v2 = 0;
@@ -398,8 +424,8 @@ __global__ void __launch_bounds__(kFinishThreads) vsl_finish_kernel(const __grid
   }
 }
 
-cudaError_t launch_vsl_finish(const VslArgs& a, int nblk_fwd, cudaStream_t stream) {
-  return launch_pdl(vsl_finish_kernel, dim3(1), dim3(kFinishThreads), 0, stream, a, nblk_fwd);
+cudaError_t launch_vsl_finish(const VslArgs& a, int nblk_fwd, cudaStream_t stream, bool pose_sums) {
+  return launch_pdl(vsl_finish_kernel, dim3(1 + (pose_sums ? a.B : 0)), dim3(kFinishThreads), 0, stream, a, nblk_fwd);
 }
 
 }  // namespace ppea

@@ -97,7 +97,7 @@ class FusedPlan:
     @property
     def launches_backward(self):
         if self.fused:
-            return 1 + (1 if self.grad_pose else 0)     # gradient finish (combines the un-normalised fields), pose finish
+            return 1     # gradient finish (combines the un-normalised fields; its last B CTAs weight the pose sums)
         n = 1 + (1 if self.grad_pose else 0)     # fused backward (tiles + smoothness CTAs), pose finish
         if self.cfg.deterministic:               # + smoothness backward + one upsample gather per coarse scale
             n += 1 + sum(1 for d in self.disps if tuple(d.shape[-2:]) != (self.H, self.W))
@@ -190,7 +190,7 @@ class FusedPlan:
     FWD_STAGES = ("fwd_unused0", "vsl_forward_kernel", "fwd_unused1", "finish")
     BWD_STAGES = ("grad_init", "vsl_backward_kernel", "upsample_gather", "pose_finish")
     FUSED_FWD_STAGES = ("grad_raw_zero", "vsl_fused_kernel", "fwd_unused1", "finish")
-    FUSED_BWD_STAGES = ("bwd_unused0", "vsl_grad_finish_kernel", "bwd_unused1", "pose_finish")
+    FUSED_BWD_STAGES = ("bwd_unused0", "vsl_grad_finish_kernel", "bwd_unused1", "bwd_unused2")
 
     def enable_trace(self):
         """Asks the library to record a CUDA event before/after every stage of forward and
