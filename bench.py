@@ -271,7 +271,7 @@ def main():
     sets = probe + make_sets(wl, n_sets - 1, 1000 * rank + 1, device, is_multi)
     plans = [build_plan(t, wl, device, is_multi, args.deterministic, fused=False if args.no_fused else None) for t in sets]
     fused = plans[0].fused
-    cfg_desc["kernels"] = ("single-launch fused step (vsl_fused_kernel) + finish + gradient finish + pose finish (tail kernels launched programmatically)" if fused
+    cfg_desc["kernels"] = ("single-launch fused step (vsl_fused_kernel, TMA-staged tiles) + finish + gradient finish (tails launched programmatically)" if fused
                            else "vsl_forward_kernel + finish + vsl_backward_kernel + pose finish")
     for p in plans:
         p.capture()
@@ -338,7 +338,7 @@ def main():
             dom_bytes = bwd_b if dom == "vsl_backward_kernel" else fwd_b
         achieved = dom_bytes / (stage_ms[dom] * 1e-3) / 1e9
         traffic = None            # DRAM bytes of one launch of that kernel from the committed ncu capture (same workload only)
-        tpath = os.path.join(ROOT, "profiles", "r1i_traffic.json" if fused else "r1f_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r1j_traffic.json" if fused else "r1f_traffic.json")
         if os.path.exists(tpath) and args.workload == "kitti" and not is_multi and not args.deterministic:
             traffic = json.load(open(tpath)).get(dom)
         roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
