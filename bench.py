@@ -256,8 +256,11 @@ def main():
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
+        # NCCL's version banner / warnings off stdout (rank 0 prints ONE JSON line): NCCL honours NCCL_DEBUG_FILE only above
+        # the VERSION level, which is what this image sets
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner out of stdout: rank 0 prints ONE JSON line
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         torch.distributed.init_process_group("nccl", device_id=device)
     from ppea_depth_b200 import _cabi
     from ppea_depth_b200.synth import algorithmic_bytes
