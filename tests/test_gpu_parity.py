@@ -184,3 +184,39 @@ def test_full_size_properties(name, det):
     if det:
         for k in grads:
             assert torch.equal(grads[k], g2[k]), k
+
+
+def test_unaligned_frames_take_the_non_tma_path():
+    """Colour frames whose base address is not 16-byte aligned cannot be described by a TMA tensor map: the fused kernel
+    stages them with its reflecting loop instead.  Same per-pixel maps and loss, bit for bit."""
+    from gpu_helpers import FeedNoise
+    from ppea_depth_b200.loss import ViewSynthesisLoss
+    cfg = SynthConfig(batch=2, height=64, width=96, num_scales=4, seed=47)
+    inputs, outputs = make_batch(cfg)
+    noise = make_noise(cfg, 4)
+    opt = O.default_opt(sclm=3, height=64, width=96, batch_size=2)
+
+    def run(shift):
+        ins, outs = O.clone_batch(inputs, outputs, device="cuda")
+        if shift:
+            for k in list(ins):
+                if k[0] == "color":
+                    t = ins[k]
+                    buf = torch.empty(t.numel() + 4, device="cuda", dtype=torch.float32)
+                    view = buf[1:1 + t.numel()].view(t.shape)          # contiguous, base address = 4 mod 16
+                    view.copy_(t)
+                    assert view.data_ptr() % 16 == 4
+                    ins[k] = view
+        mod = ViewSynthesisLoss(opt, keep_maps=True)
+        with FeedNoise(noise):
+            mod.generate_images_pred(ins, outs, False)
+            losses, _ = mod.compute_losses(ins, outs, False)
+        losses["loss"].backward()
+        return float(losses["loss"]), outs[("disp", 0)].grad.cpu(), [outs[("depth", 0, s)].cpu() for s in range(4)]
+
+    la, ga, da = run(False)
+    lb, gb, db = run(True)
+    assert la == lb
+    assert torch.equal(ga, gb)
+    for x, y in zip(da, db):
+        assert torch.equal(x, y)
