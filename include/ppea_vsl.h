@@ -231,6 +231,19 @@ int ppea_smooth_backward(const float* disp, const float* img, const float* grad_
  * `count` floats out, same order. */
 int ppea_images_u8_to_f32(const uint8_t* src, float* dst, size_t count, void* stream);
 
+/* ---- plane-sweep cost volume of the multi-frame encoder -------------------
+ * `match_features`, networks/replk_matching_adapter.py:261-340 (= replk_matching.py:127-206, resnet_encoder.py:164-246):
+ * the lookup features (B,F,C,h,w) are warped into the current frame at every hypothesised depth `depth_bins[d]`
+ * (BackprojectDepth + Project3D + F.grid_sample(padding_mode="zeros", align_corners=True)); cost_volume (B,D,h,w) is the
+ * channel-mean L1 difference to current_feats (B,C,h,w), masked at the borders, averaged over the lookup frames whose pose
+ * is not all-zero; missing_mask (B,D,h,w) flags the bins that never landed inside the image, which get the per-pixel
+ * maximum when set_missing_to_max.  K / inv_K are the (B,4,4) intrinsics of the matching scale, relative_poses (B,F,4,4).
+ * One launch, no workspace, no gradients (the reference runs it under no_grad).  num_bins <= 128. */
+int ppea_match_features(const float* current_feats, const float* lookup_feats, const float* relative_poses, const float* K,
+                        const float* inv_K, const float* depth_bins, float* cost_volume, float* missing_mask, int batch,
+                        int num_lookup, int channels, int height, int width, int num_bins, int set_missing_to_max, float eps,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

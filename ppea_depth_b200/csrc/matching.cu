@@ -1,0 +1,228 @@
+// matching.cu -- plane-sweep cost volume of the multi-frame encoder.
+//
+// Reference: `match_features`, networks/replk_matching_adapter.py:261-340 (the same code sits in
+// replk_matching.py:127-206 and resnet_encoder.py:164-246).  Per batch item the reference repeats the lookup
+// features num_depth_bins times, back-projects / projects a (D,h,w) grid through BackprojectDepth + Project3D,
+// calls F.grid_sample(padding_mode="zeros", align_corners=True), takes the channel-mean L1 difference to the
+// current features, masks it at the borders, averages over the lookup frames and fills the depth bins that never
+// landed inside the image with the per-pixel maximum -- ~15 launches and (D,C,h,w) temporaries per item, in a
+// Python loop over the batch.
+//
+// Here: ONE launch.  A thread owns one pixel of one batch item and walks the depth bins DB at a time: the
+// projection of the DB hypotheses is set up once (corner offsets + bilinear weights in registers), then the
+// channel loop reads the current feature once per channel and the four corners of every hypothesis (lanes are
+// adjacent pixels, so every load of the warp is a contiguous run of one channel plane).  The per-pixel maximum
+// over the bins and the missing flags stay in registers, so the "set missing to max" fix-up is a second sweep
+// over the thread's own outputs.  Nothing but the cost volume and its mask is written.
+//
+// Arithmetic follows the reference op by op where a rounding can flip a decision (the border masks compare
+// x_vals / y_vals with 2 and size-2): P = K @ T, ray = inv_K[:3,:3] @ (x,y,1), X = depth * ray (layers.py:164-167),
+// cam = P @ (X,1), pix = cam.xy / (cam.z + eps), normalised to [-1,1] (layers.py:187-198), x_vals = (g/2 + .5)(w-1)
+// (:302-304), sampling position ((g+1)/2)(w-1) (ATen grid_sampler_unnormalize, align_corners=True).
+#include "vsl_common.cuh"
+
+namespace ppea {
+
+constexpr int kMatchThreads = 128;
+constexpr int kMatchBins = 4;        // depth hypotheses in flight per thread
+constexpr int kMatchMaxBins = 128;   // missing flags live in four 32-bit words
+
+struct MatchArgs {
+  const float* cur;     // (B,C,h,w)
+  const float* look;    // (B,F,C,h,w)
+  const float* poses;   // (B,F,4,4)
+  const float* K;       // (B,4,4) of the matching scale
+  const float* invK;    // (B,4,4)
+  const float* bins;    // (D)
+  float* cost;          // (B,D,h,w)
+  float* missing;       // (B,D,h,w)
+  int B, F, C, h, w, D;
+  int set_missing_to_max;
+  float eps;
+};
+
+struct MatchTap {
+  int off;                     // element offset of the north-west corner inside a channel plane
+  float wnw, wne, wsw, wse;    // bilinear weights with the zero padding folded in (0 for corners outside the image)
+  float edge;                  // border mask of this hypothesis (:302-312)
+};
+
+__device__ __forceinline__ MatchTap match_setup(const float* __restrict__ P, const float* __restrict__ ray, float depth, int h, int w,
+                                                float eps, float cur_mask) {
+  // BackprojectDepth: X = depth * ray; Project3D: cam = P @ (X, 1)
+  const float X = mul_rn(depth, ray[0]), Y = mul_rn(depth, ray[1]), Z = mul_rn(depth, ray[2]);
+  float c[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    float acc = mul_rn(P[i * 4 + 0], X);
+    acc = fma_rn(P[i * 4 + 1], Y, acc);
+    acc = fma_rn(P[i * 4 + 2], Z, acc);
+    acc = fma_rn(P[i * 4 + 3], 1.f, acc);
+    c[i] = acc;
+  }
+  const float z = add_rn(c[2], eps);
+  const float gx = mul_rn(sub_rn(div_rn(div_rn(c[0], z), (float)(w - 1)), 0.5f), 2.f);
+  const float gy = mul_rn(sub_rn(div_rn(div_rn(c[1], z), (float)(h - 1)), 0.5f), 2.f);
+  // border mask on the pixel coordinates the reference derives from the grid
+  const float xv = mul_rn(add_rn(div_rn(gx, 2.f), 0.5f), (float)(w - 1));
+  const float yv = mul_rn(add_rn(div_rn(gy, 2.f), 0.5f), (float)(h - 1));
+  MatchTap t;
+  t.edge = (xv >= 2.f && xv <= (float)(w - 2) && yv >= 2.f && yv <= (float)(h - 2)) ? cur_mask : 0.f;
+  // grid_sample, zeros padding, align_corners=True
+  const float ix = mul_rn(div_rn(add_rn(gx, 1.f), 2.f), (float)(w - 1));
+  const float iy = mul_rn(div_rn(add_rn(gy, 1.f), 2.f), (float)(h - 1));
+  // (NaN / far-out coordinates: every corner falls outside, all weights 0)
+  const float fx = floorf(ix), fy = floorf(iy);
+  const bool finite = (ix > -2.f && ix < (float)(w + 1) && iy > -2.f && iy < (float)(h + 1));
+  const int x0 = finite ? (int)fx : -2, y0 = finite ? (int)fy : -2;
+  const float tx = ix - fx, ty = iy - fy;
+  const bool xin0 = x0 >= 0 && x0 < w, xin1 = x0 + 1 >= 0 && x0 + 1 < w;
+  const bool yin0 = y0 >= 0 && y0 < h, yin1 = y0 + 1 >= 0 && y0 + 1 < h;
+  t.wnw = (xin0 && yin0) ? (1.f - tx) * (1.f - ty) : 0.f;
+  t.wne = (xin1 && yin0) ? tx * (1.f - ty) : 0.f;
+  t.wsw = (xin0 && yin1) ? (1.f - tx) * ty : 0.f;
+  t.wse = (xin1 && yin1) ? tx * ty : 0.f;
+  // clamp the base so that the four addresses o, o+1, o+w, o+w+1 stay inside the plane (their weights are 0 where clamped)
+  const int xc = min(max(x0, 0), w - 2), yc = min(max(y0, 0), h - 2);
+  t.off = yc * w + xc;
+  if (xc != x0) {          // the in-image corner moved: re-route its weight
+    // x0 == -1: only the east corners are inside -> they sit at column 0 == the clamped west column
+    // x0 == w-1: only the west corners are inside -> they sit at column w-1 == the clamped east column
+    if (x0 == -1) { t.wnw = t.wne; t.wsw = t.wse; t.wne = 0.f; t.wse = 0.f; }
+    else if (x0 == w - 1) { t.wne = t.wnw; t.wse = t.wsw; t.wnw = 0.f; t.wsw = 0.f; }
+  }
+  if (yc != y0) {
+    if (y0 == -1) { t.wnw = t.wsw; t.wne = t.wse; t.wsw = 0.f; t.wse = 0.f; }
+    else if (y0 == h - 1) { t.wsw = t.wnw; t.wse = t.wne; t.wnw = 0.f; t.wne = 0.f; }
+  }
+  return t;
+}
+
+__global__ void __launch_bounds__(kMatchThreads) match_features_kernel(const MatchArgs a) {
+  __shared__ float sP[12];         // (K @ T)[:3,:] of the current lookup frame
+  __shared__ float siK[9];
+  __shared__ int s_skip;
+  const int b = blockIdx.y;
+  const int h = a.h, w = a.w, D = a.D, C = a.C;
+  const unsigned plane = (unsigned)(h * w);
+  const unsigned pix = blockIdx.x * kMatchThreads + threadIdx.x;
+  const bool live = pix < plane;
+  const int y = live ? (int)(pix / (unsigned)w) : 0, x = live ? (int)(pix - (unsigned)y * (unsigned)w) : 0;
+  if (threadIdx.x < 9) siK[threadIdx.x] = a.invK[b * 16 + (threadIdx.x / 3) * 4 + threadIdx.x % 3];
+  __syncthreads();
+  float ray[3];
+  pixel_ray(siK, (float)x, (float)y, ray);
+  const float cur_mask = (y >= 2 && y < h - 2 && x >= 2 && x < w - 2) ? 1.f : 0.f;      // current_mask[:, 2:-2, 2:-2] = 1 (:310-312)
+  const float* cur_b = a.cur + (size_t)b * C * plane + pix;
+  float* cost_b = a.cost + (size_t)b * D * plane + pix;
+  float* miss_b = a.missing + (size_t)b * D * plane + pix;
+  float vmax = -INFINITY;
+  unsigned m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;      // missing flags of the (<= 128) bins
+  const float fC = (float)C;
+
+  for (int d0 = 0; d0 < D; d0 += kMatchBins) {
+    float cost[kMatchBins], cnt[kMatchBins];
+#pragma unroll
+    for (int j = 0; j < kMatchBins; ++j) cost[j] = cnt[j] = 0.f;
+    for (int f = 0; f < a.F; ++f) {
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const float* T = a.poses + ((size_t)b * a.F + f) * 16;
+        float s = 0.f;
+        for (int e = 0; e < 16; ++e) s += T[e];
+        s_skip = (s == 0.f) ? 1 : 0;                      // "missing lookup frame" (:289-291)
+        compose_P(a.K + b * 16, T, sP);
+      }
+      __syncthreads();
+      if (s_skip) continue;
+      MatchTap tap[kMatchBins];
+      float acc[kMatchBins];
+#pragma unroll
+      for (int j = 0; j < kMatchBins; ++j) {
+        const int d = min(d0 + j, D - 1);
+        tap[j] = match_setup(sP, ray, __ldg(a.bins + d), h, w, a.eps, cur_mask);
+        acc[j] = 0.f;
+      }
+      if (live) {
+        const float* look_f = a.look + ((size_t)b * a.F + f) * C * plane;
+#pragma unroll 2
+        for (int c = 0; c < C; ++c) {
+          const float cv = __ldg(cur_b + (size_t)c * plane);
+          const float* lp = look_f + (size_t)c * plane;
+#pragma unroll
+          for (int j = 0; j < kMatchBins; ++j) {
+            const float* q = lp + tap[j].off;
+            const float v = fmaf(tap[j].wse, __ldg(q + w + 1), fmaf(tap[j].wsw, __ldg(q + w), fmaf(tap[j].wne, __ldg(q + 1), tap[j].wnw * __ldg(q))));
+            acc[j] += fabsf(v - cv);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kMatchBins; ++j) {
+        const float diff = mul_rn(div_rn(acc[j], fC), tap[j].edge);        // .mean(1) * edge_mask (:314-315)
+        cost[j] += diff;
+        cnt[j] += diff > 0.f ? 1.f : 0.f;
+      }
+    }
+    if (live) {
+#pragma unroll
+      for (int j = 0; j < kMatchBins; ++j) {
+        const int d = d0 + j;
+        if (d < D) {
+          const float v = cost[j] / (cnt[j] + 1e-7f);             // average over lookup images (:321)
+          const bool m = v == 0.f;
+          if (m) {
+            const unsigned bit = 1u << (d & 31);
+            const int ws = d >> 5;
+            m0 |= ws == 0 ? bit : 0u;
+            m1 |= ws == 1 ? bit : 0u;
+            m2 |= ws == 2 ? bit : 0u;
+            m3 |= ws == 3 ? bit : 0u;
+          }
+          vmax = fmaxf(vmax, v);
+          cost_b[(size_t)d * plane] = v;
+          miss_b[(size_t)d * plane] = m ? 1.f : 0.f;
+        }
+      }
+    }
+  }
+  if (live && a.set_missing_to_max) {                             // (:325-328)
+    for (int d = 0; d < D; ++d) {
+      const int ws = d >> 5;
+      const unsigned word = ws == 0 ? m0 : (ws == 1 ? m1 : (ws == 2 ? m2 : m3));
+      if ((word >> (d & 31)) & 1u) cost_b[(size_t)d * plane] = vmax;
+    }
+  }
+}
+
+extern "C" int ppea_match_features(const float* current_feats, const float* lookup_feats, const float* relative_poses, const float* K,
+                                   const float* inv_K, const float* depth_bins, float* cost_volume, float* missing_mask, int batch,
+                                   int num_lookup, int channels, int height, int width, int num_bins, int set_missing_to_max, float eps,
+                                   void* stream) {
+  if (!current_feats || !lookup_feats || !relative_poses || !K || !inv_K || !depth_bins || !cost_volume || !missing_mask) return PPEA_E_NULL;
+  if (batch <= 0 || batch > 65535 || num_lookup < 0 || channels <= 0 || height < 2 || width < 2 || num_bins <= 0 || num_bins > kMatchMaxBins ||
+      (long long)height * width >= (1ll << 30))
+    return PPEA_E_SHAPE;
+  MatchArgs a;
+  a.cur = current_feats;
+  a.look = lookup_feats;
+  a.poses = relative_poses;
+  a.K = K;
+  a.invK = inv_K;
+  a.bins = depth_bins;
+  a.cost = cost_volume;
+  a.missing = missing_mask;
+  a.B = batch;
+  a.F = num_lookup;
+  a.C = channels;
+  a.h = height;
+  a.w = width;
+  a.D = num_bins;
+  a.set_missing_to_max = set_missing_to_max;
+  a.eps = eps;
+  const dim3 grid((unsigned)ceil_div(height * width, kMatchThreads), (unsigned)batch);
+  match_features_kernel<<<grid, kMatchThreads, 0, (cudaStream_t)stream>>>(a);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace ppea

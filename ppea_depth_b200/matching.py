@@ -1,0 +1,55 @@
+"""Plane-sweep cost volume of the multi-frame encoder.
+
+Drop-in for `match_features` of the reference's matching encoders
+(/root/reference/ppeadepth/networks/replk_matching_adapter.py:261-340, replk_matching.py:127-206,
+resnet_encoder.py:164-246): same arguments, same two outputs, one CUDA launch instead of a Python loop over the
+batch with ~15 launches and (D,C,h,w) temporaries per item.  `install_matching(EncoderClass)` rebinds the method; the
+encoder keeps providing `num_depth_bins`, `warp_depths`, `set_missing_to_max` exactly as the reference builds them
+(`compute_depth_bins`, :134-155).  There is no CPU path: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _cabi as C
+
+
+def _f32c(t, name):
+    if not t.is_cuda:
+        raise RuntimeError("ppea_depth_b200 has no CPU path: %s must be a CUDA tensor" % name)
+    return t.detach().contiguous().float()
+
+
+def match_features(current_feats, lookup_feats, relative_poses, K, invK, depth_bins, set_missing_to_max=True, eps=1e-7):
+    """current_feats (B,C,h,w), lookup_feats (B,F,C,h,w), relative_poses (B,F,4,4), K / invK (B,4,4) of the matching scale,
+    depth_bins (D,) hypothesised depths -> (cost_volume (B,D,h,w), missing_mask (B,D,h,w)), both float32."""
+    cur = _f32c(current_feats, "current_feats")
+    look = _f32c(lookup_feats, "lookup_feats")
+    poses = _f32c(relative_poses, "relative_poses")
+    K, invK = _f32c(K, "K"), _f32c(invK, "invK")
+    B, Cn, h, w = cur.shape
+    F = look.shape[1]
+    if look.shape != (B, F, Cn, h, w) or poses.shape != (B, F, 4, 4) or K.shape != (B, 4, 4) or invK.shape != (B, 4, 4):
+        raise ValueError("match_features: inconsistent shapes")
+    bins = torch.as_tensor(depth_bins, dtype=torch.float32).reshape(-1).to(cur.device).contiguous()
+    D = bins.numel()
+    with torch.cuda.device(cur.device):
+        cost = torch.empty(B, D, h, w, device=cur.device, dtype=torch.float32)
+        missing = torch.empty(B, D, h, w, device=cur.device, dtype=torch.float32)
+        C.check(C.lib().ppea_match_features(cur.data_ptr(), look.data_ptr(), poses.data_ptr(), K.data_ptr(), invK.data_ptr(),
+                                            bins.data_ptr(), cost.data_ptr(), missing.data_ptr(), B, F, Cn, h, w, D,
+                                            1 if set_missing_to_max else 0, float(eps), torch.cuda.current_stream().cuda_stream))
+    return cost, missing
+
+
+def match_features_method(self, current_feats, lookup_feats, relative_poses, K, invK):
+    """Bound-method form with the reference's signature; reads `self.warp_depths` ((D,1,h,w): one depth per bin) and
+    `self.set_missing_to_max` like the reference method."""
+    bins = self.warp_depths.reshape(self.warp_depths.shape[0], -1)[:, 0]
+    return match_features(current_feats, lookup_feats, relative_poses, K, invK, bins, bool(self.set_missing_to_max))
+
+
+def install_matching(encoder_cls):
+    """Rebinds `match_features` of a reference matching encoder class (RepLKMatchingAdapter, RepLKMatching, ResnetEncoderMatching)."""
+    encoder_cls.match_features = match_features_method
+    return encoder_cls

@@ -27,7 +27,8 @@ def pytest_collection_modifyitems(config, items):
 
 
 def golden_names():
-    return sorted(f[:-3] for f in os.listdir(GOLDEN_DIR) if f.endswith(".pt"))
+    # (the matching_*.pt fixtures belong to the cost-volume tests, tests/test_matching.py)
+    return sorted(f[:-3] for f in os.listdir(GOLDEN_DIR) if f.endswith(".pt") and not f.startswith("matching_"))
 
 
 def load_golden(name):
