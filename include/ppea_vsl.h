@@ -238,7 +238,7 @@ int ppea_images_u8_to_f32(const uint8_t* src, float* dst, size_t count, void* st
  * channel-mean L1 difference to current_feats (B,C,h,w), masked at the borders, averaged over the lookup frames whose pose
  * is not all-zero; missing_mask (B,D,h,w) flags the bins that never landed inside the image, which get the per-pixel
  * maximum when set_missing_to_max.  K / inv_K are the (B,4,4) intrinsics of the matching scale, relative_poses (B,F,4,4).
- * One launch, no workspace, no gradients (the reference runs it under no_grad).  num_bins <= 128. */
+ * One launch for the volume plus a small fix-up launch, no workspace, no gradients (the reference runs it under no_grad). */
 int ppea_match_features(const float* current_feats, const float* lookup_feats, const float* relative_poses, const float* K,
                         const float* inv_K, const float* depth_bins, float* cost_volume, float* missing_mask, int batch,
                         int num_lookup, int channels, int height, int width, int num_bins, int set_missing_to_max, float eps,

@@ -8,12 +8,13 @@
 // landed inside the image with the per-pixel maximum -- ~15 launches and (D,C,h,w) temporaries per item, in a
 // Python loop over the batch.
 //
-// Here: ONE launch.  A thread owns one pixel of one batch item and walks the depth bins DB at a time: the
-// projection of the DB hypotheses is set up once (corner offsets + bilinear weights in registers), then the
-// channel loop reads the current feature once per channel and the four corners of every hypothesis (lanes are
-// adjacent pixels, so every load of the warp is a contiguous run of one channel plane).  The per-pixel maximum
-// over the bins and the missing flags stay in registers, so the "set missing to max" fix-up is a second sweep
-// over the thread's own outputs.  Nothing but the cost volume and its mask is written.
+// Here: one launch for the volume (+ one small fix-up launch).  A thread owns one pixel of one batch item and a chunk of
+// kMatchChunk depth bins (grid.z: enough CTAs for whole waves on 148 SMs) and walks them kMatchBins at a time: the
+// projection of the hypotheses is set up once (corner offsets + bilinear weights in registers), then the channel loop
+// reads the current feature once per channel and the four corners of every hypothesis (lanes are adjacent pixels, so
+// every load of the warp is a contiguous run of one channel plane).  "Set missing to max" needs the per-pixel maximum
+// over ALL bins: a second, bandwidth-bound kernel sweeps the finished volume (missing <=> cost == 0).  Nothing but the
+// cost volume and its mask is written; there is no workspace.
 //
 // Arithmetic follows the reference op by op where a rounding can flip a decision (the border masks compare
 // x_vals / y_vals with 2 and size-2): P = K @ T, ray = inv_K[:3,:3] @ (x,y,1), X = depth * ray (layers.py:164-167),
@@ -25,7 +26,8 @@ namespace ppea {
 
 constexpr int kMatchThreads = 128;
 constexpr int kMatchBins = 4;        // depth hypotheses in flight per thread
-constexpr int kMatchMaxBins = 128;   // missing flags live in four 32-bit words
+constexpr int kMatchChunk = 32;     // depth bins per CTA (grid.z = ceil(D / kMatchChunk))
+constexpr int kMatchMaxBins = 4096;
 
 struct MatchArgs {
   const float* cur;     // (B,C,h,w)
@@ -116,11 +118,10 @@ __global__ void __launch_bounds__(kMatchThreads) match_features_kernel(const Mat
   const float* cur_b = a.cur + (size_t)b * C * plane + pix;
   float* cost_b = a.cost + (size_t)b * D * plane + pix;
   float* miss_b = a.missing + (size_t)b * D * plane + pix;
-  float vmax = -INFINITY;
-  unsigned m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;      // missing flags of the (<= 128) bins
   const float fC = (float)C;
+  const int d_lo = blockIdx.z * kMatchChunk, d_hi = min(D, d_lo + kMatchChunk);
 
-  for (int d0 = 0; d0 < D; d0 += kMatchBins) {
+  for (int d0 = d_lo; d0 < d_hi; d0 += kMatchBins) {
     float cost[kMatchBins], cnt[kMatchBins];
 #pragma unroll
     for (int j = 0; j < kMatchBins; ++j) cost[j] = cnt[j] = 0.f;
@@ -168,31 +169,32 @@ __global__ void __launch_bounds__(kMatchThreads) match_features_kernel(const Mat
 #pragma unroll
       for (int j = 0; j < kMatchBins; ++j) {
         const int d = d0 + j;
-        if (d < D) {
+        if (d < d_hi) {
           const float v = cost[j] / (cnt[j] + 1e-7f);             // average over lookup images (:321)
-          const bool m = v == 0.f;
-          if (m) {
-            const unsigned bit = 1u << (d & 31);
-            const int ws = d >> 5;
-            m0 |= ws == 0 ? bit : 0u;
-            m1 |= ws == 1 ? bit : 0u;
-            m2 |= ws == 2 ? bit : 0u;
-            m3 |= ws == 3 ? bit : 0u;
-          }
-          vmax = fmaxf(vmax, v);
           cost_b[(size_t)d * plane] = v;
-          miss_b[(size_t)d * plane] = m ? 1.f : 0.f;
+          miss_b[(size_t)d * plane] = (v == 0.f) ? 1.f : 0.f;     // missing_val_mask (:324)
         }
       }
     }
   }
-  if (live && a.set_missing_to_max) {                             // (:325-328)
-    for (int d = 0; d < D; ++d) {
-      const int ws = d >> 5;
-      const unsigned word = ws == 0 ? m0 : (ws == 1 ? m1 : (ws == 2 ? m2 : m3));
-      if ((word >> (d & 31)) & 1u) cost_b[(size_t)d * plane] = vmax;
-    }
+}
+
+// cost = cost * (1 - missing) + max_d(cost) * missing   (:325-328): one thread per pixel, two sweeps over its bins
+__global__ void __launch_bounds__(256) match_fill_missing_kernel(float* __restrict__ cost, int D, unsigned plane) {
+  const unsigned pix = blockIdx.x * 256 + threadIdx.x;
+  if (pix >= plane) return;
+  float* c = cost + (size_t)blockIdx.y * D * plane + pix;
+  float vmax = -INFINITY;
+  bool any = false;
+#pragma unroll 8
+  for (int d = 0; d < D; ++d) {
+    const float v = c[(size_t)d * plane];
+    vmax = fmaxf(vmax, v);
+    any = any || v == 0.f;
   }
+  if (!any || vmax == 0.f) return;
+  for (int d = 0; d < D; ++d)
+    if (c[(size_t)d * plane] == 0.f) c[(size_t)d * plane] = vmax;
 }
 
 extern "C" int ppea_match_features(const float* current_feats, const float* lookup_feats, const float* relative_poses, const float* K,
@@ -200,7 +202,7 @@ extern "C" int ppea_match_features(const float* current_feats, const float* look
                                    int num_lookup, int channels, int height, int width, int num_bins, int set_missing_to_max, float eps,
                                    void* stream) {
   if (!current_feats || !lookup_feats || !relative_poses || !K || !inv_K || !depth_bins || !cost_volume || !missing_mask) return PPEA_E_NULL;
-  if (batch <= 0 || batch > 65535 || num_lookup < 0 || channels <= 0 || height < 2 || width < 2 || num_bins <= 0 || num_bins > kMatchMaxBins ||
+  if (batch <= 0 || batch > 65535 || num_lookup < 0 || channels <= 0 || height < 2 || width < 2 || num_bins <= 0 || num_bins > kMatchMaxBins || ceil_div(num_bins, kMatchChunk) > 65535 ||
       (long long)height * width >= (1ll << 30))
     return PPEA_E_SHAPE;
   MatchArgs a;
@@ -220,9 +222,16 @@ extern "C" int ppea_match_features(const float* current_feats, const float* look
   a.D = num_bins;
   a.set_missing_to_max = set_missing_to_max;
   a.eps = eps;
-  const dim3 grid((unsigned)ceil_div(height * width, kMatchThreads), (unsigned)batch);
+  const dim3 grid((unsigned)ceil_div(height * width, kMatchThreads), (unsigned)batch, (unsigned)ceil_div(num_bins, kMatchChunk));
   match_features_kernel<<<grid, kMatchThreads, 0, (cudaStream_t)stream>>>(a);
-  return (int)cudaGetLastError();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  if (set_missing_to_max) {
+    const dim3 g2((unsigned)ceil_div(height * width, 256), (unsigned)batch);
+    match_fill_missing_kernel<<<g2, 256, 0, (cudaStream_t)stream>>>(cost_volume, num_bins, (unsigned)(height * width));
+    e = cudaGetLastError();
+  }
+  return (int)e;
 }
 
 }  // namespace ppea
