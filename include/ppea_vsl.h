@@ -244,6 +244,14 @@ int ppea_match_features(const float* current_feats, const float* lookup_feats, c
                         int num_lookup, int channels, int height, int width, int num_bins, int set_missing_to_max, float eps,
                         void* stream);
 
+/* Tail of the matching block (replk_matching_adapter.py:380-387 compute_confidence_mask, :439-453 in forward), one sweep:
+ * confidence (B,h,w) = [#(cost * (1 - missing) > 0 over the bins) == threshold] (missing may be NULL: cost is taken as is);
+ * (mins, argmin) (B,h,w) = torch.min over the bins of the volume with exact zeros replaced by 100 (argmin int64, first
+ * minimum); with mask_volume the volume is multiplied by the confidence in place.  Any output pointer may be NULL. */
+int ppea_match_tail(float* cost_volume, const float* missing_mask_or_null, float* confidence_or_null, float* mins_or_null,
+                    long long* argmin_or_null, int batch, int num_bins, int height, int width, int threshold,
+                    int mask_volume, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

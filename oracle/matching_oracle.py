@@ -68,6 +68,19 @@ def match_features(current_feats, lookup_feats, relative_poses, K, invK, bins, s
     return torch.stack(vols, 0), torch.stack(masks, 0)
 
 
+def cost_volume_tail(cost_volume, missing_mask, num_bins_threshold=None, mask_volume=True):
+    """replk_matching_adapter.py:380-387 (compute_confidence_mask) and :439-453 (forward): confidence mask, min / argmin of the
+    volume with its zeros set to 100, volume masked by the confidence.  Returns (confidence, mins, argmin, masked volume)."""
+    D = cost_volume.shape[1]
+    thr = D if num_bins_threshold is None else num_bins_threshold
+    confidence = (((cost_volume * (1 - missing_mask)) > 0).sum(1) == thr).float()            # :380-387, :439-440
+    viz = cost_volume.clone()
+    viz[viz == 0] = 100                                                                      # :443-444
+    mins, argmin = torch.min(viz, 1)                                                         # :445
+    out = cost_volume * confidence.unsqueeze(1) if mask_volume else cost_volume.clone()      # :449
+    return confidence, mins, argmin, out
+
+
 def run_reference_match_features(current_feats, lookup_feats, relative_poses, K, invK, bins, set_missing_to_max=True):
     """The reference's own `RepLKMatchingAdapter.match_features`, unbound, on a stand-in self."""
     from . import ref_import as R

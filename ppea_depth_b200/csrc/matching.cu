@@ -197,6 +197,52 @@ __global__ void __launch_bounds__(256) match_fill_missing_kernel(float* __restri
     if (c[(size_t)d * plane] == 0.f) c[(size_t)d * plane] = vmax;
 }
 
+// Tail of the encoder's matching block (replk_matching_adapter.py:380-387, :439-453), one sweep per pixel over its bins:
+//   confidence = [ #(cost * (1 - missing) > 0) == threshold ]                       compute_confidence_mask
+//   (mins, argmin) = min_d viz,  viz = cost with exact zeros replaced by 100          (first minimum, like torch.min)
+//   cost *= confidence                                                                (optional, in place)
+__global__ void __launch_bounds__(256) match_tail_kernel(float* __restrict__ cost, const float* __restrict__ missing,
+                                                         float* __restrict__ confidence, float* __restrict__ mins,
+                                                         long long* __restrict__ argmin, int D, unsigned plane, int threshold,
+                                                         int mask_volume) {
+  const unsigned pix = blockIdx.x * 256 + threadIdx.x;
+  if (pix >= plane) return;
+  const size_t base = (size_t)blockIdx.y * D * plane + pix;
+  float* c = cost + base;
+  const float* m = missing ? missing + base : nullptr;
+  int count = 0, best = 0;
+  float vmin = INFINITY;
+#pragma unroll 4
+  for (int d = 0; d < D; ++d) {
+    const float v = c[(size_t)d * plane];
+    const float keep = m ? mul_rn(v, sub_rn(1.f, __ldg(m + (size_t)d * plane))) : v;
+    count += keep > 0.f ? 1 : 0;
+    const float viz = (v == 0.f) ? 100.f : v;
+    if (viz < vmin) {
+      vmin = viz;
+      best = d;
+    }
+  }
+  const float conf = (count == threshold) ? 1.f : 0.f;
+  const size_t o = (size_t)blockIdx.y * plane + pix;
+  if (confidence) confidence[o] = conf;
+  if (mins) mins[o] = vmin;
+  if (argmin) argmin[o] = best;
+  if (mask_volume && conf == 0.f)
+    for (int d = 0; d < D; ++d) c[(size_t)d * plane] = mul_rn(c[(size_t)d * plane], 0.f);
+}
+
+extern "C" int ppea_match_tail(float* cost_volume, const float* missing_mask_or_null, float* confidence_or_null, float* mins_or_null,
+                               long long* argmin_or_null, int batch, int num_bins, int height, int width, int threshold,
+                               int mask_volume, void* stream) {
+  if (!cost_volume) return PPEA_E_NULL;
+  if (batch <= 0 || batch > 65535 || num_bins <= 0 || height <= 0 || width <= 0 || (long long)height * width >= (1ll << 30)) return PPEA_E_SHAPE;
+  const dim3 grid((unsigned)ceil_div(height * width, 256), (unsigned)batch);
+  match_tail_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(cost_volume, missing_mask_or_null, confidence_or_null, mins_or_null, argmin_or_null,
+                                                         num_bins, (unsigned)(height * width), threshold, mask_volume);
+  return (int)cudaGetLastError();
+}
+
 extern "C" int ppea_match_features(const float* current_feats, const float* lookup_feats, const float* relative_poses, const float* K,
                                    const float* inv_K, const float* depth_bins, float* cost_volume, float* missing_mask, int batch,
                                    int num_lookup, int channels, int height, int width, int num_bins, int set_missing_to_max, float eps,

@@ -42,6 +42,38 @@ def match_features(current_feats, lookup_feats, relative_poses, K, invK, depth_b
     return cost, missing
 
 
+def cost_volume_tail(cost_volume, missing_mask=None, num_bins_threshold=None, mask_volume=True):
+    """The rest of the reference's matching block in one sweep (replk_matching_adapter.py:380-387, :439-453):
+    confidence_mask = compute_confidence_mask(cost_volume * (1 - missing_mask)); mins, argmin = torch.min over the bins of
+    the volume with its zeros set to 100; cost_volume *= confidence_mask (in place, when `mask_volume`).
+    Returns (confidence_mask (B,h,w), mins (B,h,w), argmin (B,h,w) int64)."""
+    if not cost_volume.is_cuda or cost_volume.dtype != torch.float32 or not cost_volume.is_contiguous():
+        raise RuntimeError("cost_volume_tail: contiguous float32 CUDA volume expected (there is no CPU path)")
+    B, D, h, w = cost_volume.shape
+    miss = _f32c(missing_mask, "missing_mask") if missing_mask is not None else None
+    thr = D if num_bins_threshold is None else int(num_bins_threshold)
+    with torch.cuda.device(cost_volume.device):
+        conf = torch.empty(B, h, w, device=cost_volume.device, dtype=torch.float32)
+        mins = torch.empty(B, h, w, device=cost_volume.device, dtype=torch.float32)
+        argmin = torch.empty(B, h, w, device=cost_volume.device, dtype=torch.int64)
+        C.check(C.lib().ppea_match_tail(cost_volume.data_ptr(), miss.data_ptr() if miss is not None else None, conf.data_ptr(),
+                                        mins.data_ptr(), argmin.data_ptr(), B, D, h, w, thr, 1 if mask_volume else 0,
+                                        torch.cuda.current_stream().cuda_stream))
+    return conf, mins, argmin
+
+
+def compute_confidence_mask_method(self, cost_volume, num_bins_threshold=None):
+    """Bound-method form of compute_confidence_mask (replk_matching_adapter.py:380-387)."""
+    vol = _f32c(cost_volume, "cost_volume")
+    thr = self.num_depth_bins if num_bins_threshold is None else num_bins_threshold
+    B, D, h, w = vol.shape
+    with torch.cuda.device(vol.device):
+        conf = torch.empty(B, h, w, device=vol.device, dtype=torch.float32)
+        C.check(C.lib().ppea_match_tail(vol.data_ptr(), None, conf.data_ptr(), None, None, B, D, h, w, int(thr), 0,
+                                        torch.cuda.current_stream().cuda_stream))
+    return conf
+
+
 def match_features_method(self, current_feats, lookup_feats, relative_poses, K, invK):
     """Bound-method form with the reference's signature; reads `self.warp_depths` ((D,1,h,w): one depth per bin) and
     `self.set_missing_to_max` like the reference method."""
@@ -50,6 +82,7 @@ def match_features_method(self, current_feats, lookup_feats, relative_poses, K, 
 
 
 def install_matching(encoder_cls):
-    """Rebinds `match_features` of a reference matching encoder class (RepLKMatchingAdapter, RepLKMatching, ResnetEncoderMatching)."""
+    """Rebinds `match_features` and `compute_confidence_mask` of a reference matching encoder class (RepLKMatchingAdapter, RepLKMatching, ResnetEncoderMatching)."""
     encoder_cls.match_features = match_features_method
+    encoder_cls.compute_confidence_mask = compute_confidence_mask_method
     return encoder_cls

@@ -89,3 +89,35 @@ def test_install_matching_rebinds_the_method():
     assert torch.equal(missing.cpu(), want[1])
     with pytest.raises(RuntimeError):
         P.match_features(cur, look, poses, K, invK, bins)          # no CPU path
+
+
+def test_oracle_tail_on_fixture():
+    """CPU: the tail restatement is self-consistent on a reference-made volume (confidence <=> no missing bin)."""
+    fx = _load([p for p in GOLDEN if p.endswith("_max.pt")][0])
+    conf, mins, argmin, masked = M.cost_volume_tail(fx["cost"], fx["missing"])
+    assert torch.equal(conf, (fx["missing"].sum(1) == 0).float())
+    assert torch.equal(masked, fx["cost"] * conf.unsqueeze(1))
+    assert torch.equal(mins, torch.gather(torch.where(fx["cost"] == 0, torch.full_like(fx["cost"], 100.0), fx["cost"]), 1,
+                                          argmin.unsqueeze(1)).squeeze(1))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("stm", [True, False])
+def test_cuda_tail_matches_oracle(stm):
+    import ppea_depth_b200 as P
+    cur, look, poses, K, invK, bins = M.synthetic_case(B=2, Fr=1, C=16, h=40, w=72, D=24, seed=21, min_bin=2.0, max_bin=12.0)
+    cost, missing = M.match_features(cur, look, poses, K, invK, bins, stm)
+    want = M.cost_volume_tail(cost, missing)
+    vol = cost.cuda().clone()
+    conf, mins, argmin = P.cost_volume_tail(vol, missing.cuda())
+    assert torch.equal(conf.cpu(), want[0]) and 0.05 < float(want[0].mean()) < 0.95
+    assert torch.equal(mins.cpu(), want[1])
+    assert torch.equal(argmin.cpu(), want[2])
+    assert torch.equal(vol.cpu(), want[3])
+
+    class Enc:
+        num_depth_bins = 24
+
+    P.install_matching(Enc)
+    c2 = Enc().compute_confidence_mask((cost * (1 - missing)).cuda())
+    assert torch.equal(c2.cpu(), want[0])
