@@ -252,6 +252,14 @@ int ppea_match_tail(float* cost_volume, const float* missing_mask_or_null, float
                     long long* argmin_or_null, int batch, int num_bins, int height, int width, int threshold,
                     int mask_volume, void* stream);
 
+/* ---- pose-network output -> camera transform --------------------------------
+ * `transformation_from_parameters` (layers.py:26-42 = rot_from_axisangle :62-100 + get_translation_matrix :45-59 + one
+ * (B,4,4) matmul), one launch each way: axisangle (B,3), translation (B,3) -> T (B,4,4) row-major; the backward contracts
+ * the Jacobian (dual numbers over the same program) with grad_T.  norm() at the origin has derivative 0 as in PyTorch. */
+int ppea_pose_to_matrix_forward(const float* axisangle, const float* translation, int invert, float* T, int batch, void* stream);
+int ppea_pose_to_matrix_backward(const float* axisangle, const float* translation, int invert, const float* grad_T,
+                                 float* grad_axisangle, float* grad_translation, int batch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

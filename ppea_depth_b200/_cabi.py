@@ -17,7 +17,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.environ.get("PPEA_LIB") or os.path.join(PKG_DIR, "libppea_vsl.so")
 INCLUDE_DIR = os.path.join(os.path.dirname(PKG_DIR), "include")
-SOURCES = ("api.cu", "vsl_fwd.cu", "vsl_bwd.cu", "vsl_fused.cu", "smooth.cu", "ops.cu", "matching.cu")
+SOURCES = ("api.cu", "vsl_fwd.cu", "vsl_bwd.cu", "vsl_fused.cu", "smooth.cu", "ops.cu", "matching.cu", "pose.cu")
 HEADERS = ("vsl_common.cuh", "vsl_math.cuh", "vsl_gather.cuh", "smooth.cuh")
 
 ABI_VERSION = 5
@@ -115,6 +115,8 @@ SIGNATURES = {
     "ppea_smooth_forward": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "ppea_smooth_backward": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "ppea_images_u8_to_f32": (_I, [_P, _P, _SZ, _P]),
+    "ppea_pose_to_matrix_forward": (_I, [_P, _P, _I, _P, _I, _P]),
+    "ppea_pose_to_matrix_backward": (_I, [_P, _P, _I, _P, _P, _P, _I, _P]),
     "ppea_match_tail": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "ppea_match_features": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P]),
 }

@@ -1,0 +1,201 @@
+// pose.cu -- pose-network output -> 4x4 camera transform, forward and backward.
+//
+// Reference: `transformation_from_parameters` (layers.py:26-42) = rot_from_axisangle (:62-100) + get_translation_matrix
+// (:45-59) + one (B,4,4) matmul: ~30 tiny launches forward and ~60 in autograd's backward, on the critical path between the
+// pose network and the loss (the fused loss hands back dL/dT, this function carries it to the pose head).
+// Here: one launch each way, one thread per batch item.  The forward follows the reference op by op in fp32; the backward
+// evaluates the same program on dual numbers (value + 6 partials w.r.t. axis-angle and translation) and contracts the
+// Jacobian with dL/dT -- no hand-derived Rodrigues adjoint to get wrong.  norm() at the origin has derivative 0, as in
+// PyTorch's norm_backward.
+#include "vsl_common.cuh"
+
+namespace ppea {
+
+template <int N>
+struct Dual {
+  float v;
+  float d[N];
+};
+template <int N>
+__device__ __forceinline__ Dual<N> dconst(float c) {
+  Dual<N> r;
+  r.v = c;
+#pragma unroll
+  for (int i = 0; i < N; ++i) r.d[i] = 0.f;
+  return r;
+}
+template <int N>
+__device__ __forceinline__ Dual<N> dvar(float c, int k) {
+  Dual<N> r = dconst<N>(c);
+  r.d[k] = 1.f;
+  return r;
+}
+template <int N>
+__device__ __forceinline__ Dual<N> operator+(const Dual<N>& a, const Dual<N>& b) {
+  Dual<N> r;
+  r.v = add_rn(a.v, b.v);
+#pragma unroll
+  for (int i = 0; i < N; ++i) r.d[i] = a.d[i] + b.d[i];
+  return r;
+}
+template <int N>
+__device__ __forceinline__ Dual<N> operator-(const Dual<N>& a, const Dual<N>& b) {
+  Dual<N> r;
+  r.v = sub_rn(a.v, b.v);
+#pragma unroll
+  for (int i = 0; i < N; ++i) r.d[i] = a.d[i] - b.d[i];
+  return r;
+}
+template <int N>
+__device__ __forceinline__ Dual<N> operator*(const Dual<N>& a, const Dual<N>& b) {
+  Dual<N> r;
+  r.v = mul_rn(a.v, b.v);
+#pragma unroll
+  for (int i = 0; i < N; ++i) r.d[i] = a.d[i] * b.v + a.v * b.d[i];
+  return r;
+}
+template <int N>
+__device__ __forceinline__ Dual<N> operator/(const Dual<N>& a, const Dual<N>& b) {
+  Dual<N> r;
+  r.v = div_rn(a.v, b.v);
+  const float ib = 1.f / b.v;
+#pragma unroll
+  for (int i = 0; i < N; ++i) r.d[i] = (a.d[i] - r.v * b.d[i]) * ib;
+  return r;
+}
+template <int N>
+__device__ __forceinline__ Dual<N> dneg(const Dual<N>& a) {
+  Dual<N> r;
+  r.v = -a.v;
+#pragma unroll
+  for (int i = 0; i < N; ++i) r.d[i] = -a.d[i];
+  return r;
+}
+template <int N>
+__device__ __forceinline__ Dual<N> dsqrt(const Dual<N>& a) {
+  Dual<N> r;
+  r.v = sqrtf(a.v);
+  const float k = r.v > 0.f ? 0.5f / r.v : 0.f;        // norm_backward: zero (sub)gradient at the origin
+#pragma unroll
+  for (int i = 0; i < N; ++i) r.d[i] = k * a.d[i];
+  return r;
+}
+template <int N>
+__device__ __forceinline__ void dsincos(const Dual<N>& a, Dual<N>& s, Dual<N>& c) {
+  s.v = sinf(a.v);
+  c.v = cosf(a.v);
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    s.d[i] = c.v * a.d[i];
+    c.d[i] = -s.v * a.d[i];
+  }
+}
+
+// the reference program on a generic scalar type; M is row-major 4x4
+template <int N>
+__device__ __forceinline__ void pose_program(const Dual<N> (&aa)[3], const Dual<N> (&tr)[3], bool invert, Dual<N> (&M)[16]) {
+  using D = Dual<N>;
+  // rot_from_axisangle (layers.py:62-100)
+  const D angle = dsqrt(aa[0] * aa[0] + aa[1] * aa[1] + aa[2] * aa[2]);          // torch.norm(vec, 2, 2, True)
+  const D den = angle + dconst<N>(1e-7f);
+  const D x = aa[0] / den, y = aa[1] / den, z = aa[2] / den;
+  D sa, ca;
+  dsincos(angle, sa, ca);
+  const D C = dconst<N>(1.f) - ca;
+  const D xs = x * sa, ys = y * sa, zs = z * sa;
+  const D xC = x * C, yC = y * C, zC = z * C;
+  const D xyC = x * yC, yzC = y * zC, zxC = z * xC;
+  D R[9];
+  R[0] = x * xC + ca;
+  R[1] = xyC - zs;
+  R[2] = zxC + ys;
+  R[3] = xyC + zs;
+  R[4] = y * yC + ca;
+  R[5] = yzC - xs;
+  R[6] = zxC - ys;
+  R[7] = yzC + xs;
+  R[8] = z * zC + ca;
+  const D zero = dconst<N>(0.f), one = dconst<N>(1.f);
+  if (!invert) {
+    // M = T @ R (layers.py:40-41): rotation block of R, translation column t
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) M[i * 4 + j] = R[i * 3 + j];
+      M[i * 4 + 3] = tr[i];
+    }
+  } else {
+    // M = R^T @ T(-t) (layers.py:33-39): last column = R^T (-t), accumulated in matmul order
+    const D nt[3] = {dneg(tr[0]), dneg(tr[1]), dneg(tr[2])};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) M[i * 4 + j] = R[j * 3 + i];
+      M[i * 4 + 3] = (R[0 * 3 + i] * nt[0] + R[1 * 3 + i] * nt[1]) + R[2 * 3 + i] * nt[2];
+    }
+  }
+  M[12] = zero;
+  M[13] = zero;
+  M[14] = zero;
+  M[15] = one;
+}
+
+__global__ void pose_to_matrix_forward_kernel(const float* __restrict__ aa, const float* __restrict__ tr, int invert,
+                                              float* __restrict__ out, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  Dual<1> a[3], t[3], M[16];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    a[i] = dconst<1>(aa[b * 3 + i]);
+    t[i] = dconst<1>(tr[b * 3 + i]);
+  }
+  pose_program<1>(a, t, invert != 0, M);
+#pragma unroll
+  for (int e = 0; e < 16; ++e) out[b * 16 + e] = M[e].v;
+}
+
+__global__ void pose_to_matrix_backward_kernel(const float* __restrict__ aa, const float* __restrict__ tr, int invert,
+                                               const float* __restrict__ gT, float* __restrict__ g_aa, float* __restrict__ g_tr,
+                                               int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  Dual<6> a[3], t[3], M[16];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    a[i] = dvar<6>(aa[b * 3 + i], i);
+    t[i] = dvar<6>(tr[b * 3 + i], 3 + i);
+  }
+  pose_program<6>(a, t, invert != 0, M);
+  float g[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    const float w = gT[b * 16 + e];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) g[k] = fmaf(w, M[e].d[k], g[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    g_aa[b * 3 + k] = g[k];
+    g_tr[b * 3 + k] = g[3 + k];
+  }
+}
+
+extern "C" int ppea_pose_to_matrix_forward(const float* axisangle, const float* translation, int invert, float* T, int batch,
+                                           void* stream) {
+  if (!axisangle || !translation || !T) return PPEA_E_NULL;
+  if (batch <= 0) return PPEA_E_SHAPE;
+  pose_to_matrix_forward_kernel<<<ceil_div(batch, 64), 64, 0, (cudaStream_t)stream>>>(axisangle, translation, invert, T, batch);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int ppea_pose_to_matrix_backward(const float* axisangle, const float* translation, int invert, const float* grad_T,
+                                            float* grad_axisangle, float* grad_translation, int batch, void* stream) {
+  if (!axisangle || !translation || !grad_T || !grad_axisangle || !grad_translation) return PPEA_E_NULL;
+  if (batch <= 0) return PPEA_E_SHAPE;
+  pose_to_matrix_backward_kernel<<<ceil_div(batch, 64), 64, 0, (cudaStream_t)stream>>>(axisangle, translation, invert, grad_T,
+                                                                                      grad_axisangle, grad_translation, batch);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace ppea

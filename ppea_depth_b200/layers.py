@@ -6,8 +6,9 @@ Same names, constructor/forward signatures and return shapes as the reference
 `get_smooth_loss` :210-223, `SSIM` :226-257), so `trainer.py` and the
 cost-volume encoders bind to them unchanged.  The module classes and
 `get_smooth_loss` run hand-written sm_100a kernels through the C ABI
-(`include/ppea_vsl.h`); the pose -> matrix helpers are tiny (B,4,4) tensor
-algebra and stay PyTorch.  There is no CPU fallback: a CPU
+(`include/ppea_vsl.h`); `transformation_from_parameters` takes the fused pose
+kernels for CUDA tensors (csrc/pose.cu) and stays PyTorch tensor algebra on the
+host side (dataset / test tooling).  There is no CPU fallback: a CPU
 tensor raises.
 """
 from __future__ import annotations
@@ -53,9 +54,44 @@ def rot_from_axisangle(vec):
     return torch.cat(rows, 1)
 
 
+class _PoseToMatrix(torch.autograd.Function):
+    """One launch each way (csrc/pose.cu) instead of ~30 + ~60 tiny ones."""
+
+    @staticmethod
+    def forward(ctx, axisangle, translation, invert):
+        import ctypes  # noqa: F401
+        from . import _cabi as C
+        aa = axisangle.detach().reshape(-1, 3).contiguous().float()
+        tr = translation.detach().reshape(-1, 3).contiguous().float()
+        B = aa.shape[0]
+        with torch.cuda.device(aa.device):
+            T = torch.empty(B, 4, 4, device=aa.device, dtype=torch.float32)
+            C.check(C.lib().ppea_pose_to_matrix_forward(aa.data_ptr(), tr.data_ptr(), int(bool(invert)), T.data_ptr(), B,
+                                                        torch.cuda.current_stream().cuda_stream))
+        ctx.save_for_backward(aa, tr)
+        ctx.invert = bool(invert)
+        ctx.shapes = (axisangle.shape, translation.shape)
+        return T
+
+    @staticmethod
+    def backward(ctx, grad_T):
+        from . import _cabi as C
+        aa, tr = ctx.saved_tensors
+        B = aa.shape[0]
+        g = grad_T.contiguous().float()
+        with torch.cuda.device(aa.device):
+            g_aa, g_tr = torch.empty_like(aa), torch.empty_like(tr)
+            C.check(C.lib().ppea_pose_to_matrix_backward(aa.data_ptr(), tr.data_ptr(), int(ctx.invert), g.data_ptr(), g_aa.data_ptr(),
+                                                         g_tr.data_ptr(), B, torch.cuda.current_stream().cuda_stream))
+        return g_aa.reshape(ctx.shapes[0]), g_tr.reshape(ctx.shapes[1]), None
+
+
 def transformation_from_parameters(axisangle, translation, invert=False):
-    """Pose-net output -> 4x4 camera transform; layers.py:26-42.  The fused
-    loss returns dL/dT (B,4,4); autograd carries it through this function."""
+    """Pose-net output -> 4x4 camera transform; layers.py:26-42.  The fused loss returns dL/dT (B,4,4); autograd carries it
+    through this function.  CUDA tensors take the fused kernels (`ppea_pose_to_matrix_forward/backward`); CPU tensors -- the
+    dataset / test-tooling side, where the reference also runs it on the host -- the same tensor algebra in PyTorch."""
+    if axisangle.is_cuda:
+        return _PoseToMatrix.apply(axisangle, translation, invert)
     R = rot_from_axisangle(axisangle)
     t = translation.clone()
     if invert:

@@ -27,8 +27,8 @@ def pytest_collection_modifyitems(config, items):
 
 
 def golden_names():
-    # (the matching_*.pt fixtures belong to the cost-volume tests, tests/test_matching.py)
-    return sorted(f[:-3] for f in os.listdir(GOLDEN_DIR) if f.endswith(".pt") and not f.startswith("matching_"))
+    # (the matching_*.pt / pose_*.pt fixtures belong to tests/test_matching.py / tests/test_pose.py)
+    return sorted(f[:-3] for f in os.listdir(GOLDEN_DIR) if f.endswith(".pt") and not f.startswith(("matching_", "pose_")))
 
 
 def load_golden(name):
