@@ -260,6 +260,10 @@ int ppea_pose_to_matrix_forward(const float* axisangle, const float* translation
 int ppea_pose_to_matrix_backward(const float* axisangle, const float* translation, int invert, const float* grad_T,
                                  float* grad_axisangle, float* grad_translation, int batch, void* stream);
 
+/* Trainer.compute_matching_mask (trainer.py:859-869): mask[i] = ((1/lowest_cost - mono) / mono < 1) && ((mono - 1/lowest_cost) /
+ * (1/lowest_cost) < 1), one byte per element (torch.bool layout); mono_depth (B,1,H,W) and lowest_cost (B,H,W) flattened. */
+int ppea_matching_mask(const float* mono_depth, const float* lowest_cost, uint8_t* mask, size_t count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,6 +50,14 @@ def images_from_u8(img_u8):
     return img_u8.to(torch.float32).div(255)
 
 
+def compute_matching_mask(mono_depth, lowest_cost):
+    """Trainer.compute_matching_mask, trainer.py:859-869 (mono_depth (B,1,H,W), lowest_cost (B,H,W)) -> (B,H,W) bool."""
+    matching_depth = 1 / lowest_cost.unsqueeze(1)
+    mask = ((matching_depth - mono_depth) / mono_depth) < 1.0
+    mask = mask * (((mono_depth - matching_depth) / matching_depth) < 1.0)
+    return mask[:, 0]
+
+
 def disp_to_depth(disp, min_depth, max_depth):
     # layers.py:14-23 -- scaled = 1/max + (1/min - 1/max) * disp ; depth = 1/scaled
     lo = 1.0 / max_depth

@@ -117,6 +117,7 @@ SIGNATURES = {
     "ppea_images_u8_to_f32": (_I, [_P, _P, _SZ, _P]),
     "ppea_pose_to_matrix_forward": (_I, [_P, _P, _I, _P, _I, _P]),
     "ppea_pose_to_matrix_backward": (_I, [_P, _P, _I, _P, _P, _P, _I, _P]),
+    "ppea_matching_mask": (_I, [_P, _P, _P, _SZ, _P]),
     "ppea_match_tail": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "ppea_match_features": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P]),
 }

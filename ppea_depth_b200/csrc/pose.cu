@@ -181,6 +181,27 @@ __global__ void pose_to_matrix_backward_kernel(const float* __restrict__ aa, con
   }
 }
 
+// Trainer.compute_matching_mask (trainer.py:859-869): where the cost volume's best depth and the teacher disagree by less
+// than a factor of two either way.  matching_depth = 1 / lowest_cost; mask = ((md - mono) / mono < 1) * ((mono - md) / md < 1).
+__global__ void __launch_bounds__(256) matching_mask_kernel(const float* __restrict__ mono_depth, const float* __restrict__ lowest_cost,
+                                                            uint8_t* __restrict__ mask, size_t n) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const float mono = __ldg(mono_depth + i);
+  const float md = div_rn(1.f, __ldg(lowest_cost + i));
+  const bool a = div_rn(sub_rn(md, mono), mono) < 1.f;
+  const bool b = div_rn(sub_rn(mono, md), md) < 1.f;
+  mask[i] = (a && b) ? 1 : 0;
+}
+
+extern "C" int ppea_matching_mask(const float* mono_depth, const float* lowest_cost, uint8_t* mask, size_t count, void* stream) {
+  if (!mono_depth || !lowest_cost || !mask) return PPEA_E_NULL;
+  if (count == 0) return PPEA_OK;
+  if (count > ((size_t)1 << 40)) return PPEA_E_SHAPE;
+  matching_mask_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(mono_depth, lowest_cost, mask, count);
+  return (int)cudaGetLastError();
+}
+
 extern "C" int ppea_pose_to_matrix_forward(const float* axisangle, const float* translation, int invert, float* T, int batch,
                                            void* stream) {
   if (!axisangle || !translation || !T) return PPEA_E_NULL;

@@ -173,12 +173,36 @@ def compute_losses(self, inputs, outputs, is_multi=False):
     return losses, []
 
 
+def compute_matching_mask(self, outputs):
+    """Trainer.compute_matching_mask (trainer.py:859-869) in one launch: where the cost volume's best depth and the teacher
+    network disagree by less than a factor of two either way.  Returns the (B,H,W) bool mask."""
+    import ctypes
+    from . import _cabi as C
+    mono = outputs[("mono_depth", 0, 0)]
+    if not mono.is_cuda:
+        raise RuntimeError("ppea_depth_b200 has no CPU path: mono_depth must be a CUDA tensor")
+    mono = mono.detach().contiguous().float()
+    lowest = outputs["lowest_cost"]
+    if not torch.is_tensor(lowest):
+        lowest = torch.as_tensor(lowest)
+    lowest = lowest.to(mono.device).detach().contiguous().float()
+    B, _, H, W = mono.shape
+    if lowest.numel() != B * H * W:
+        raise ValueError("compute_matching_mask: lowest_cost must be (B,H,W) at the resolution of mono_depth")
+    with torch.cuda.device(mono.device):
+        mask = torch.empty(B, H, W, device=mono.device, dtype=torch.bool)
+        C.check(C.lib().ppea_matching_mask(mono.data_ptr(), lowest.data_ptr(), mask.data_ptr(), ctypes.c_size_t(mask.numel()),
+                                           torch.cuda.current_stream().cuda_stream))
+    return mask
+
+
 def install(trainer_cls, deterministic=False, noise_mode="reference", fused=None):
     """Rebinds the reference Trainer's loss methods to the fused implementation."""
     trainer_cls.generate_images_pred = generate_images_pred
     trainer_cls.compute_reprojection_loss = compute_reprojection_loss
     trainer_cls.compute_loss_masks = staticmethod(compute_loss_masks)
     trainer_cls.compute_losses = compute_losses
+    trainer_cls.compute_matching_mask = compute_matching_mask
     trainer_cls.ppea_deterministic = deterministic
     trainer_cls.ppea_noise_mode = noise_mode
     trainer_cls.ppea_fused = fused     # None: single-launch training step whenever it applies (functional.VslConfig.fused)

@@ -74,3 +74,33 @@ def test_cuda_pose_large_batch_and_loss_chain():
         assert float((M.detach().cpu().double() - M64).abs().max()) <= 2e-6
         assert float((a.grad.cpu().double() - ga).abs().max()) <= 2e-5 * float(ga.abs().max())
         assert float((t.grad.cpu().double() - gt).abs().max()) <= 2e-5 * float(gt.abs().max())
+
+
+def test_oracle_matching_mask_matches_reference_live():
+    """compute_matching_mask restatement vs the reference's own Trainer method (unbound, stand-in self)."""
+    if not os.path.isdir("/root/reference/ppeadepth"):
+        pytest.skip("reference not mounted")
+    from types import SimpleNamespace
+    from oracle import ref_import as R
+    from oracle import vsl_oracle as O
+    T = R.load_reference()
+    g = torch.Generator().manual_seed(3)
+    mono = 0.5 + 10 * torch.rand(2, 1, 24, 40, generator=g)
+    lowest = 1 / (mono[:, 0] * torch.exp(1.2 * torch.randn(2, 24, 40, generator=g)))
+    me = SimpleNamespace(device="cpu")
+    want = T.Trainer.compute_matching_mask(me, {("mono_depth", 0, 0): mono, "lowest_cost": lowest})
+    got = O.compute_matching_mask(mono, lowest)
+    assert torch.equal(got, want) and 0.1 < float(want.float().mean()) < 0.9
+
+
+@pytest.mark.gpu
+def test_cuda_matching_mask():
+    from oracle import vsl_oracle as O
+    from ppea_depth_b200.loss import compute_matching_mask
+    g = torch.Generator().manual_seed(4)
+    mono = 0.5 + 10 * torch.rand(3, 1, 33, 47, generator=g)
+    lowest = 1 / (mono[:, 0] * torch.exp(1.2 * torch.randn(3, 33, 47, generator=g)))
+    want = O.compute_matching_mask(mono, lowest)
+    got = compute_matching_mask(None, {("mono_depth", 0, 0): mono.cuda(), "lowest_cost": lowest.cuda()})
+    assert got.dtype == torch.bool and got.shape == (3, 33, 47)
+    assert torch.equal(got.cpu(), want) and 0.1 < float(want.float().mean()) < 0.9
