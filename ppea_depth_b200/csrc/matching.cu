@@ -9,7 +9,8 @@
 // Python loop over the batch.
 //
 // Here: one launch for the volume (+ one small fix-up launch).  A thread owns one pixel of one batch item and a chunk of
-// kMatchChunk depth bins (grid.z: enough CTAs for whole waves on 148 SMs) and walks them kMatchBins at a time: the
+// kMatchChunk depth bins (grid.z; measured best with one group of four bins per CTA: 17 280 CTAs at the KITTI shape, the
+// 128 pixels of a CTA sample one contiguous footprint per bin) and walks them kMatchBins at a time: the
 // projection of the hypotheses is set up once (corner offsets + bilinear weights in registers), then the channel loop
 // reads the current feature once per channel and the four corners of every hypothesis (lanes are adjacent pixels, so
 // every load of the warp is a contiguous run of one channel plane).  "Set missing to max" needs the per-pixel maximum
@@ -24,9 +25,18 @@
 
 namespace ppea {
 
-constexpr int kMatchThreads = 128;
-constexpr int kMatchBins = 4;        // depth hypotheses in flight per thread
-constexpr int kMatchChunk = 32;     // depth bins per CTA (grid.z = ceil(D / kMatchChunk))
+#ifndef PPEA_MATCH_THREADS
+#define PPEA_MATCH_THREADS 128
+#endif
+constexpr int kMatchThreads = PPEA_MATCH_THREADS;
+#ifndef PPEA_MATCH_BINS
+#define PPEA_MATCH_BINS 4
+#endif
+#ifndef PPEA_MATCH_CHUNK
+#define PPEA_MATCH_CHUNK 4
+#endif
+constexpr int kMatchBins = PPEA_MATCH_BINS;        // depth hypotheses in flight per thread
+constexpr int kMatchChunk = PPEA_MATCH_CHUNK;     // depth bins per CTA (grid.z = ceil(D / kMatchChunk))
 constexpr int kMatchMaxBins = 4096;
 
 struct MatchArgs {
