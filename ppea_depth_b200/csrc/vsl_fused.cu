@@ -322,11 +322,10 @@ __global__ void __launch_bounds__(NT, PPEA_FUSED_CTAS) vsl_fused_kernel(const __
   const int col = tid % TW;
   const int row0 = (tid / TW) * R;
   const int gx_own = x0 + col;
-  const ColCtx col_own = make_col(sm.G, gx_own, W);              // this thread's tile column (reflect-clamped for partial tiles)
-  const int px_own = col_own.px;
-  const SrcPlanes sp = make_planes(src_b[0], src_b[1], plane);
+  // this thread's tile column (reflect-clamped for partial tiles); the context (6 registers of folded projection) is
+  // rebuilt from the geometry block where it is needed instead of living across the whole scale loop
+  const int px_own = reflect_index(gx_own, W);
   // reflection multiplicities of the taps left/right of this thread's column
-  const f2 mL = dup2((gx_own == 1) ? 2.f : 1.f), mR = dup2((gx_own == W - 2) ? 2.f : 1.f);
 
 #pragma unroll 1
   for (int s = 0; s < a.S; ++s) {
@@ -340,7 +339,8 @@ __global__ void __launch_bounds__(NT, PPEA_FUSED_CTAS) vsl_fused_kernel(const __
 
     // ---- gather.  Warp w walks its own R tile rows (lane == tile column, derivatives kept) plus its share
     // of the four halo rows; the four halo columns are a flat list of extra cells.
-    ColCtx cc = col_own;
+    ColCtx cc = make_col(sm.G, gx_own, W);
+    const SrcPlanes sp = make_planes(a.src[0] + (size_t)b * 3 * plane, a.src[1] + (size_t)b * 3 * plane, plane);   // (per scale: not kept live across pass Q / fold)
     if (!same_res) cc.cx = up_coef(cc.px, sc.ws, sc.up_sx);
     // the (upsampled) disparity of region row i at this thread's column: loads only, so the rows of a
     // thread can have them in flight together, ahead of the dependent source gathers
@@ -485,6 +485,7 @@ __global__ void __launch_bounds__(NT, PPEA_FUSED_CTAS) vsl_fused_kernel(const __
         const int sl = i % 3;
         if (!no_ssim) {
           const int qrow = (row0 + i) * QW + col;
+          const f2 mL = dup2((gx_own == 1) ? 2.f : 1.f), mR = dup2((gx_own == W - 2) ? 2.f : 1.f);
           const f2 i0 = vmul(mL, sm.ind[qrow]), i1 = sm.ind[qrow + 1], i2 = vmul(mR, sm.ind[qrow + 2]);
 #pragma unroll
           for (int e = 0; e < 3; ++e) {
@@ -528,13 +529,14 @@ __global__ void __launch_bounds__(NT, PPEA_FUSED_CTAS) vsl_fused_kernel(const __
       const int gy = y0 + row0 + k;
       if (gy < H && gx_own < W) {
         f2 A[3];
-        const ProjT<f2> pr = project_cell(sm.G, col_own, gy, dep[k], a.eps, wmax, hmax, A);
+        const float depk = dep[k];
+        const ProjT<f2> pr = project_cell(sm.G, make_col(sm.G, gx_own, W), gy, depk, a.eps, wmax, hmax, A);
         const f2 gc0 = vmul(gu[k], pr.rz), gc1 = vmul(gv[k], pr.rz);
         const f2 gc2 = vneg(vmul(vfma(gu[k], pr.u, vmul(gv[k], pr.v)), pr.rz));
         const f2 gd2 = vfma(gc2, A[2], vfma(gc1, A[1], vmul(gc0, A[0])));
         const float g = gd2.x + gd2.y;
         if (POSE) {
-          const f2 dk = dup2(dep[k]), fy = dup2(int_to_float(gy));
+          const f2 dk = dup2(depk), fy = dup2(int_to_float(gy));
           const f2 w0 = vmul(gc0, dk), w1 = vmul(gc1, dk), w2 = vmul(gc2, dk);
           Sw[0] = vadd(Sw[0], w0);
           Sw[1] = vadd(Sw[1], w1);
@@ -546,7 +548,7 @@ __global__ void __launch_bounds__(NT, PPEA_FUSED_CTAS) vsl_fused_kernel(const __
           Sg[1] = vadd(Sg[1], gc1);
           Sg[2] = vadd(Sg[2], gc2);
         }
-        const float dd = ddepth_ddisp(dep[k], a.disp_range);
+        const float dd = ddepth_ddisp(depk, a.disp_range);
         const float g_dup = g * dd;
         float c_dup = 0.f;
         if (MULTI) {
@@ -554,7 +556,7 @@ __global__ void __launch_bounds__(NT, PPEA_FUSED_CTAS) vsl_fused_kernel(const __
           // gradient goes to a field of its own (its upstream weight differs from the photometric one)
           const size_t o = (size_t)b * plane + (size_t)gy * W + gx_own;
           const float om = 1.f - (motion ? __ldg(a.cons_mask + o) : 1.f) * one_minus_aug;
-          const float dm = dep[k] - __ldg(sc.mono_depth + o);
+          const float dm = depk - __ldg(sc.mono_depth + o);
           s_c = fmaf(fabsf(dm), om, s_c);
           c_dup = sign_of(dm) * om * dd;
         }
