@@ -302,23 +302,31 @@ constexpr int kFinishThreads = 32 * kFinishWarps * kMaxScales;
 
 // Fused step: CTAs 1..B of the finish launch reduce the per-tile pose partials of one image each to per-scale sums
 // (fixed order, double), so that the backward only has to weight S x 24 numbers per image (vsl_fused.cu pose_combine_role).
+// Thread t < 768 owns entry t % 24 of the tiles t / 24, t / 24 + 32, ...: a warp reads 32 consecutive floats of the
+// [tile][scale][24] array (coalesced), every load is independent; the 32 tile groups are then added in group order.
 __device__ __forceinline__ void pose_sums_role(const VslArgs& a, int b, int tiles_per_image) {
-  const int tid = threadIdx.x, lane = tid & 31, e = tid >> 5;      // warp e reduces entry e of every scale
-  if (e >= 24) return;
-  const int S = a.S;
-  double t[kMaxScales] = {0, 0, 0, 0};
-  const float* p = a.pose_partials + (size_t)b * tiles_per_image * S * 24 + e;
+  constexpr int kGroups = 32;
+  __shared__ double red[kGroups][kMaxScales][24];
+  const int tid = threadIdx.x, S = a.S;
+  if (tid < kGroups * 24) {
+    const int e = tid % 24, g = tid / 24;
+    double t[kMaxScales] = {0, 0, 0, 0};
+    const float* p = a.pose_partials + (size_t)b * tiles_per_image * S * 24 + e;
 #pragma unroll 2
-  for (int i = lane; i < tiles_per_image; i += 32) {
+    for (int i = g; i < tiles_per_image; i += kGroups) {
 #pragma unroll
-    for (int s = 0; s < kMaxScales; ++s)
-      if (s < S) t[s] += (double)__ldg(p + ((size_t)i * S + s) * 24);
+      for (int s = 0; s < kMaxScales; ++s)
+        if (s < S) t[s] += (double)__ldg(p + ((size_t)i * S + s) * 24);
+    }
+#pragma unroll
+    for (int s = 0; s < kMaxScales; ++s) red[g][s][e] = t[s];
   }
-#pragma unroll
-  for (int s = 0; s < kMaxScales; ++s) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t[s] += __shfl_xor_sync(0xffffffffu, t[s], o);
-    if (lane == 0 && s < S) a.pose_sums[((size_t)b * S + s) * 24 + e] = t[s];
+  __syncthreads();
+  if (tid < 24 * S) {
+    const int e = tid % 24, s = tid / 24;
+    double t = 0;
+    for (int g = 0; g < kGroups; ++g) t += red[g][s][e];
+    a.pose_sums[((size_t)b * S + s) * 24 + e] = t;
   }
 }
 
