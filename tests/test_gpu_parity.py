@@ -220,3 +220,64 @@ def test_unaligned_frames_take_the_non_tma_path():
     assert torch.equal(ga, gb)
     for x, y in zip(da, db):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("multi,det", [(False, False), (True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("shape", [(2, 33, 47, 3), (1, 50, 70, 4), (2, 64, 96, 4)])
+def test_no_out_of_bounds_writes(shape, multi, det):
+    """compute-sanitizer is not available on this pool: every buffer the host layer allocates for one fused forward +
+    backward (outputs, sums, losses, both workspaces, gradients) is placed between two guard regions filled with a
+    sentinel, and the guards must come back untouched (ragged sizes: partial tiles on every border)."""
+    from unittest import mock
+    from ppea_depth_b200 import functional as Fn
+    from ppea_depth_b200.loss import ViewSynthesisLoss
+    from gpu_helpers import FeedNoise
+    B, H, W, S = shape
+    cfg = SynthConfig(batch=B, height=H, width=W, num_scales=S, seed=53)
+    inputs, outputs = make_batch(cfg)
+    for s in range(1, S):
+        hs, ws = H >> s, W >> s
+        outputs[("disp", s)] = outputs[("disp", s)][..., :hs, :ws].contiguous()
+        inputs[("color", 0, s)] = inputs[("color", 0, s)][..., :hs, :ws].contiguous()
+        if ("mono_depth", 0, s) in outputs:
+            outputs[("mono_depth", 0, s)] = outputs[("mono_depth", 0, s)].contiguous()
+    noise = make_noise(cfg, S)
+    opt = O.default_opt(sclm=S - 1, height=H, width=W, batch_size=B)
+    ins, outs = O.clone_batch(inputs, outputs, device="cuda")
+    G = 1024                                     # guard elements on each side (keeps 16-byte alignment)
+    real_empty, real_empty_like = torch.empty, torch.empty_like
+    SENT = {torch.float32: float("nan"), torch.uint8: 0xAB, torch.int64: -7, torch.bool: True}
+    tracked = []
+
+    def guarded_empty(*size, **kw):
+        if len(size) == 1 and isinstance(size[0], (tuple, list, torch.Size)):
+            size = tuple(size[0])
+        dev = kw.get("device")
+        if dev is None or torch.device(dev).type != "cuda":
+            return real_empty(*size, **kw)
+        dt = kw.get("dtype", torch.float32)
+        n = 1
+        for d in size:
+            n *= int(d)
+        buf = torch.full((n + 2 * G,), SENT[dt], device=dev, dtype=dt)
+        tracked.append((buf, n, dt))
+        return buf[G:G + n].view(*size)
+
+    def guarded_empty_like(t, **kw):
+        return guarded_empty(*t.shape, device=t.device, dtype=kw.get("dtype", t.dtype))
+
+    mod = ViewSynthesisLoss(opt, deterministic=det, keep_maps=True)
+    with mock.patch.object(Fn.torch, "empty", guarded_empty), mock.patch.object(Fn.torch, "empty_like", guarded_empty_like):
+        with FeedNoise(noise):
+            mod.generate_images_pred(ins, outs, multi)
+            losses, _ = mod.compute_losses(ins, outs, multi)
+        losses["loss"].backward()
+        torch.cuda.synchronize()
+    assert len(tracked) >= 2 * S + 4
+    assert torch.isfinite(losses["loss"]).item()
+    for buf, n, dt in tracked:
+        for guard in (buf[:G], buf[G + n:]):
+            if dt == torch.float32:
+                assert bool(torch.isnan(guard).all()), (n, dt)
+            else:
+                assert bool((guard == SENT[dt]).all()), (n, dt)
