@@ -121,3 +121,34 @@ def test_cuda_tail_matches_oracle(stm):
     P.install_matching(Enc)
     c2 = Enc().compute_confidence_mask((cost * (1 - missing)).cuda())
     assert torch.equal(c2.cpu(), want[0])
+
+
+@pytest.mark.gpu
+def test_matching_no_out_of_bounds_writes():
+    """Guard regions around the cost volume / mask / tail outputs stay untouched (ragged size, far bins)."""
+    from unittest import mock
+    import ppea_depth_b200 as P
+    from ppea_depth_b200 import matching as MM
+    cur, look, poses, K, invK, bins = M.synthetic_case(B=2, Fr=2, C=5, h=33, w=47, D=13, seed=31, min_bin=0.05, max_bin=60.0)
+    G = 1024
+    real_empty = torch.empty
+    tracked = []
+
+    def guarded_empty(*size, **kw):
+        dt = kw.get("dtype", torch.float32)
+        n = 1
+        for d in size:
+            n *= int(d)
+        sent = float("nan") if dt == torch.float32 else -7
+        buf = torch.full((n + 2 * G,), sent, device=kw["device"], dtype=dt)
+        tracked.append((buf, n, dt, sent))
+        return buf[G:G + n].view(*size)
+
+    with mock.patch.object(MM.torch, "empty", guarded_empty):
+        cost, missing = P.match_features(cur.cuda(), look.cuda(), poses.cuda(), K.cuda(), invK.cuda(), bins, True)
+        conf, mins, argmin = P.cost_volume_tail(cost, missing)
+        torch.cuda.synchronize()
+    assert len(tracked) == 5 and torch.isfinite(cost).all()
+    for buf, n, dt, sent in tracked:
+        for guard in (buf[:G], buf[G + n:]):
+            assert bool(torch.isnan(guard).all()) if dt == torch.float32 else bool((guard == sent).all())
