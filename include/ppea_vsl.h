@@ -66,7 +66,8 @@ extern "C" {
                                           opt.disable_automasking only drops the noise (trainer.py:1084-1091) => pass noise = NULL */
 #define PPEA_F_SELEC_REPROJ (1u << 2)  /* opt.selec_reproj (default True, options.py:428-430; trainer.py:1077-1083) */
 #define PPEA_F_NO_SSIM (1u << 3)       /* opt.no_ssim (trainer.py:1001-1002) */
-#define PPEA_F_DETERMINISTIC (1u << 4) /* backward: two-pass gather of the disparity gradient instead of float atomics */
+#define PPEA_F_DETERMINISTIC (1u << 4) /* bit-reproducible disparity gradient: two-pass gather (ppea_vsl_backward) or 64-bit fixed-point
+                                          accumulation (fused step) instead of float atomics */
 #define PPEA_F_MOTION_MASK (1u << 5)   /* not opt.disable_motion_masking (trainer.py:1103-1105) */
 #define PPEA_F_MATCH_AUG (1u << 6)     /* not opt.no_matching_augmentation (trainer.py:1106-1108) */
 #define PPEA_F_GRAD_POSE (1u << 7)     /* backward: also produce dL/dT (mono path) */
@@ -137,7 +138,8 @@ typedef struct PpeaVslParams {
   void* const* trace_events; /* NULL, or PPEA_TRACE_EVENTS cudaEvent_t handles (ppea_event_create) recorded on `stream`:
                                 [0] before the first kernel, then after each stage --
                                 forward:  [1] (unused)  [2] fused forward kernel  [3] (unused)  [4] finish
-                                backward: [1] grad zero-fill (or smoothness backward when deterministic)  [2] fused backward kernel  [3] upsample gather  [4] pose finish */
+                                backward: [1] grad zero-fill (or smoothness backward when deterministic)  [2] fused backward kernel  [3] upsample gather  [4] pose finish;
+                                fused step: forward [1] field zero-fill (unless RAW_PREZEROED)  [2] fused kernel  [4] finish; backward [2] gradient finish */
 } PpeaVslParams;
 
 typedef struct PpeaVslGrads {
