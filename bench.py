@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--path", default="mono", choices=["mono", "multi"])
     ap.add_argument("--deterministic", action="store_true")
     ap.add_argument("--no-fused", action="store_true", help="forward + backward kernel pair instead of the single-launch step")
+    ap.add_argument("--tiles", action="store_true", help="fused step by the shared-memory tile kernel (round 1) instead of the streaming kernel")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of one repetition of the e2e leg (default: min(steps, 100))")
@@ -272,8 +273,9 @@ def main():
     n_sets = max(4, int(2.5 * L2_BYTES // step_bytes) + 1)
     n_sets = min(n_sets, 12)
     sets = probe + make_sets(wl, n_sets - 1, 1000 * rank + 1, device, is_multi)
-    plans = [build_plan(t, wl, device, is_multi, args.deterministic, fused=False if args.no_fused else None) for t in sets]
+    plans = [build_plan(t, wl, device, is_multi, args.deterministic, fused=False if args.no_fused else ("tiles" if args.tiles else None)) for t in sets]
     fused = plans[0].fused
+    tiles = plans[0].tiles
     cfg_desc["kernels"] = ("single-launch fused step (vsl_fused_kernel, TMA-staged tiles) + finish + gradient finish (tails launched programmatically)" if fused
                            else "vsl_forward_kernel + finish + vsl_backward_kernel + pose finish")
     for p in plans:
@@ -334,7 +336,7 @@ def main():
             # two-launch figure of SURVEY.md §8d: target/sources are read once, sel never round-trips.  Its own compulsory
             # bytes: tgt 12 + src 24 + noise 4 + depth 4 + sel 1 + loss 4 + (disp 4 + colour 12 + raw grad 4 + stencil 4)/4^s;
             # multi path: cons_mask 4 + mono_depth 4 instead of the noise, + consistency field 4/4^s.
-            dom = "vsl_fused_kernel"
+            dom = "vsl_fused_kernel" if tiles else "vsl_stream_kernel"
             dom_bytes = sum((53.0 if is_multi else 49.0) + (28.0 if is_multi else 24.0) / 4 ** s for s in range(S)) * n_px
         else:
             dom = "vsl_backward_kernel" if stage_ms["vsl_backward_kernel"] >= stage_ms["vsl_forward_kernel"] else "vsl_forward_kernel"
@@ -361,7 +363,7 @@ def main():
                               frame_ids=[0, -1, 1], disable_automasking=False, no_ssim=False, selec_reproj=True,
                               disable_motion_masking=False, no_matching_augmentation=False, batch_size=B,
                               disparity_smoothness=1e-3)
-        mod = ViewSynthesisLoss(opt, deterministic=args.deterministic, noise_mode="device", fused=False if args.no_fused else None)
+        mod = ViewSynthesisLoss(opt, deterministic=args.deterministic, noise_mode="device", fused=False if args.no_fused else ("tiles" if args.tiles else None))
         def collate(t):
             """One pinned arena per batch (what a collate_fn writing into a pinned buffer gives): a step's inputs cross
             PCIe as ONE copy.  Returns (arena, layout) with layout[key] = (byte offset, shape, dtype); uint8 frames first,

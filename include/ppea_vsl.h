@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define PPEA_ABI_VERSION 5
+#define PPEA_ABI_VERSION 6
 
 /* error codes (negative) */
 #define PPEA_OK 0
@@ -78,6 +78,10 @@ extern "C" {
                                            entry of ppea_vsl_fused_forward (zero-filled once by the caller); ppea_vsl_fused_backward
                                            then clears them again on its way out, so a replayed forward/backward pair needs no
                                            memset.  Every fused_forward must be followed by exactly one fused_backward. */
+
+#define PPEA_F_FUSED_TILES (1u << 10)   /* fused step: run the round-1 shared-memory tile kernel (vsl_fused.cu, TMA-staged tiles) instead of
+                                           the warp-streaming kernel (vsl_stream.cu); same results to the documented tolerances.  Pass it to
+                                           ppea_vsl_fused_workspace_bytes / _forward / _backward alike. */
 
 /* sel map (uint8 per full-res pixel, written by forward, read by backward):
  *   bits 0-1: source frame whose loss is propagated: 0 -> frame_ids[1] (-1),

@@ -15,12 +15,12 @@ import sys
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(PKG_DIR, "csrc")
-LIB_PATH = os.environ.get("PPEA_LIB") or os.path.join(PKG_DIR, "libppea_vsl.so")
+LIB_PATH = (os.environ.get("PPEA_LIB") and os.path.abspath(os.environ["PPEA_LIB"])) or os.path.join(PKG_DIR, "libppea_vsl.so")
 INCLUDE_DIR = os.path.join(os.path.dirname(PKG_DIR), "include")
-SOURCES = ("api.cu", "vsl_fwd.cu", "vsl_bwd.cu", "vsl_fused.cu", "smooth.cu", "ops.cu", "matching.cu", "pose.cu")
+SOURCES = ("api.cu", "vsl_fwd.cu", "vsl_bwd.cu", "vsl_fused.cu", "vsl_stream.cu", "smooth.cu", "ops.cu", "matching.cu", "pose.cu")
 HEADERS = ("vsl_common.cuh", "vsl_math.cuh", "vsl_gather.cuh", "smooth.cuh")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 TRACE_EVENTS = 5
 MAX_SCALES = 4
 SUMS_PER_SCALE = 8
@@ -36,6 +36,7 @@ F_MATCH_AUG = 1 << 6
 F_GRAD_POSE = 1 << 7
 F_GRAD_PREZEROED = 1 << 8
 F_RAW_PREZEROED = 1 << 9
+F_FUSED_TILES = 1 << 10
 
 SEL_SRC_MASK = 3
 SEL_AUTOMASK = 4

@@ -3,6 +3,8 @@
 // host synchronisation, no global state: every call only enqueues on `stream`.
 #include "vsl_common.cuh"
 
+#include <algorithm>
+
 using namespace ppea;
 
 namespace {
@@ -229,6 +231,7 @@ static_assert(kFusedTileWc == kFwdTileW && kFusedTileHc >= kFwdTileH, "the fused
 
 struct FusedWorkspace {
   size_t off_pose, off_pose_sums, off_raw[kMaxScales], off_raw2[kMaxScales], off_st[kMaxScales], raw_floats[kMaxScales], total_floats;
+  size_t off_flag, off_ident, off_pk[2];       // streaming step: format flag (4 floats), identity-loss map, packed sources
 };
 // Layout (floats): [pose partials: nblk*S*24][per-image pose sums: B*S*24 doubles][raw photometric gradient of disp_s][multi path: raw consistency
 // gradient of disp_s][smoothness stencil field of disp_s].  A coarse-scale raw field takes 2 floats per pixel:
@@ -236,7 +239,8 @@ struct FusedWorkspace {
 static FusedWorkspace fused_workspace(const PpeaVslParams* p) {
   FusedWorkspace w;
   w.off_pose = 0;
-  size_t off = align_up((size_t)fused_blocks(p->batch, p->height, p->width) * p->num_scales * 24, 4);
+  const size_t n_tiles = (size_t)std::max(fused_blocks(p->batch, p->height, p->width), stream_tiles(p->batch, p->height, p->width));
+  size_t off = align_up(n_tiles * p->num_scales * 24, 4);
   w.off_pose_sums = off;                                             // [B][S][24] doubles
   off += align_up((size_t)p->batch * p->num_scales * 24 * 2, 4);
   for (int s = 0; s < kMaxScales; ++s) {
@@ -259,6 +263,15 @@ static FusedWorkspace fused_workspace(const PpeaVslParams* p) {
     w.off_st[s] = off;
     if (s < p->num_scales) off += align_up((size_t)p->batch * p->scales[s].disp_h * p->scales[s].disp_w, 4);
   }
+  const size_t n_px = align_up((size_t)p->batch * p->height * p->width, 4);
+  w.off_flag = off;
+  off += 4;
+  w.off_ident = off;
+  off += n_px;
+  w.off_pk[0] = off;
+  off += n_px;
+  w.off_pk[1] = off;
+  off += n_px;
   w.total_floats = off;
   return w;
 }
@@ -303,16 +316,26 @@ static bool frame_tensor_map(CUtensorMap* tm, const float* base, int B, int H, i
              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-static void fused_args(const PpeaVslParams* p, const PpeaVslFused* f, VslArgs& a) {
+static bool use_tiles(const PpeaVslParams* p) { return p->flags & PPEA_F_FUSED_TILES; }
+static int fused_tiles(const PpeaVslParams* p) {
+  return use_tiles(p) ? fused_blocks(p->batch, p->height, p->width) : stream_tiles(p->batch, p->height, p->width);
+}
+
+static void fused_args(const PpeaVslParams* p, const PpeaVslFused* f, VslArgs& a, bool forward) {
   fill_args(p, a);
-  a.use_tma = (frame_tensor_map(&a.tm_tgt, a.tgt, a.B, a.H, a.W) && frame_tensor_map(&a.tm_src[0], a.src[0], a.B, a.H, a.W) &&
+  const bool tiles = use_tiles(p);
+  a.use_tma = (tiles && forward && frame_tensor_map(&a.tm_tgt, a.tgt, a.B, a.H, a.W) && frame_tensor_map(&a.tm_src[0], a.src[0], a.B, a.H, a.W) &&
                frame_tensor_map(&a.tm_src[1], a.src[1], a.B, a.H, a.W))
                   ? 1
                   : 0;
   const FusedWorkspace fw = fused_workspace(p);
   const FwdWorkspace ws = fwd_workspace(p->batch, p->height, p->width, p->num_scales);
-  a.tiles_x = ceil_div(a.W, kFusedTileWc);
-  a.tiles_y = ceil_div(a.H, kFusedTileHc);
+  a.tiles_x = tiles ? ceil_div(a.W, kFusedTileWc) : stream_strips(a.W);
+  a.tiles_y = tiles ? ceil_div(a.H, kFusedTileHc) : stream_segs(a.H);
+  a.fmt_flag = reinterpret_cast<unsigned*>((float*)f->workspace + fw.off_flag);
+  a.ident = (float*)f->workspace + fw.off_ident;
+  a.pk[0] = reinterpret_cast<uint32_t*>((float*)f->workspace + fw.off_pk[0]);
+  a.pk[1] = reinterpret_cast<uint32_t*>((float*)f->workspace + fw.off_pk[1]);
   a.partials = (float*)p->workspace + ws.off_partials;
   a.smooth_ws = (float*)p->workspace + ws.off_smooth;
   a.pose_partials = (float*)f->workspace + fw.off_pose;
@@ -339,11 +362,12 @@ int ppea_vsl_fused_forward(const PpeaVslParams* p, const PpeaVslFused* f, void* 
   if (!aligned(p->workspace, 16) || p->workspace_bytes < ws.total_floats * sizeof(float)) return PPEA_E_WORKSPACE;
   cudaStream_t stream = (cudaStream_t)stream_;
   VslArgs a;
-  fused_args(p, f, a);
+  fused_args(p, f, a, true);
   for (int s = 0; s < a.S; ++s) a.sc[s].grad_disp = nullptr;     // (the smoothness role would pre-zero it)
   PPEA_TRACE(p, 0);
   if (!(p->flags & PPEA_F_RAW_PREZEROED)) {                      // coarse scales accumulate atomically
     const FusedWorkspace fw = fused_workspace(p);
+    PPEA_TRY(cudaMemsetAsync(a.fmt_flag, 0, 16, stream));        // (the finish launch leaves it cleared for the next step)
     for (int s = 0; s < a.S; ++s)
       if (a.sc[s].hs != a.H || a.sc[s].ws != a.W) {
         PPEA_TRY(cudaMemsetAsync(a.sc[s].grad_raw, 0, sizeof(float) * fw.raw_floats[s], stream));
@@ -351,10 +375,17 @@ int ppea_vsl_fused_forward(const PpeaVslParams* p, const PpeaVslFused* f, void* 
       }
   }
   PPEA_TRACE(p, 1);
-  PPEA_TRY(launch_vsl_fused(a, stream));
-  PPEA_TRACE(p, 2);
+  if (use_tiles(p)) {
+    a.fmt_flag = nullptr;
+    PPEA_TRY(launch_vsl_fused(a, stream));
+    PPEA_TRACE(p, 2);
+  } else {
+    PPEA_TRY(launch_vsl_prep(a, stream));       // packed sources + identity loss, once for all scales
+    PPEA_TRACE(p, 2);
+    PPEA_TRY(launch_vsl_stream(a, stream));
+  }
   PPEA_TRACE(p, 3);
-  PPEA_TRY(launch_vsl_finish(a, fused_blocks(a.B, a.H, a.W), stream, (p->flags & PPEA_F_GRAD_POSE) && !(p->flags & PPEA_F_MULTI)));
+  PPEA_TRY(launch_vsl_finish(a, fused_tiles(p), stream, (p->flags & PPEA_F_GRAD_POSE) && !(p->flags & PPEA_F_MULTI)));
   PPEA_TRACE(p, 4);
   return PPEA_OK;
 }
@@ -369,7 +400,7 @@ int ppea_vsl_fused_backward(const PpeaVslParams* p, const PpeaVslGrads* g, const
   if (pose && (!g->grad_T[0] || !g->grad_T[1])) return PPEA_E_NULL;
   cudaStream_t stream = (cudaStream_t)stream_;
   VslArgs a;
-  fused_args(p, f, a);
+  fused_args(p, f, a, false);
   a.grad_losses = g->grad_losses;
   a.grad_T[0] = g->grad_T[0];
   a.grad_T[1] = g->grad_T[1];

@@ -49,19 +49,19 @@ struct SmoothChunk {
   int x, y_lo, y_hi;      // column of this thread (may be >= w), row band
   bool active;            // chunk id maps to work
 };
-__device__ __forceinline__ SmoothChunk smooth_chunk(int w, int h, int chunk) {
-  const int bd = blockDim.x;
+__device__ __forceinline__ SmoothChunk smooth_chunk(int w, int h, int chunk, int bd, int tid) {
   const int strips = (w + bd - 1) / bd;                    // <= kSmoothChunks is checked by the API (w <= 32 * 128)
   const int bands = kSmoothChunks / strips > 0 ? kSmoothChunks / strips : 1;
   const int rows = (h + bands - 1) / bands;
   SmoothChunk c;
   const int strip = chunk % strips, band = chunk / strips;
   c.active = band < bands && band * rows < h;
-  c.x = strip * bd + threadIdx.x;
+  c.x = strip * bd + tid;
   c.y_lo = band * rows;
   c.y_hi = c.y_lo + rows < h ? c.y_lo + rows : h;
   return c;
 }
+__device__ __forceinline__ SmoothChunk smooth_chunk(int w, int h, int chunk) { return smooth_chunk(w, h, chunk, blockDim.x, threadIdx.x); }
 
 struct SmoothPx {
   float d, i0, i1, i2;
@@ -142,19 +142,17 @@ __device__ __forceinline__ void smooth_forward_role(const VslArgs& a, int role, 
 //   R = sign(d - d_right) * e_right,  D = sign(d - d_down) * e_down,
 // from the same column walk (the edge weights are the forward's own), so that the backward proper is
 // elementwise:  d smooth / d d_j = inv_b * ( st_j - inv_b * (X_b / N_x + Y_b / N_y) / (h*w) )  (times upstream).
-__device__ __forceinline__ void smooth_fused_role(const VslArgs& a, int role, float* red) {
-  int s, b, chunk;
-  smooth_role_ids(a, role, s, b, chunk);
+// the column walk of one (virtual) thread `tid` of a `bd`-wide chunk CTA; adds its share to (sd, sx, sy)
+__device__ __forceinline__ void smooth_fused_walk(const VslArgs& a, int s, int b, int chunk, int bd, int tid, float& sd, float& sx, float& sy) {
   const ScaleArgs& sc = a.sc[s];
   const int h = sc.hs, w = sc.ws;
   const unsigned n = (unsigned)(h * w);
   const float* d = sc.disp + (size_t)b * n;
   const float* img = sc.color + (size_t)b * 3 * n;
   float* st = sc.grad_st + (size_t)b * n;
-  const SmoothChunk ck = smooth_chunk(w, h, chunk);
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const SmoothChunk ck = smooth_chunk(w, h, chunk, bd, tid);
+  const int lane = tid & 31;
   const float cx = w > 1 ? 1.f / ((float)a.B * h * (w - 1)) : 0.f, cy = h > 1 ? 1.f / ((float)a.B * (h - 1) * w) : 0.f;
-  float sd = 0.f, sx = 0.f, sy = 0.f;
   if (ck.active) {
     const bool xin = ck.x < w, has_r = ck.x + 1 < w, has_l = xin && ck.x > 0;
     SmoothPx cur = smooth_load(d, img, n, (unsigned)(ck.y_lo * w + ck.x), xin);
@@ -191,6 +189,14 @@ __device__ __forceinline__ void smooth_fused_role(const VslArgs& a, int role, fl
       cur = nxt;
     }
   }
+}
+
+__device__ __forceinline__ void smooth_fused_role(const VslArgs& a, int role, float* red) {
+  int s, b, chunk;
+  smooth_role_ids(a, role, s, b, chunk);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float sd = 0.f, sx = 0.f, sy = 0.f;
+  smooth_fused_walk(a, s, b, chunk, blockDim.x, threadIdx.x, sd, sx, sy);
   sd = warp_sum(sd);
   sx = warp_sum(sx);
   sy = warp_sum(sy);
@@ -205,6 +211,24 @@ __device__ __forceinline__ void smooth_fused_role(const VslArgs& a, int role, fl
     for (int k = 0; k < nw; ++k) t += red[threadIdx.x * nw + k];
     a.smooth_ws[(((size_t)s * a.B + b) * kSmoothChunks + chunk) * 3 + threadIdx.x] = t;
   }
+}
+
+// The same role run by ONE warp (a 32-thread CTA of the streaming kernel): the warp plays the four warps of a
+// kSmoothThreads-wide chunk CTA one after the other; same chunk geometry, same per-warp sums, same order of addition.
+__device__ __forceinline__ void smooth_fused_role_warp(const VslArgs& a, int role) {
+  int s, b, chunk;
+  smooth_role_ids(a, role, s, b, chunk);
+  const int lane = threadIdx.x & 31;
+  float tot[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+  for (int sub = 0; sub < kSmoothThreads / 32; ++sub) {
+    float sd = 0.f, sx = 0.f, sy = 0.f;
+    smooth_fused_walk(a, s, b, chunk, kSmoothThreads, sub * 32 + lane, sd, sx, sy);
+    tot[0] += warp_sum(sd);
+    tot[1] += warp_sum(sx);
+    tot[2] += warp_sum(sy);
+  }
+  if (lane < 3) a.smooth_ws[(((size_t)s * a.B + b) * kSmoothChunks + chunk) * 3 + lane] = lane == 0 ? tot[0] : (lane == 1 ? tot[1] : tot[2]);
 }
 
 // Backward role: smoothness gradient of one chunk.  MODE 0: overwrite grad_disp;  1: atomically add into a

@@ -59,6 +59,10 @@ struct VslArgs {
   // fused step: TMA descriptors of the colour frames viewed as (B*3, H, W) fp32 tensors, box 3 x (TH+4) x (TW+8)
   // (valid when use_tma; interior tiles are staged by cp.async.bulk.tensor, border tiles by the reflecting loop)
   int use_tma;
+  // streaming step (vsl_stream.cu): per-step products of the preparation launch
+  uint32_t* pk[2];      // (B,H,W) source frames packed to one RGBA8 word per pixel (exact when the frames are k/255)
+  float* ident;         // (B,H,W) identity loss min_f photo(src_f, tgt) (trainer.py:1060-1069), scale-invariant
+  unsigned* fmt_flag;   // != 0 after the preparation launch: some source value is not exactly k/255 -> planar fp32 gathers
   alignas(64) CUtensorMap tm_tgt;
   alignas(64) CUtensorMap tm_src[2];
 };
@@ -81,6 +85,10 @@ constexpr int kSmoothThreads = 128;
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+#ifndef PPEA_STREAM_SEG
+#define PPEA_STREAM_SEG 48
+#endif
+#define PPEA_STREAM_SEG_ROWS PPEA_STREAM_SEG
 inline int fwd_blocks(int B, int H, int W) { return B * ceil_div(W, kFwdTileW) * ceil_div(H, kFwdTileH); }
 inline int bwd_blocks(int B, int H, int W) { return B * ceil_div(W, kBwdTileW) * ceil_div(H, kBwdTileH); }
 __host__ __device__ inline int sums_stride(int B) { return PPEA_SUMS_PER_SCALE + 4 * B; }
@@ -92,7 +100,9 @@ struct FwdWorkspace {
 inline FwdWorkspace fwd_workspace(int B, int H, int W, int S) {
   FwdWorkspace w;
   w.off_partials = 0;
-  w.off_smooth = align_up((size_t)fwd_blocks(B, H, W) * S * 4, 4);
+  const int stream = B * ceil_div(W, 28) * ceil_div(H, PPEA_STREAM_SEG_ROWS);     // warp tasks of the streaming step (vsl_stream.cu)
+  const int nblk = fwd_blocks(B, H, W) > stream ? fwd_blocks(B, H, W) : stream;
+  w.off_smooth = align_up((size_t)nblk * S * 4, 4);
   w.total_floats = w.off_smooth + (size_t)S * B * kSmoothChunks * 3;
   return w;
 }
@@ -126,6 +136,14 @@ cudaError_t launch_smooth_backward(const VslArgs& a, cudaStream_t stream);
 cudaError_t launch_upsample_gather(const VslArgs& a, cudaStream_t stream);
 cudaError_t launch_pose_finish(const VslArgs& a, int nblk_bwd, cudaStream_t stream);
 cudaError_t launch_vsl_fused(const VslArgs& a, cudaStream_t stream);
+// streaming step (vsl_stream.cu): warp-per-strip row walk, no CTA barriers; tiles_x/tiles_y = strips / row segments
+constexpr int kStripW = 28;           // output columns per warp (32 gathered, 30 decided)
+constexpr int kSegRows = PPEA_STREAM_SEG;   // output rows per warp task
+inline int stream_strips(int W) { return ceil_div(W, kStripW); }
+inline int stream_segs(int H) { return ceil_div(H, kSegRows); }
+inline int stream_tiles(int B, int H, int W) { return B * stream_strips(W) * stream_segs(H); }
+cudaError_t launch_vsl_prep(const VslArgs& a, cudaStream_t stream);
+cudaError_t launch_vsl_stream(const VslArgs& a, cudaStream_t stream);
 cudaError_t launch_vsl_grad_finish(const VslArgs& a, cudaStream_t stream);
 
 // Programmatic dependent launch (sm_90+): a kernel launched with launch_pdl may become resident while its

@@ -429,6 +429,7 @@ __global__ void __launch_bounds__(kFinishThreads) vsl_finish_kernel(const __grid
       total += loss;
     }
     a.losses[0] = total / (float)a.total_scales;
+    if (a.fmt_flag) *a.fmt_flag = 0u;      // streaming step: the main launch has consumed the format flag; clear it for the next step
   }
 }
 

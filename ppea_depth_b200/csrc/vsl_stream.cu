@@ -1,0 +1,777 @@
+// vsl_stream.cu -- the training step of the view-synthesis loss as a WARP-STREAMING kernel: forward
+// products and un-normalised gradient fields of every pyramid scale (same contract as vsl_fused.cu,
+// same C entry points), organised so that no window tap is ever re-read and no CTA barrier exists.
+//
+// Why (round-1 ncu of the tile kernel, profiles/README.md r1j): 1 500 lane-instructions per pixel and
+// scale, every SSIM tap a shared-memory load (nine per window and channel, the three row sums of a
+// window recomputed for every q), eight barriers per scale, 4 x 57 KB of shared memory starving the
+// L1 that serves the gathers, a 70 KB loop body.  Here:
+//
+//   * a WARP owns a strip of 32 image columns (lane == column) and walks DOWN the rows of its
+//     segment; a warp task is (image, scale, strip, row segment).  Warps never talk to each other:
+//     no __syncthreads, no shared tile.
+//   * every quantity is produced exactly once per (row, lane) and carried in registers: the warped
+//     samples of a row, their horizontal 3-tap sums (x, x^2, x y per channel, both sources packed in
+//     one f32x2), the target's row sums.  The 3x3 window sum is (row r-2) + (row r-1) + (row r) of
+//     register-resident row sums -- two adds per quantity instead of eight adds + nine loads.
+//     Horizontal neighbours come by warp shuffle (lanes 0 / 31 are the strip's halo columns, so a
+//     strip yields 30 decided and 28 output columns).
+//   * the pipeline is skewed by one row per stage: iteration r gathers row r, decides row r-1
+//     (SSIM + L1 of both sources, min / selec_reproj / automask, SSIM adjoint coefficients) and
+//     folds / chains row r-2 (3x3 box sums of the coefficients -> dL/d warped -> dL/d(u,v) ->
+//     projection adjoint -> dL/d disp -> upsample adjoint, pose partials).  The two-row register
+//     rings alternate between two named slots (loop unrolled by two), so nothing is ever moved.
+//   * what does not depend on the scale is computed once per step by a small preparation launch
+//     (vsl_prep_kernel): the identity-reprojection loss map (trainer.py:1060-1069) and the source
+//     frames packed to ONE 32-bit RGBA8 word per pixel -- the loss frames are ToTensor of uint8 images
+//     (datasets/mono_dataset.py:62,106), i.e. exactly k/255, which the kernel verifies value by value
+//     (fmt_flag); a bilinear corner is then one 32-bit load for three channels instead of three, and
+//     the gather footprint shrinks 3x.  Frames that are not k/255 take the planar fp32 gathers
+//     (same kernel, warp-uniform branch) -- results then match the tile kernel bit for bit.
+//   * the adjoint of the bilinear upsample is aggregated in registers while the walk stays on the
+//     same coarse row, so a coarse scale issues 1 / 0.5 / 0.25 atomics per pixel instead of 4.
+//
+// Arithmetic (vsl_math.cuh) and summation order of the window sums are those of the tile kernel:
+// the per-pixel maps are bit-identical on the planar path.
+#include "vsl_common.cuh"
+#include <type_traits>
+
+#include "smooth.cuh"
+#include "vsl_gather.cuh"
+
+namespace ppea {
+
+// One warp per CTA: the task then derives from blockIdx alone, so everything per task (image / scale base pointers,
+// segment bounds, flags) lives in UNIFORM registers instead of costing two vector registers per pointer.
+#ifndef PPEA_STREAM_WARPS
+#define PPEA_STREAM_WARPS 1
+#endif
+#ifndef PPEA_STREAM_CTAS
+#define PPEA_STREAM_CTAS 8
+#endif
+constexpr int kStreamWarps = PPEA_STREAM_WARPS;
+constexpr int kStreamThreads = 32 * kStreamWarps;
+constexpr int kPrepSegRows = 16;      // rows per warp task of the preparation launch
+constexpr int kPrepStripW = 30;       // decided columns per warp there
+
+__device__ __forceinline__ f2 shfl_up2(f2 v) {
+  return mk2(__shfl_up_sync(0xffffffffu, v.x, 1), __shfl_up_sync(0xffffffffu, v.y, 1));
+}
+__device__ __forceinline__ f2 shfl_down2(f2 v) {
+  return mk2(__shfl_down_sync(0xffffffffu, v.x, 1), __shfl_down_sync(0xffffffffu, v.y, 1));
+}
+
+// -(t) * sign(d) without conversions:  d > 0 -> -t,  d < 0 -> +t,  d == 0 -> 0   (one LOP3 + compare + select)
+__device__ __forceinline__ float neg_signed(float t, float d) {
+  const float r = __uint_as_float(__float_as_uint(t) ^ (~__float_as_uint(d) & 0x80000000u));
+  return d == 0.f ? 0.f : r;
+}
+
+// SSIM + L1 of both sources (lanes of the f2) for ONE channel from its 3x3 window sums; xc / yc are the
+// window centres.  With ADJ also the adjoint coefficients (cA, cB, cC) of this channel.  Same expressions, in
+// the same order, as photo_q of the tile kernel; `w_ssim` is PPEA_W_SSIM, or 0 with opt.no_ssim (then the
+// SSIM term adds an exact zero and the coefficients vanish: no branch).
+template <bool ADJ>
+__device__ __forceinline__ void photo_channel(f2 Sx, f2 Sxx, f2 Sxy, float Sy, float Syy, f2 xc, float yc, float w_ssim, float w_l1,
+                                              f2& L, f2& cs, f2* __restrict__ co) {
+  const f2 d = vsub(dup2(yc), xc);
+  L.x = fma_rn(w_l1, fabsf(d.x), L.x);
+  L.y = fma_rn(w_l1, fabsf(d.y), L.y);
+  cs = vadd(cs, xc);
+  const SsimYT<f2> yst = ssim_y_stats<f2>(dup2(Sy), dup2(Syy));
+  const SsimTermsT<f2> t = ssim_terms<f2>(Sx, Sxx, Sxy, yst);
+  const f2 inv_d = vrcp(vmul(t.d1, t.d2));
+  const f2 R = vmul(vmul(t.n1, t.n2), inv_d);
+  const f2 v = vfma(dup2(-0.5f), R, dup2(0.5f));
+  L = vfma(dup2(w_ssim), mk2(clamp01(v.x), clamp01(v.y)), L);
+  if (ADJ) {
+    // torch.clamp passes the gradient where 0 <= v <= 1 (inclusive), i.e. |R| <= 1  (v = (1 - R) / 2 is exact enough:
+    // every float R > 1 gives v <= -2^-24)
+    f2 k = vmul(dup2(-0.5f * w_ssim), inv_d);
+    k = mk2(fabsf(R.x) <= 1.f ? k.x : 0.f, fabsf(R.y) <= 1.f ? k.y : 0.f);
+    const f2 p = vmul(vmul(dup2(2.f), yst.s), vsub(t.n2, t.n1));
+    const f2 q = vmul(vmul(vmul(dup2(2.f), R), Sx), vsub(t.d2, t.d1));
+    co[0] = vmul(k, vsub(p, q));
+    co[1] = vmul(k, vmul(vmul(dup2(-18.f), R), t.d1));
+    co[2] = vmul(k, vmul(dup2(18.f), t.n1));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Packed RGBA8 gathers.  A source pixel is one word r | g << 8 | b << 16 (k = round(255 x), exact for
+// ToTensor frames).  A byte becomes a float through the mantissa: PRMT builds 0x4B0000kk = 2^23 + k,
+// one packed add removes 2^23 for both sources.  The blend runs on k; the 1/255 is folded into the
+// row weights, so  val = sum_i w_i k_i / 255  (the reference blends fl(k/255): same number to 1 ulp).
+// The eight loads of a row are ISSUED one iteration ahead of their use (RowFetch), so the L2 latency of
+// the gather is covered by a whole row of arithmetic.
+// ---------------------------------------------------------------------------------------------------
+template <int C>
+__device__ __forceinline__ f2 unpack2(unsigned wa, unsigned wb, unsigned k4b) {
+  unsigned pa, pb;      // (selector as an immediate, the 2^23 pattern in ONE register: ptxas otherwise spends a register per selector)
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(pa) : "r"(wa), "r"(k4b), "n"(0x7540 | C));
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(pb) : "r"(wb), "r"(k4b), "n"(0x7540 | C));
+  return vadd(mk2(__uint_as_float(pa), __uint_as_float(pb)), dup2(-8388608.f));
+}
+
+struct RowFetch {
+  unsigned a_nw, a_ne, a_sw, a_se, b_nw, b_ne, b_sw, b_se;   // corner words of source 0 / source 1
+  f2 tx, ty;         // fractional sampling position
+  unsigned clip;     // bit 0 / 1: u inside the image (source 0 / 1), bit 2 / 3: v inside  (GridSampler.h clip_coordinates_set_grad)
+  float d;           // depth of the pixel
+};
+
+__device__ __forceinline__ void fetch_packed(const uint32_t* s0, const uint32_t* s1, int W, const ProjT<f2>& pr, float wm1, float hm1,
+                                             float d, RowFetch& rf) {
+  const FloorIF x0 = floor_if(pr.ix.x), x1 = floor_if(pr.ix.y), y0 = floor_if(pr.iy.x), y1 = floor_if(pr.iy.y);
+  const unsigned o0 = (unsigned)(y0.i * W + x0.i), o1 = (unsigned)(y1.i * W + x1.i), uW = (unsigned)W;
+  const uint32_t* p0 = s0 + o0;
+  const uint32_t* p1 = s1 + o1;
+  const uint32_t* q0 = s0 + (o0 + uW);
+  const uint32_t* q1 = s1 + (o1 + uW);
+  rf.a_nw = __ldg(p0), rf.a_ne = __ldg(p0 + 1), rf.a_sw = __ldg(q0), rf.a_se = __ldg(q0 + 1);
+  rf.b_nw = __ldg(p1), rf.b_ne = __ldg(p1 + 1), rf.b_sw = __ldg(q1), rf.b_se = __ldg(q1 + 1);
+  rf.tx = vsub(pr.ix, mk2(x0.f, x1.f));
+  rf.ty = vsub(pr.iy, mk2(y0.f, y1.f));
+  rf.clip = ((pr.u.x > 0.f && pr.u.x < wm1) ? 1u : 0u) | ((pr.u.y > 0.f && pr.u.y < wm1) ? 2u : 0u) |
+            ((pr.v.x > 0.f && pr.v.x < hm1) ? 4u : 0u) | ((pr.v.y > 0.f && pr.v.y < hm1) ? 8u : 0u);
+  rf.d = d;
+}
+
+__device__ __forceinline__ void blend_packed(const RowFetch& rf, unsigned k4b, f2 (&val)[3], f2 (&ddx)[3], f2 (&ddy)[3]) {
+  constexpr float kInv255 = 1.f / 255.f;
+  const f2 tx = rf.tx, ty = rf.ty;
+  const f2 ex = vsub(dup2(1.f), tx);
+  const f2 tys = vmul(ty, dup2(kInv255));                      // rows carry the 1/255
+  const f2 eys = vfma(ty, dup2(-kInv255), dup2(kInv255));      // (1 - ty) / 255
+  const f2 wnw = vmul(eys, ex), wne = vmul(eys, tx), wsw = vmul(tys, ex), wse = vmul(tys, tx);
+  const f2 mx = mk2((rf.clip & 1u) ? 1.f : 0.f, (rf.clip & 2u) ? 1.f : 0.f);
+  const f2 my = mk2((rf.clip & 4u) ? kInv255 : 0.f, (rf.clip & 8u) ? kInv255 : 0.f);
+  const f2 eym = vmul(eys, mx), tym = vmul(tys, mx), exm = vmul(ex, my), txm = vmul(tx, my);
+#define PPEA_PACKED_CHANNEL(C)                                                                                     \
+  {                                                                                                                \
+    const f2 nw = unpack2<C>(rf.a_nw, rf.b_nw, k4b), ne = unpack2<C>(rf.a_ne, rf.b_ne, k4b),                        \
+             sw = unpack2<C>(rf.a_sw, rf.b_sw, k4b), se = unpack2<C>(rf.a_se, rf.b_se, k4b);                        \
+    val[C] = vfma(se, wse, vfma(sw, wsw, vfma(ne, wne, vmul(nw, wnw))));                                            \
+    ddx[C] = vfma(vsub(se, sw), tym, vmul(vsub(ne, nw), eym));                                                     \
+    ddy[C] = vfma(vsub(se, ne), txm, vmul(vsub(sw, nw), exm));                                                     \
+  }
+  PPEA_PACKED_CHANNEL(0)
+  PPEA_PACKED_CHANNEL(1)
+  PPEA_PACKED_CHANNEL(2)
+#undef PPEA_PACKED_CHANNEL
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Preparation launch, once per step (everything here is independent of the scale, of disp and of T):
+//   * packs both source frames to RGBA8 words and verifies value by value that the packing is exact
+//     (fmt_flag is raised otherwise; the main launch then gathers from the planar fp32 frames);
+//   * identity loss  min_f photo(src_f, tgt)  (trainer.py:1060-1069) of every pixel, with the same
+//     streaming window sums as the main kernel (forward only).
+// A warp task = (image, strip of 30 decided columns, segment of kPrepSegRows rows); the nine loads of a
+// row are issued one row ahead.
+// ---------------------------------------------------------------------------------------------------
+// k = round(255 v) and whether v is EXACTLY fl(k / 255), ToTensor's value for the byte k.  fl(k / 255) is
+// formed without a division: q = k * fl(1/255), then one Newton correction fma(fma(-q, 255, k), fl(1/255), q),
+// which equals the IEEE quotient for every k in 0..255 (checked exhaustively, tests/test_host.py).
+__device__ __forceinline__ unsigned byte_of(float v, bool& exact) {
+  constexpr float r = 1.f / 255.f;
+  const float k = fminf(fmaxf(rintf(v * 255.f), 0.f), 255.f);
+  const float q = mul_rn(k, r);
+  const float q2 = fma_rn(fma_rn(-q, 255.f, k), r, q);
+  exact = exact && (q2 == v);
+  return (unsigned)__float2int_rn(k);
+}
+__device__ __forceinline__ unsigned pack_rgb(float r, float g, float b, bool& exact) {
+  return byte_of(r, exact) | (byte_of(g, exact) << 8) | (byte_of(b, exact) << 16);
+}
+
+struct PrepRow {
+  float y[3];
+  f2 x[3];
+};
+
+__global__ void __launch_bounds__(128) vsl_prep_kernel(const __grid_constant__ VslArgs a, int strips, int segs) {
+  grid_launch_dependents();      // the main launch may take idle SMs early (it waits for our results where it needs them)
+  const int lane = threadIdx.x & 31;
+  int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= a.B * strips * segs) return;
+  const int strip = t % strips;
+  t /= strips;
+  const int seg = t % segs;
+  const int b = t / segs;
+  const int H = a.H, W = a.W;
+  const unsigned plane = (unsigned)(H * W);
+  const bool automask = !(a.flags & PPEA_F_MULTI) && (a.flags & PPEA_F_AUTOMASK);
+  const bool no_ssim = a.flags & PPEA_F_NO_SSIM;
+  const float l1w = no_ssim ? (1.f / 3.f) : PPEA_W_L1, w_ssim = no_ssim ? 0.f : PPEA_W_SSIM;
+  const int x0 = strip * kPrepStripW - 1, gx = x0 + lane;
+  const int px = reflect_index(gx, W);
+  const bool own_col = lane >= 1 && lane <= 30 && gx < W;      // (gx >= 0 for lane >= 1)
+  const int y0 = seg * kPrepSegRows, y1 = min(y0 + kPrepSegRows, H);
+  const float* tgt_b = a.tgt + (size_t)b * 3 * plane;
+  const float* s0_b = a.src[0] + (size_t)b * 3 * plane;
+  const float* s1_b = a.src[1] + (size_t)b * 3 * plane;
+  uint32_t* pk0 = a.pk[0] + (size_t)b * plane;
+  uint32_t* pk1 = a.pk[1] + (size_t)b * plane;
+  float* ident_b = a.ident + (size_t)b * plane;
+
+  f2 hx[2][9], xr[2][3];
+  float yh[2][6], ycr[2][3];
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+#pragma unroll
+    for (int e = 0; e < 9; ++e) hx[p][e] = dup2(0.f);
+#pragma unroll
+    for (int e = 0; e < 3; ++e) xr[p][e] = dup2(0.f), ycr[p][e] = 0.f;
+#pragma unroll
+    for (int e = 0; e < 6; ++e) yh[p][e] = 0.f;
+  }
+  bool exact = true;
+
+  auto load_row = [&](int gi, PrepRow& r) {
+    const unsigned o = (unsigned)reflect_index(gi, H) * (unsigned)W + (unsigned)px;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      r.y[c] = __ldg(tgt_b + (c * plane + o));
+      r.x[c] = mk2(__ldg(s0_b + (c * plane + o)), __ldg(s1_b + (c * plane + o)));
+    }
+  };
+  const int g_lo = automask ? y0 - 1 : y0, g_hi = automask ? y1 : y1 - 1;
+  PrepRow nxt;
+  load_row(g_lo, nxt);
+
+  auto step = [&](auto par, const int gi) {
+    constexpr int P = decltype(par)::value, Q = 1 - P;
+    const PrepRow cur = nxt;
+    load_row(gi + 1 <= g_hi ? gi + 1 : gi, nxt);       // next row in flight while this one is processed
+    if (gi >= y0 && gi < y1) {                         // (then the row is not a reflected one)
+      const unsigned w0 = pack_rgb(cur.x[0].x, cur.x[1].x, cur.x[2].x, exact), w1 = pack_rgb(cur.x[0].y, cur.x[1].y, cur.x[2].y, exact);
+      if (own_col) {
+        pk0[(unsigned)gi * (unsigned)W + (unsigned)gx] = w0;
+        pk1[(unsigned)gi * (unsigned)W + (unsigned)gx] = w1;
+      }
+    }
+    if (!automask) return;
+    f2 hxn[9];
+    float yhn[6];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float yl = __shfl_up_sync(0xffffffffu, cur.y[c], 1), yr = __shfl_down_sync(0xffffffffu, cur.y[c], 1);
+      row_sums_y<float>(yl, cur.y[c], yr, yhn[2 * c], yhn[2 * c + 1]);
+      const f2 xl = shfl_up2(cur.x[c]), xrt = shfl_down2(cur.x[c]);
+      row_sums_x<f2>(xl, cur.x[c], xrt, dup2(yl), dup2(cur.y[c]), dup2(yr), hxn[3 * c], hxn[3 * c + 1], hxn[3 * c + 2]);
+    }
+    const int qi = gi - 1;
+    if (qi >= y0) {                                    // (qi < y1 by the loop bounds)
+      f2 L = dup2(0.f), cs = dup2(0.f);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const f2 Sx = vadd(vadd(hx[P][3 * c], hx[Q][3 * c]), hxn[3 * c]);
+        const f2 Sxx = vadd(vadd(hx[P][3 * c + 1], hx[Q][3 * c + 1]), hxn[3 * c + 1]);
+        const f2 Sxy = vadd(vadd(hx[P][3 * c + 2], hx[Q][3 * c + 2]), hxn[3 * c + 2]);
+        const float Sy = add_rn(add_rn(yh[P][2 * c], yh[Q][2 * c]), yhn[2 * c]);
+        const float Syy = add_rn(add_rn(yh[P][2 * c + 1], yh[Q][2 * c + 1]), yhn[2 * c + 1]);
+        photo_channel<false>(Sx, Sxx, Sxy, Sy, Syy, xr[Q][c], ycr[Q][c], w_ssim, l1w, L, cs, nullptr);
+      }
+      if (own_col) ident_b[(unsigned)qi * (unsigned)W + (unsigned)gx] = fminf(L.x, L.y);
+    }
+#pragma unroll
+    for (int e = 0; e < 9; ++e) hx[P][e] = hxn[e];
+#pragma unroll
+    for (int e = 0; e < 6; ++e) yh[P][e] = yhn[e];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) xr[P][c] = cur.x[c], ycr[P][c] = cur.y[c];
+  };
+#pragma unroll 1
+  for (int gi = g_lo; gi <= g_hi; gi += 2) {
+    step(std::integral_constant<int, 0>{}, gi);
+    if (gi + 1 <= g_hi) step(std::integral_constant<int, 1>{}, gi + 1);
+  }
+  if (!__all_sync(0xffffffffu, exact) && lane == 0) *a.fmt_flag = 1u;
+}
+
+cudaError_t launch_vsl_prep(const VslArgs& a, cudaStream_t stream) {
+  const int strips = ceil_div(a.W, kPrepStripW), segs = ceil_div(a.H, kPrepSegRows);
+  const int tasks = a.B * strips * segs;
+  vsl_prep_kernel<<<ceil_div(tasks, 4), 128, 0, stream>>>(a, strips, segs);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Deterministic mode: 64-bit fixed-point accumulation of the coarse-scale fields (see vsl_fused.cu).
+// ---------------------------------------------------------------------------------------------------
+constexpr float kFixScaleS = 1099511627776.f;          // 2^40
+__device__ __forceinline__ void fixed_add_s(float* field, unsigned idx, float v) {
+  const long long q = __float2ll_rn(fminf(fmaxf(v, -8.3e6f), 8.3e6f) * kFixScaleS);
+  atomicAdd(reinterpret_cast<unsigned long long*>(field) + idx, (unsigned long long)q);
+}
+template <bool DET>
+__device__ __forceinline__ void field_add(float* field, unsigned idx, float v) {
+  if (v == 0.f) return;
+  if (DET)
+    fixed_add_s(field, idx, v);
+  else
+    atomicAdd(field + idx, v);
+}
+
+// Adjoint of the bilinear upsample of one column, aggregated while the walk stays on the same pair of coarse
+// rows (cur, cur + 1): a full-resolution pixel adds into four register accumulators, and a coarse row is
+// flushed (two atomics) only when the walk leaves it.
+template <bool DET>
+struct UpAgg {
+  float a00, a01, a10, a11;
+  int cur;
+  __device__ __forceinline__ void init(int i0) {
+    a00 = a01 = a10 = a11 = 0.f;
+    cur = i0;
+  }
+  __device__ __forceinline__ void flush_row0(float* field, int ws, const UpCoef& cx, bool own) {
+    if (own) {
+      field_add<DET>(field, (unsigned)(cur * ws + cx.i0), a00);
+      field_add<DET>(field, (unsigned)(cur * ws + cx.i1), a01);
+    }
+  }
+  // cy is warp-uniform (the row), cx this lane's column
+  __device__ __forceinline__ void add(float* field, int ws, float g, const UpCoef& cy, const UpCoef& cx, bool own) {
+    if (cy.i0 != cur) {          // (warp-uniform; the coarse row index grows by at most one per full-resolution row)
+      flush_row0(field, ws, cx, own);
+      a00 = a10, a01 = a11;
+      a10 = a11 = 0.f;
+      cur = cy.i0;
+    }
+    const float t0 = g * cy.l0, t1 = g * cy.l1;
+    a00 = fmaf(t0, cx.l0, a00);
+    a01 = fmaf(t0, cx.l1, a01);
+    if (cy.i1 != cy.i0) {
+      a10 = fmaf(t1, cx.l0, a10);
+      a11 = fmaf(t1, cx.l1, a11);
+    } else {                     // bottom border: both taps are the last coarse row
+      a00 = fmaf(t1, cx.l0, a00);
+      a01 = fmaf(t1, cx.l1, a01);
+    }
+  }
+  __device__ __forceinline__ void finish(float* field, int ws, int hs, const UpCoef& cx, bool own) {
+    flush_row0(field, ws, cx, own);
+    if (own && cur + 1 < hs) {
+      field_add<DET>(field, (unsigned)((cur + 1) * ws + cx.i0), a10);
+      field_add<DET>(field, (unsigned)((cur + 1) * ws + cx.i1), a11);
+    }
+  }
+};
+
+// an image base pointer the optimiser cannot see through: every address formed from it is ONE IMAD.WIDE.U32 of a
+// 32-bit element offset instead of a 64-bit add chain per access
+template <class T>
+__device__ __forceinline__ const T* opaque_base(const T* p) {
+  unsigned long long v = reinterpret_cast<unsigned long long>(p);
+  asm volatile("" : "+l"(v));
+  return reinterpret_cast<const T*>(v);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Main launch.  grid = one CTA (one warp) per task, then the S*B*32 smoothness role CTAs.
+// Iteration gi:  issue the loads of row gi+1 (gather corners, target, noise / identity loss of the row
+// decided next) -> blend row gi from the words fetched one iteration ago -> row sums -> decide row
+// gi-1 -> fold + chain row gi-2.
+// ---------------------------------------------------------------------------------------------------
+template <bool POSE, bool MULTI, bool DET>
+__global__ void __launch_bounds__(kStreamThreads, PPEA_STREAM_CTAS) vsl_stream_kernel(const __grid_constant__ VslArgs a, int n_task_ctas) {
+  // per warp: ring of three rows of bilinear derivatives (d warped_c / d(u,v), 12 floats per lane and row) and the
+  // folded projection of the image (vsl_math.cuh Geom, lanes = sources)
+  __shared__ float4 s_dd[kStreamWarps][3][3][32];
+  __shared__ f2 s_G[kStreamWarps][12];
+
+  grid_launch_dependents();      // the dependent is the small finish kernel: let it take its place early
+  if ((int)blockIdx.x >= n_task_ctas) {
+    // smoothness roles: the LAST CTAs of the grid (short; they fill the tail).  Independent of the preparation launch.
+    if (kStreamWarps == 1)
+      smooth_fused_role_warp(a, blockIdx.x - n_task_ctas);
+    else
+      smooth_fused_role(a, blockIdx.x - n_task_ctas, reinterpret_cast<float*>(&s_dd[0][0][0][0]));
+    return;
+  }
+  const int lane = threadIdx.x & 31, wid = kStreamWarps == 1 ? 0 : threadIdx.x >> 5;
+  const int strips = a.tiles_x, segs = a.tiles_y;
+  int t = blockIdx.x * kStreamWarps + wid;
+  if (t >= a.B * strips * segs * a.S) return;          // (whole warp; nothing below synchronises across warps)
+  const int s = t % a.S;
+  t /= a.S;
+  const int strip = t % strips;
+  t /= strips;
+  const int seg = t % segs;
+  const int b = t / segs;
+  const int tile_id = (b * segs + seg) * strips + strip;
+
+  const int H = a.H, W = a.W;
+  const unsigned plane = (unsigned)(H * W), uW = (unsigned)W;
+  const ScaleArgs& sc = a.sc[s];
+  const int hs = sc.hs, ws = sc.ws;
+  const bool same_res = (hs == H && ws == W);
+  const bool automask = !MULTI && (a.flags & PPEA_F_AUTOMASK);
+  const bool motion = MULTI && (a.flags & PPEA_F_MOTION_MASK);
+  const float one_minus_aug = (MULTI && (a.flags & PPEA_F_MATCH_AUG)) ? 1.f - a.aug_mask[b] : 1.f;
+  const bool no_ssim = a.flags & PPEA_F_NO_SSIM;
+  const bool selec = a.flags & PPEA_F_SELEC_REPROJ;
+  const float l1w = no_ssim ? (1.f / 3.f) : PPEA_W_L1, w_ssim = no_ssim ? 0.f : PPEA_W_SSIM;
+  const bool use_noise = automask && sc.noise != nullptr;
+
+  f2* const G = s_G[wid];
+  if (lane < 24) {
+    const int f = lane / 12, e = lane % 12;
+    const float v = geom_entry(a.K + b * 16, a.T[f] + b * 16, a.inv_K + b * 16, e);
+    (f ? G[e].y : G[e].x) = v;
+  }
+  __syncwarp();
+
+  const int x0 = strip * kStripW - 2, gx = x0 + lane;
+  const bool col_in = gx >= 0 && gx < W;
+  const bool q_lane = col_in && lane >= 1 && lane <= 30;
+  const bool own_col = lane >= 2 && lane <= 29 && gx < W;
+  const int y0 = seg * kSegRows, y1 = min(y0 + kSegRows, H);
+  ColCtx cc = make_col(G, gx, W);
+  if (!same_res) cc.cx = up_coef(cc.px, ws, sc.up_sx);
+  const float wmax = coord_max(W), hmax = coord_max(H);
+  const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
+  const unsigned upx = (unsigned)cc.px, ugx = (unsigned)(col_in ? gx : 0);
+  const unsigned img0 = (unsigned)b * plane;          // first pixel of image b in the (B,1,H,W) maps (B*H*W < 2^31 is checked by the API)
+
+  const float* tgt_b = a.tgt + (size_t)b * 3 * plane;
+  const float* disp_b = sc.disp + (size_t)b * hs * ws;
+
+  grid_dependency_wait();        // packed sources, identity loss and the format flag come from the preparation launch
+  const bool packed = (*reinterpret_cast<const volatile unsigned*>(a.fmt_flag) == 0u);
+  const uint32_t* pk0 = opaque_base(a.pk[0] + (size_t)b * plane);
+  const uint32_t* pk1 = opaque_base(a.pk[1] + (size_t)b * plane);
+  const SrcPlanes sp = make_planes(a.src[0] + (size_t)b * 3 * plane, a.src[1] + (size_t)b * 3 * plane, plane);
+  // 2^23 as a bit pattern, in a register ptxas cannot fold (it would otherwise make it the immediate of every PRMT and
+  // spend a register move per byte selector): B > 0, so the shifted term is zero
+  const unsigned k4b = 0x4B000000u | ((unsigned)a.B >> 31);
+
+  // ---- register rings (slot = parity of the iteration that produced the row)
+  f2 hx[2][9];        // horizontal 3-tap sums of (x, x^2, x y) per channel, both sources
+  f2 xr[2][3];        // warped samples
+  float yh[2][6];     // horizontal sums of (y, y^2) per channel
+  float ycr[2][3];    // target values
+  f2 hc[2][9];        // horizontal (multiplicity-weighted) sums of the masked adjoint coefficients
+  f2 indr[2];         // mask(q) * [sel(q) == lane]
+  float dep[2];
+  RowFetch rf[2];     // gather of the row blended by iteration parity p
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+#pragma unroll
+    for (int e = 0; e < 9; ++e) hx[p][e] = hc[p][e] = dup2(0.f);
+#pragma unroll
+    for (int e = 0; e < 3; ++e) xr[p][e] = dup2(0.f), ycr[p][e] = 0.f;
+#pragma unroll
+    for (int e = 0; e < 6; ++e) yh[p][e] = 0.f;
+    indr[p] = dup2(0.f);
+    dep[p] = 0.f;
+    rf[p] = RowFetch{};
+  }
+  const f2 mL = dup2((gx == 1) ? 2.f : 1.f), mR = dup2((gx == W - 2) ? 2.f : 1.f);   // reflection multiplicities (layers.py:238)
+
+  float s_rm = 0.f, s_m = 0.f, s_c = 0.f;
+  f2 Sw[POSE ? 3 : 1], Swy[POSE ? 3 : 1], Sg[POSE ? 3 : 1];
+#pragma unroll
+  for (int e = 0; e < (POSE ? 3 : 1); ++e) Sw[e] = Swy[e] = Sg[e] = dup2(0.f);
+
+  const size_t img_off = (size_t)b * hs * ws;
+  float* gr_b = sc.grad_raw + (DET && !same_res ? 2 * img_off : img_off);          // (fixed-point fields: 8 bytes per pixel)
+  float* gc_b = MULTI ? sc.grad_raw2 + (DET && !same_res ? 2 * img_off : img_off) : nullptr;
+  UpAgg<DET> agg, agg2;
+  {
+    const int i0 = same_res ? 0 : up_coef(y0, hs, sc.up_sy).i0;
+    agg.init(i0);
+    agg2.init(i0);
+  }
+
+  // the (upsampled) disparity of row gi at this lane's column: loads only, issued two rows ahead of the blend
+  auto load_disp = [&](int gi) -> float {
+    const int py = reflect_index(gi, H);
+    if (same_res) return __ldg(disp_b + ((unsigned)py * uW + upx));
+    return up_sample(disp_b, ws, up_coef(py, hs, sc.up_sy), cc.cx);
+  };
+  // projection of row gi and the loads of its eight packed corners (consumed by the next iteration)
+  auto fetch_row = [&](int gi, float dup, RowFetch& r) {
+    const int py = reflect_index(gi, H);
+    const float d = depth_from_disp_fast(dup, a.disp_lo, a.disp_range);
+    f2 A[3];
+    const ProjT<f2> pr = project_cell(G, cc, py, d, a.eps, wmax, hmax, A);
+    fetch_packed(pk0, pk1, W, pr, wm1, hm1, d, r);
+  };
+  auto load_tgt = [&](int gi, float (&y)[3]) {
+    const unsigned o = (unsigned)reflect_index(gi, H) * uW + upx;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) y[c] = __ldg(tgt_b + (c * plane + o));
+  };
+  // identity loss (+ tie-break noise) / consistency mask of the row decided by the NEXT iteration
+  auto load_decide = [&](int qi, float& idv, float& nzv, float& cmv) {
+    idv = nzv = 0.f;
+    cmv = 1.f;
+    if (q_lane && qi >= 0 && qi < H) {
+      const unsigned o = img0 + (unsigned)qi * uW + ugx;
+      if (automask) idv = __ldg(a.ident + o);
+      if (use_noise) nzv = __ldg(sc.noise + o);
+      if (motion) cmv = __ldg(a.cons_mask + o);
+    }
+  };
+
+  // The row loop, specialised on the gather format and on full / coarse resolution of disp_s: only the executed copy
+  // occupies the instruction cache, and the compiler sees straight-line code.
+  auto run_rows = [&](auto packed_c) {
+  constexpr bool packed = decltype(packed_c)::value;
+  float dup_pf = load_disp(y0 - 2);
+  if (packed) fetch_row(y0 - 2, dup_pf, rf[0]);
+  dup_pf = load_disp(y0 - 1);
+  float y_pf[3];
+  load_tgt(y0 - 2, y_pf);
+  float id_pf = 0.f, nz_pf = 0.f, cm_pf = 1.f;       // (the first two iterations decide nothing that is kept)
+  int dslot = 0;                                     // ring slot the derivatives of the current row go to
+
+  // One loop body for every row (no unrolling: the body must stay inside the instruction cache; the two-row rings are
+  // (older, newer) slot pairs P / Q rotated by register moves, which issue in the shadow of the dependent arithmetic).
+  constexpr int P = 0, Q = 1;
+#pragma unroll 1
+  for (int gi = y0 - 2; gi <= y1 + 1; ++gi) {
+    // ---- loads of the next iteration
+    float yv[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) yv[c] = y_pf[c];
+    const float idv = id_pf, nzv = nz_pf, cmv = cm_pf;
+    float dup_cur = 0.f;
+    if (packed) {
+      fetch_row(gi + 1, dup_pf, rf[Q]);
+      dup_pf = load_disp(gi + 2);
+    } else {
+      dup_cur = dup_pf;
+      dup_pf = load_disp(gi + 1);
+    }
+    load_tgt(gi + 1, y_pf);
+    load_decide(gi, id_pf, nz_pf, cm_pf);
+    const int pi = gi - 2;
+    float md = 0.f, cmf = 1.f;                        // fold row: mono depth / consistency mask (multi path)
+    if (MULTI && own_col && pi >= y0) {
+      const unsigned o = img0 + (unsigned)pi * uW + ugx;
+      md = __ldg(sc.mono_depth + o);
+      if (motion) cmf = __ldg(a.cons_mask + o);
+    }
+
+    // ---- the ring slot that this iteration replaces is folded into partial sums FIRST, so that it is dead before its
+    // successor is born and the two share registers (no moves at the loop edge)
+    f2 T[9], Vp[9];
+    float Ty[6];
+    const f2 mU = dup2((pi == 1) ? 2.f : 1.f), mD = dup2((pi == H - 2) ? 2.f : 1.f);
+#pragma unroll
+    for (int e = 0; e < 9; ++e) {
+      T[e] = vadd(hx[P][e], hx[Q][e]);                 // rows gi-2, gi-1 of the window of row gi-1
+      Vp[e] = vfma(mU, hc[P][e], hc[Q][e]);            // coefficient rows gi-3 (weighted), gi-2 of the box around row gi-2
+    }
+#pragma unroll
+    for (int e = 0; e < 6; ++e) Ty[e] = add_rn(yh[P][e], yh[Q][e]);
+
+    // ---- blend row gi: bilinear samples of both sources, derivatives to the ring
+    f2 xn[3];
+    float d;
+    {
+      f2 dx[3], dy[3];
+      if (packed) {
+        blend_packed(rf[P], k4b, xn, dx, dy);
+        d = rf[P].d;
+      } else {
+        const int py = reflect_index(gi, H);
+        d = depth_from_disp_fast(dup_cur, a.disp_lo, a.disp_range);
+        f2 A[3];
+        const ProjT<f2> pr = project_cell(G, cc, py, d, a.eps, wmax, hmax, A);
+        sample_sources<true, false>(sp, W, pr, wm1, hm1, xn, dx, dy);
+      }
+      float4* ring = &s_dd[wid][dslot][0][lane];
+      ring[0] = make_float4(dx[0].x, dx[0].y, dx[1].x, dx[1].y);
+      ring[32] = make_float4(dx[2].x, dx[2].y, dy[0].x, dy[0].y);
+      ring[64] = make_float4(dy[1].x, dy[1].y, dy[2].x, dy[2].y);
+    }
+    if (gi >= y0 && gi < y1 && own_col) sc.depth[img0 + (unsigned)gi * uW + ugx] = d;   // trainer.py:893
+
+    // ---- horizontal 3-tap sums of this row
+    f2 hxn[9];
+    float yhn[6];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float yl = __shfl_up_sync(0xffffffffu, yv[c], 1), yrt = __shfl_down_sync(0xffffffffu, yv[c], 1);
+      row_sums_y<float>(yl, yv[c], yrt, yhn[2 * c], yhn[2 * c + 1]);
+      const f2 xl = shfl_up2(xn[c]), xrt = shfl_down2(xn[c]);
+      row_sums_x<f2>(xl, xn[c], xrt, dup2(yl), dup2(yv[c]), dup2(yrt), hxn[3 * c], hxn[3 * c + 1], hxn[3 * c + 2]);
+    }
+
+    // ---- decide row qi = gi - 1: loss of both sources, selection, mask, masked adjoint coefficients.
+    // (Runs in the two warm-up iterations too, on rows nobody owns: their products are never consumed.)
+    const int qi = gi - 1;
+    f2 hcn[9];
+    f2 indn = dup2(0.f);
+    {
+      f2 L = dup2(0.f), cs = dup2(0.f);
+      f2 co[9];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const f2 Sx = vadd(T[3 * c], hxn[3 * c]), Sxx = vadd(T[3 * c + 1], hxn[3 * c + 1]), Sxy = vadd(T[3 * c + 2], hxn[3 * c + 2]);
+        const float Sy = add_rn(Ty[2 * c], yhn[2 * c]), Syy = add_rn(Ty[2 * c + 1], yhn[2 * c + 1]);
+        photo_channel<true>(Sx, Sxx, Sxy, Sy, Syy, xr[Q][c], ycr[Q][c], w_ssim, l1w, L, cs, &co[3 * c]);
+      }
+      const Select sl = select_source(L.x, L.y, cs.x, cs.y, selec);
+      bool on = true;
+      float mq = 1.f;
+      if (MULTI) {
+        mq = cmv * one_minus_aug;
+      } else if (automask) {
+        const float idl = use_noise ? add_rn(idv, mul_rn(nzv, 0.00001f)) : idv;      // trainer.py:1086-1087
+        on = sl.r <= idl;                                                            // argmin([r, id]) == 0
+        mq = on ? 1.f : 0.f;
+      }
+      const bool q_ok = q_lane && qi >= 0 && qi < H;
+      if (!q_ok) mq = 0.f;
+      indn = mk2(sl.src == 0 ? mq : 0.f, sl.src == 1 ? mq : 0.f);
+      if (own_col && qi >= y0 && qi < y1) {      // owner of q: forward products
+        const unsigned o = img0 + (unsigned)qi * uW + ugx;
+        if (sc.loss_px) sc.loss_px[o] = sl.r;
+        sc.sel[o] = (uint8_t)((unsigned)sl.src | (on ? PPEA_SEL_AUTOMASK : 0u));
+        s_rm = fmaf(sl.r, mq, s_rm);
+        s_m += mq;
+      }
+      // horizontal box sums of the masked coefficients, with the reflection multiplicities of the columns
+#pragma unroll
+      for (int e = 0; e < 9; ++e) {
+        const f2 cm = vmul(co[e], indn);
+        hcn[e] = vfma(mL, shfl_up2(cm), vfma(mR, shfl_down2(cm), cm));
+      }
+    }
+
+    // ---- fold + chain row pi = gi - 2
+    if (gi >= y0 + 2 && pi < y1) {
+      const int rslot = dslot == 2 ? 0 : dslot + 1;        // (dslot + 1) % 3 == (dslot - 2) % 3
+      const float4* ring = &s_dd[wid][rslot][0][lane];
+      const float4 r0 = ring[0], r1 = ring[32], r2 = ring[64];
+      const f2 ddx[3] = {mk2(r0.x, r0.y), mk2(r0.z, r0.w), mk2(r1.x, r1.y)};
+      const f2 ddy[3] = {mk2(r1.z, r1.w), mk2(r2.x, r2.y), mk2(r2.z, r2.w)};
+      const f2 wl = vmul(indr[Q], dup2(l1w));        // (decided by the previous iteration)
+      f2 gu = dup2(0.f), gv = dup2(0.f);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const f2 xv = xr[P][c], yv2 = dup2(ycr[P][c]);
+        const f2 dd = vsub(yv2, xv);
+        // L1 term:  -ind * l1w * sign(y - x);  SSIM term from the 3x3 box sums of the coefficients (zero with no_ssim)
+        const f2 Ac = vfma(mD, hcn[3 * c], Vp[3 * c]), Bc = vfma(mD, hcn[3 * c + 1], Vp[3 * c + 1]), Cc = vfma(mD, hcn[3 * c + 2], Vp[3 * c + 2]);
+        const f2 Gc = vadd(mk2(neg_signed(wl.x, dd.x), neg_signed(wl.y, dd.y)), vfma(Bc, xv, vfma(Cc, yv2, Ac)));   // d L / d warped_c(p)
+        gu = vfma(Gc, ddx[c], gu);
+        gv = vfma(Gc, ddy[c], gv);
+      }
+      float g_dup = 0.f, c_dup = 0.f;
+      if (own_col) {       // (pi in [y0, y1) by the loop bounds)
+        f2 A[3];
+        const float depk = dep[P];
+        const ProjT<f2> pr = project_cell(G, cc, pi, depk, a.eps, wmax, hmax, A);
+        const f2 gc0 = vmul(gu, pr.rz), gc1 = vmul(gv, pr.rz);
+        const f2 gc2 = vneg(vmul(vfma(gu, pr.u, vmul(gv, pr.v)), pr.rz));
+        const f2 gd2 = vfma(gc2, A[2], vfma(gc1, A[1], vmul(gc0, A[0])));
+        const float g = gd2.x + gd2.y;
+        if (POSE) {
+          const f2 dk = dup2(depk), fy = dup2(int_to_float(pi));
+          const f2 w0 = vmul(gc0, dk), w1 = vmul(gc1, dk), w2 = vmul(gc2, dk);
+          Sw[0] = vadd(Sw[0], w0);
+          Sw[1] = vadd(Sw[1], w1);
+          Sw[2] = vadd(Sw[2], w2);
+          Swy[0] = vfma(w0, fy, Swy[0]);
+          Swy[1] = vfma(w1, fy, Swy[1]);
+          Swy[2] = vfma(w2, fy, Swy[2]);
+          Sg[0] = vadd(Sg[0], gc0);
+          Sg[1] = vadd(Sg[1], gc1);
+          Sg[2] = vadd(Sg[2], gc2);
+        }
+        const float ddd = ddepth_ddisp(depk, a.disp_range);
+        g_dup = g * ddd;
+        if (MULTI) {
+          // consistency term mean(|depth - mono_depth| * (1 - mask))  (trainer.py:1128-1132): its un-normalised
+          // gradient goes to a field of its own (its upstream weight differs from the photometric one)
+          const float om = 1.f - cmf * one_minus_aug;
+          const float dm = depk - md;
+          s_c = fmaf(fabsf(dm), om, s_c);
+          c_dup = sign_of(dm) * om * ddd;
+        }
+        if (same_res) {
+          const unsigned o0 = (unsigned)pi * uW + ugx;
+          gr_b[o0] = g_dup;     // sole owner: plain store, no pre-zero needed
+          if (MULTI) gc_b[o0] = c_dup;
+        }
+      }
+      if (!same_res) {          // (warp-uniform: the aggregation decides its flushes on the row)
+        const UpCoef cy = up_coef(pi, hs, sc.up_sy);
+        agg.add(gr_b, ws, g_dup, cy, cc.cx, own_col);
+        if (MULTI) agg2.add(gc_b, ws, c_dup, cy, cc.cx, own_col);
+      }
+    }
+
+    // ---- rotate the rings: newer -> older, this row -> newer
+#pragma unroll
+    for (int e = 0; e < 9; ++e) hx[P][e] = hx[Q][e], hx[Q][e] = hxn[e], hc[P][e] = hc[Q][e], hc[Q][e] = hcn[e];
+#pragma unroll
+    for (int e = 0; e < 6; ++e) yh[P][e] = yh[Q][e], yh[Q][e] = yhn[e];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) xr[P][c] = xr[Q][c], xr[Q][c] = xn[c], ycr[P][c] = ycr[Q][c], ycr[Q][c] = yv[c];
+    dep[P] = dep[Q], dep[Q] = d;
+    indr[P] = indr[Q], indr[Q] = indn;
+    if (packed) rf[P] = rf[Q];
+    dslot = dslot == 2 ? 0 : dslot + 1;
+  }
+  if (!same_res) {
+    agg.finish(gr_b, ws, hs, cc.cx, own_col);
+    if (MULTI) agg2.finish(gc_b, ws, hs, cc.cx, own_col);
+  }
+  };
+  if (packed)
+    run_rows(std::true_type{});
+  else
+    run_rows(std::false_type{});
+
+  // ---- task sums: masked loss sums, consistency sum, pose partials (fixed order)
+  s_rm = warp_sum(s_rm);
+  s_m = warp_sum(s_m);
+  if (MULTI) s_c = warp_sum(s_c);
+  if (lane == 0)
+    *reinterpret_cast<float4*>(a.partials + ((size_t)tile_id * a.S + s) * 4) = make_float4(s_rm, s_m, s_c, 0.f);
+  if (POSE) {
+    // per source f and row r of dL/dP: (sum gc_r*depth*x, sum gc_r*depth*y, sum gc_r*depth, sum gc_r)
+    const float fx = int_to_float(cc.px);
+    float v[24];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      v[0 * 12 + r * 4 + 0] = Sw[r].x * fx;
+      v[0 * 12 + r * 4 + 1] = Swy[r].x;
+      v[0 * 12 + r * 4 + 2] = Sw[r].x;
+      v[0 * 12 + r * 4 + 3] = Sg[r].x;
+      v[1 * 12 + r * 4 + 0] = Sw[r].y * fx;
+      v[1 * 12 + r * 4 + 1] = Swy[r].y;
+      v[1 * 12 + r * 4 + 2] = Sw[r].y;
+      v[1 * 12 + r * 4 + 3] = Sg[r].y;
+    }
+    const float tsum = warp_sum24(v, lane);
+    const int e = warp_sum24_index(lane);
+    if (e < 24) a.pose_partials[((size_t)tile_id * a.S + s) * 24 + e] = tsum;
+  }
+}
+
+template <bool POSE, bool MULTI, bool DET>
+static cudaError_t launch_vsl_stream_as(const VslArgs& a, cudaStream_t stream) {
+  const int tasks = a.B * a.tiles_x * a.tiles_y * a.S;
+  const int n_task_ctas = ceil_div(tasks, kStreamWarps);
+  const int nblk = n_task_ctas + a.S * a.B * kSmoothChunks;
+  return launch_pdl(vsl_stream_kernel<POSE, MULTI, DET>, dim3(nblk), dim3(kStreamThreads), 0, stream, a, n_task_ctas);
+}
+
+cudaError_t launch_vsl_stream(const VslArgs& a, cudaStream_t stream) {
+  const bool det = a.flags & PPEA_F_DETERMINISTIC;
+  if (a.flags & PPEA_F_MULTI)      // T is detached on the multi path (trainer.py:900-902)
+    return det ? launch_vsl_stream_as<false, true, true>(a, stream) : launch_vsl_stream_as<false, true, false>(a, stream);
+  if (a.flags & PPEA_F_GRAD_POSE)
+    return det ? launch_vsl_stream_as<true, false, true>(a, stream) : launch_vsl_stream_as<true, false, false>(a, stream);
+  return det ? launch_vsl_stream_as<false, false, true>(a, stream) : launch_vsl_stream_as<false, false, false>(a, stream);
+}
+
+}  // namespace ppea

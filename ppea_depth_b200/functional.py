@@ -52,11 +52,12 @@ class VslConfig:
     first_scale: int = 0
     total_scales: Optional[int] = None
     want_loss_px: bool = False
-    fused: Optional[bool] = None     # single-launch training step (vsl_fused.cu); None = whenever some input
-                                     # requires grad (False: forward + backward kernel pair)
+    fused: object = None             # fused training step; None / True = whenever some input requires grad: the
+                                     # warp-streaming kernel (vsl_stream.cu); "tiles" = the shared-memory tile kernel
+                                     # (vsl_fused.cu); False = the forward + backward kernel pair
 
     def use_fused(self, needs_grad):
-        return bool(needs_grad) and (self.fused is None or self.fused)
+        return bool(needs_grad) and (self.fused is None or bool(self.fused))
 
     def flags(self, grad_pose):
         f = 0
@@ -76,6 +77,8 @@ class VslConfig:
             f |= C.F_MATCH_AUG
         if grad_pose:
             f |= C.F_GRAD_POSE
+        if self.fused == "tiles":
+            f |= C.F_FUSED_TILES
         return f
 
 

@@ -12,6 +12,7 @@ addresses are baked into the graph).
 from __future__ import annotations
 
 import ctypes
+import dataclasses
 from typing import List, Optional, Sequence
 
 import torch
@@ -45,6 +46,9 @@ class FusedPlan:
         self.grad_pose = (not cfg.is_multi) if grad_pose is None else bool(grad_pose)
         # single-launch training step (vsl_fused.cu) unless the forward + backward kernel pair is asked for
         self.fused = True if fused is None else bool(fused)
+        if fused == "tiles":          # the shared-memory tile kernel of the fused step instead of the streaming kernel
+            self.cfg = cfg = dataclasses.replace(cfg, fused="tiles")
+        self.tiles = self.fused and cfg.fused == "tiles"
         f32 = dict(device=dev, dtype=torch.float32)
         with torch.cuda.device(dev):
             self.depth = [torch.empty(B, 1, H, W, **f32) for _ in range(S)]
@@ -92,6 +96,8 @@ class FusedPlan:
     # kernels launched by one forward / backward call (for bench.py's gpu_launches)
     @property
     def launches_forward(self):
+        if self.fused and not self.tiles:
+            return 3        # preparation (packed sources + identity loss), streaming step (+ smoothness CTAs), finish
         return 2            # fused forward / fused step (tiles + smoothness CTAs), finish
 
     @property
@@ -190,6 +196,7 @@ class FusedPlan:
     FWD_STAGES = ("fwd_unused0", "vsl_forward_kernel", "fwd_unused1", "finish")
     BWD_STAGES = ("grad_init", "vsl_backward_kernel", "upsample_gather", "pose_finish")
     FUSED_FWD_STAGES = ("grad_raw_zero", "vsl_fused_kernel", "fwd_unused1", "finish")
+    STREAM_FWD_STAGES = ("grad_raw_zero", "vsl_prep_kernel", "vsl_stream_kernel", "finish")
     FUSED_BWD_STAGES = ("bwd_unused0", "vsl_grad_finish_kernel", "bwd_unused1", "bwd_unused2")
 
     def enable_trace(self):
@@ -218,6 +225,8 @@ class FusedPlan:
         out = {}
         ms = ctypes.c_float()
         stages = (self.FUSED_FWD_STAGES, self.FUSED_BWD_STAGES) if self.fused else (self.FWD_STAGES, self.BWD_STAGES)
+        if self.fused and not self.tiles:
+            stages = (self.STREAM_FWD_STAGES, self.FUSED_BWD_STAGES)
         for arr, names in zip(self._ev, stages):
             for i, name in enumerate(names):
                 C.check(self._lib.ppea_event_elapsed_ms(arr[i], arr[i + 1], ctypes.byref(ms)))

@@ -12,9 +12,10 @@ from ppea_depth_b200.synth import CITYSCAPES_K, SynthConfig, make_batch, make_no
 pytestmark = pytest.mark.gpu
 
 
-# fused: None = the single-launch training step (vsl_fused.cu: mono and multi path, atomic or deterministic);
+# fused: None = the fused training step, warp-streaming kernel (vsl_stream.cu: mono and multi path, atomic or deterministic);
+#        "tiles" = the same step by the shared-memory tile kernel (vsl_fused.cu);
 #        False = the forward + backward kernel pair (vsl_fwd.cu / vsl_bwd.cu)
-@pytest.mark.parametrize("fused", [None, False])
+@pytest.mark.parametrize("fused", [None, "tiles", False])
 @pytest.mark.parametrize("name", golden_names())
 def test_cuda_matches_golden(name, fused):
     fx = load_golden(name)
@@ -36,7 +37,7 @@ def test_cuda_matches_golden(name, fused):
 
 
 @pytest.mark.parametrize("det", [False, True])
-@pytest.mark.parametrize("multi,fused", [(False, None), (False, False), (True, None), (True, False)])
+@pytest.mark.parametrize("multi,fused", [(False, None), (False, "tiles"), (False, False), (True, None), (True, "tiles"), (True, False)])
 @pytest.mark.parametrize("shape", [(2, 64, 96, 4), (1, 50, 70, 3), (3, 33, 47, 1)])
 def test_cuda_matches_oracle_synthetic(shape, multi, fused, det):
     B, H, W, S = shape
@@ -79,7 +80,7 @@ def test_fused_step_equals_kernel_pair(multi):
             assert float((g_a[k] - g_b[k]).abs().max()) <= 2e-5 * scale + 1e-12, k
 
 
-@pytest.mark.parametrize("multi,fused", [(False, None), (False, False), (True, None), (True, False)])
+@pytest.mark.parametrize("multi,fused", [(False, None), (False, "tiles"), (False, False), (True, None), (True, "tiles"), (True, False)])
 def test_cuda_deterministic_backward_matches_and_repeats(multi, fused):
     """fused step: 64-bit fixed-point accumulation of the coarse-scale fields; kernel pair: scratch field +
     fixed-order gather.  Both must repeat bit for bit and agree with the float-atomics backward."""
@@ -97,7 +98,7 @@ def test_cuda_deterministic_backward_matches_and_repeats(multi, fused):
     check_against_oracle(inputs, outputs, opt, multi, make_noise(cfg, 4), l_det, g_det1, maps)
 
 
-@pytest.mark.parametrize("fused", [None, False])
+@pytest.mark.parametrize("fused", [None, "tiles", False])
 def test_cuda_upstream_gradient_is_linear(fused):
     """backward honours the upstream gradient of every entry of the loss dict (not just "loss")."""
     from ppea_depth_b200.loss import ViewSynthesisLoss
@@ -134,7 +135,7 @@ FULL = {
 }
 
 
-@pytest.mark.parametrize("multi,fused", [(False, None), (False, False), (True, None), (True, False)])
+@pytest.mark.parametrize("multi,fused", [(False, None), (False, "tiles"), (False, False), (True, None), (True, "tiles"), (True, False)])
 def test_full_size_kitti_against_oracle(multi, fused):
     """BASELINE.json configs[0]/[1]: the whole 12x3x192x640, 4-scale batch against the oracle
     (a few seconds of CPU)."""
