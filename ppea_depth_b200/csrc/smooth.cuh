@@ -142,7 +142,10 @@ __device__ __forceinline__ void smooth_forward_role(const VslArgs& a, int role, 
 //   R = sign(d - d_right) * e_right,  D = sign(d - d_down) * e_down,
 // from the same column walk (the edge weights are the forward's own), so that the backward proper is
 // elementwise:  d smooth / d d_j = inv_b * ( st_j - inv_b * (X_b / N_x + Y_b / N_y) / (h*w) )  (times upstream).
-// the column walk of one (virtual) thread `tid` of a `bd`-wide chunk CTA; adds its share to (sd, sx, sy)
+// The column walk of one (virtual) thread `tid` of a `bd`-wide chunk CTA; adds its share to (sd, sx, sy).
+// A warp covers 32 adjacent columns of which the inner 30 are its own: both horizontal neighbours of an owned column
+// live in the warp and come by shuffle, so a row costs each lane ONE 4-word load (disp + 3 colour channels), issued a row
+// ahead -- no lane waits for a neighbour it had to load itself.  A chunk is a strip of 30 * (bd / 32) columns x a band of rows.
 __device__ __forceinline__ void smooth_fused_walk(const VslArgs& a, int s, int b, int chunk, int bd, int tid, float& sd, float& sx, float& sy) {
   const ScaleArgs& sc = a.sc[s];
   const int h = sc.hs, w = sc.ws;
@@ -150,44 +153,42 @@ __device__ __forceinline__ void smooth_fused_walk(const VslArgs& a, int s, int b
   const float* d = sc.disp + (size_t)b * n;
   const float* img = sc.color + (size_t)b * 3 * n;
   float* st = sc.grad_st + (size_t)b * n;
-  const SmoothChunk ck = smooth_chunk(w, h, chunk, bd, tid);
-  const int lane = tid & 31;
+  const int lane = tid & 31, cols = 30 * (bd >> 5);
+  const int strips = (w + cols - 1) / cols;                 // <= kSmoothChunks is checked by the API (w <= 32 * 120)
+  const int bands = kSmoothChunks / strips > 0 ? kSmoothChunks / strips : 1;
+  const int rows = (h + bands - 1) / bands;
+  const int strip = chunk % strips, band = chunk / strips;
+  if (!(band < bands && band * rows < h)) return;
+  const int x = strip * cols + (tid >> 5) * 30 + lane - 1;
+  const int y_lo = band * rows, y_hi = y_lo + rows < h ? y_lo + rows : h;
   const float cx = w > 1 ? 1.f / ((float)a.B * h * (w - 1)) : 0.f, cy = h > 1 ? 1.f / ((float)a.B * (h - 1) * w) : 0.f;
-  if (ck.active) {
-    const bool xin = ck.x < w, has_r = ck.x + 1 < w, has_l = xin && ck.x > 0;
-    SmoothPx cur = smooth_load(d, img, n, (unsigned)(ck.y_lo * w + ck.x), xin);
-    float d_up = 0.f;                      // D(x, y-1)
-    if (ck.y_lo > 0 && xin) {
-      const SmoothPx up = smooth_load(d, img, n, (unsigned)((ck.y_lo - 1) * w + ck.x), true);
-      d_up = sign_of(up.d - cur.d) * smooth_weight(up, cur);
+  const bool xin = x >= 0 && x < w, has_r = xin && x + 1 < w;
+  const bool own = xin && lane >= 1 && lane <= 30;
+  const unsigned ux = (unsigned)(xin ? x : 0);
+  SmoothPx cur = smooth_load(d, img, n, (unsigned)(y_lo * w) + ux, xin);
+  float d_up = 0.f;                      // D(x, y-1)
+  if (y_lo > 0 && xin) {
+    const SmoothPx up = smooth_load(d, img, n, (unsigned)((y_lo - 1) * w) + ux, true);
+    d_up = sign_of(up.d - cur.d) * smooth_weight(up, cur);
+  }
+  for (int y = y_lo; y < y_hi; ++y) {
+    const unsigned o = (unsigned)(y * w) + ux;
+    const bool has_d = y + 1 < h;
+    const SmoothPx nxt = smooth_load(d, img, n, o + (unsigned)w, xin && has_d);
+    const SmoothPx rgt = smooth_shfl_down(cur);
+    const float dr = cur.d - rgt.d, dd = cur.d - nxt.d;
+    const float er = has_r ? smooth_weight(cur, rgt) : 0.f;
+    const float ed = (xin && has_d) ? smooth_weight(cur, nxt) : 0.f;
+    const float r_here = sign_of(dr) * er, d_here = sign_of(dd) * ed;
+    const float r_left = __shfl_up_sync(0xffffffffu, r_here, 1);      // (0 at the image border: lane 0 is outside, er = 0)
+    if (own) {
+      sd += cur.d;
+      sx += fabsf(dr) * er;
+      sy += fabsf(dd) * ed;
+      st[o] = (r_here - r_left) * cx + (d_here - d_up) * cy;
     }
-    for (int y = ck.y_lo; y < ck.y_hi; ++y) {
-      const unsigned o = (unsigned)(y * w + ck.x);
-      const bool has_d = y + 1 < h;
-      const SmoothPx nxt = smooth_load(d, img, n, o + (unsigned)w, xin && has_d);
-      SmoothPx rgt = smooth_shfl_down(cur);
-      if (lane == 31) rgt = smooth_load(d, img, n, o + 1u, has_r);     // the neighbour lives in the next warp / strip
-      const float dr = cur.d - rgt.d, dd = cur.d - nxt.d;
-      const float er = (xin && has_r) ? smooth_weight(cur, rgt) : 0.f;
-      const float ed = (xin && has_d) ? smooth_weight(cur, nxt) : 0.f;
-      const float r_here = sign_of(dr) * er, d_here = sign_of(dd) * ed;
-      float r_left = __shfl_up_sync(0xffffffffu, r_here, 1);
-      if (lane == 0) {
-        r_left = 0.f;
-        if (has_l) {
-          const SmoothPx lft = smooth_load(d, img, n, o - 1u, true);
-          r_left = sign_of(lft.d - cur.d) * smooth_weight(lft, cur);
-        }
-      }
-      if (xin) {
-        sd += cur.d;
-        sx += fabsf(dr) * er;
-        sy += fabsf(dd) * ed;
-        st[o] = (r_here - r_left) * cx + (d_here - d_up) * cy;
-      }
-      d_up = d_here;
-      cur = nxt;
-    }
+    d_up = d_here;
+    cur = nxt;
   }
 }
 

@@ -190,8 +190,19 @@ struct PrepRow {
   f2 x[3];
 };
 
-__global__ void __launch_bounds__(128) vsl_prep_kernel(const __grid_constant__ VslArgs a, int strips, int segs) {
+#ifndef PPEA_PREP_CTAS
+#define PPEA_PREP_CTAS 4
+#endif
+__global__ void __launch_bounds__(kSmoothThreads, PPEA_PREP_CTAS) vsl_prep_kernel(const __grid_constant__ VslArgs a, int strips, int segs, int n_task_ctas) {
+  __shared__ float red[3 * kSmoothThreads / 32];
   grid_launch_dependents();      // the main launch may take idle SMs early (it waits for our results where it needs them)
+  if ((int)blockIdx.x >= n_task_ctas) {
+    // Smoothness term of every scale (smooth.cuh: sums + un-normalised stencil field) as extra CTAs of this launch: like
+    // the preparation tasks they depend on nothing and are latency-bound column walks, so the two kinds of CTA share the
+    // SMs instead of queueing behind each other.
+    smooth_fused_role(a, blockIdx.x - n_task_ctas, red);
+    return;
+  }
   const int lane = threadIdx.x & 31;
   int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= a.B * strips * segs) return;
@@ -292,8 +303,8 @@ __global__ void __launch_bounds__(128) vsl_prep_kernel(const __grid_constant__ V
 
 cudaError_t launch_vsl_prep(const VslArgs& a, cudaStream_t stream) {
   const int strips = ceil_div(a.W, kPrepStripW), segs = ceil_div(a.H, kPrepSegRows);
-  const int tasks = a.B * strips * segs;
-  vsl_prep_kernel<<<ceil_div(tasks, 4), 128, 0, stream>>>(a, strips, segs);
+  const int n_task_ctas = ceil_div(a.B * strips * segs, kSmoothThreads / 32);
+  vsl_prep_kernel<<<n_task_ctas + a.S * a.B * kSmoothChunks, kSmoothThreads, 0, stream>>>(a, strips, segs, n_task_ctas);
   return cudaGetLastError();
 }
 
@@ -369,7 +380,7 @@ __device__ __forceinline__ const T* opaque_base(const T* p) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Main launch.  grid = one CTA (one warp) per task, then the S*B*32 smoothness role CTAs.
+// Main launch.  grid = one CTA (one warp) per task.
 // Iteration gi:  issue the loads of row gi+1 (gather corners, target, noise / identity loss of the row
 // decided next) -> blend row gi from the words fetched one iteration ago -> row sums -> decide row
 // gi-1 -> fold + chain row gi-2.
@@ -382,14 +393,6 @@ __global__ void __launch_bounds__(kStreamThreads, PPEA_STREAM_CTAS) vsl_stream_k
   __shared__ f2 s_G[kStreamWarps][12];
 
   grid_launch_dependents();      // the dependent is the small finish kernel: let it take its place early
-  if ((int)blockIdx.x >= n_task_ctas) {
-    // smoothness roles: the LAST CTAs of the grid (short; they fill the tail).  Independent of the preparation launch.
-    if (kStreamWarps == 1)
-      smooth_fused_role_warp(a, blockIdx.x - n_task_ctas);
-    else
-      smooth_fused_role(a, blockIdx.x - n_task_ctas, reinterpret_cast<float*>(&s_dd[0][0][0][0]));
-    return;
-  }
   const int lane = threadIdx.x & 31, wid = kStreamWarps == 1 ? 0 : threadIdx.x >> 5;
   const int strips = a.tiles_x, segs = a.tiles_y;
   int t = blockIdx.x * kStreamWarps + wid;
@@ -486,10 +489,32 @@ __global__ void __launch_bounds__(kStreamThreads, PPEA_STREAM_CTAS) vsl_stream_k
   }
 
   // the (upsampled) disparity of row gi at this lane's column: loads only, issued two rows ahead of the blend
-  auto load_disp = [&](int gi) -> float {
+  // (coarse scales: the four taps of the bilinear upsample are fetched raw and blended where the value is used, so that
+  // the blend does not wait for them inside the iteration that issued the loads)
+  struct DispTaps {
+    float v00, v01, v10, v11;
+  };
+  auto load_disp = [&](int gi) -> DispTaps {
     const int py = reflect_index(gi, H);
-    if (same_res) return __ldg(disp_b + ((unsigned)py * uW + upx));
-    return up_sample(disp_b, ws, up_coef(py, hs, sc.up_sy), cc.cx);
+    DispTaps t;
+    if (same_res) {
+      t.v00 = __ldg(disp_b + ((unsigned)py * uW + upx));
+      t.v01 = t.v10 = t.v11 = 0.f;
+    } else {
+      const UpCoef cy = up_coef(py, hs, sc.up_sy);
+      const unsigned r0 = (unsigned)cy.i0 * (unsigned)ws, r1 = (unsigned)cy.i1 * (unsigned)ws;
+      t.v00 = __ldg(disp_b + (r0 + (unsigned)cc.cx.i0)), t.v01 = __ldg(disp_b + (r0 + (unsigned)cc.cx.i1));
+      t.v10 = __ldg(disp_b + (r1 + (unsigned)cc.cx.i0)), t.v11 = __ldg(disp_b + (r1 + (unsigned)cc.cx.i1));
+    }
+    return t;
+  };
+  // same roundings as up_sample (vsl_math.cuh): every kernel gets the same bits
+  auto disp_value = [&](int gi, const DispTaps& t) -> float {
+    if (same_res) return t.v00;
+    const UpCoef cy = up_coef(reflect_index(gi, H), hs, sc.up_sy);
+    const float top = fma_rn(cc.cx.l1, t.v01, mul_rn(cc.cx.l0, t.v00));
+    const float bot = fma_rn(cc.cx.l1, t.v11, mul_rn(cc.cx.l0, t.v10));
+    return fma_rn(cy.l1, bot, mul_rn(cy.l0, top));
   };
   // projection of row gi and the loads of its eight packed corners (consumed by the next iteration)
   auto fetch_row = [&](int gi, float dup, RowFetch& r) {
@@ -520,9 +545,11 @@ __global__ void __launch_bounds__(kStreamThreads, PPEA_STREAM_CTAS) vsl_stream_k
   // occupies the instruction cache, and the compiler sees straight-line code.
   auto run_rows = [&](auto packed_c) {
   constexpr bool packed = decltype(packed_c)::value;
-  float dup_pf = load_disp(y0 - 2);
-  if (packed) fetch_row(y0 - 2, dup_pf, rf[0]);
-  dup_pf = load_disp(y0 - 1);
+  DispTaps dup_pf = load_disp(y0 - 2);
+  if (packed) {                 // (the planar gathers are not prefetched: they keep the disparity of the row itself)
+    fetch_row(y0 - 2, disp_value(y0 - 2, dup_pf), rf[0]);
+    dup_pf = load_disp(y0 - 1);
+  }
   float y_pf[3];
   load_tgt(y0 - 2, y_pf);
   float id_pf = 0.f, nz_pf = 0.f, cm_pf = 1.f;       // (the first two iterations decide nothing that is kept)
@@ -540,10 +567,10 @@ __global__ void __launch_bounds__(kStreamThreads, PPEA_STREAM_CTAS) vsl_stream_k
     const float idv = id_pf, nzv = nz_pf, cmv = cm_pf;
     float dup_cur = 0.f;
     if (packed) {
-      fetch_row(gi + 1, dup_pf, rf[Q]);
+      fetch_row(gi + 1, disp_value(gi + 1, dup_pf), rf[Q]);
       dup_pf = load_disp(gi + 2);
     } else {
-      dup_cur = dup_pf;
+      dup_cur = disp_value(gi, dup_pf);
       dup_pf = load_disp(gi + 1);
     }
     load_tgt(gi + 1, y_pf);
@@ -761,8 +788,7 @@ template <bool POSE, bool MULTI, bool DET>
 static cudaError_t launch_vsl_stream_as(const VslArgs& a, cudaStream_t stream) {
   const int tasks = a.B * a.tiles_x * a.tiles_y * a.S;
   const int n_task_ctas = ceil_div(tasks, kStreamWarps);
-  const int nblk = n_task_ctas + a.S * a.B * kSmoothChunks;
-  return launch_pdl(vsl_stream_kernel<POSE, MULTI, DET>, dim3(nblk), dim3(kStreamThreads), 0, stream, a, n_task_ctas);
+  return launch_pdl(vsl_stream_kernel<POSE, MULTI, DET>, dim3(n_task_ctas), dim3(kStreamThreads), 0, stream, a, n_task_ctas);
 }
 
 cudaError_t launch_vsl_stream(const VslArgs& a, cudaStream_t stream) {
