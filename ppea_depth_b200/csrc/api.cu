@@ -19,7 +19,7 @@ int check_params(const PpeaVslParams* p, bool backward) {
       p->first_scale + p->num_scales > 16)
     return PPEA_E_SHAPE;
   if ((size_t)p->batch * p->height * p->width >= (size_t)1 << 31) return PPEA_E_SHAPE;
-  if (p->width > kSmoothChunks * 120) return PPEA_E_SHAPE;   // smoothness strips (smooth.cuh): 120 columns x 32 chunks
+  if (p->width > 32 * 120) return PPEA_E_SHAPE;   // smoothness strips (smooth.cuh): at most 32 strips of 120 columns
   const bool multi = p->flags & PPEA_F_MULTI;
   if (multi && (p->flags & PPEA_F_GRAD_POSE)) return PPEA_E_FLAGS;   // T is detached on the multi path (trainer.py:900-902)
   if (!p->tgt || !p->src[0] || !p->src[1] || !p->K || !p->inv_K || !p->T[0] || !p->T[1] || !p->sums || !p->losses)

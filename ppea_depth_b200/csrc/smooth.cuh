@@ -165,16 +165,21 @@ __device__ __forceinline__ void smooth_fused_walk(const VslArgs& a, int s, int b
   const bool xin = x >= 0 && x < w, has_r = xin && x + 1 < w;
   const bool own = xin && lane >= 1 && lane <= 30;
   const unsigned ux = (unsigned)(xin ? x : 0);
-  SmoothPx cur = smooth_load(d, img, n, (unsigned)(y_lo * w) + ux, xin);
+  // Three row registers in rotation (the loop is unrolled by three so that the roles are names, not moves): a row is
+  // requested two iterations before it is used, and nothing touches its registers in between -- a register move of a
+  // load result that has not arrived yet would stall for the whole memory latency.
+  SmoothPx r0 = smooth_load(d, img, n, (unsigned)(y_lo * w) + ux, xin);
+  SmoothPx r1 = smooth_load(d, img, n, (unsigned)((y_lo + 1) * w) + ux, xin && y_lo + 1 < h);
+  SmoothPx r2;
   float d_up = 0.f;                      // D(x, y-1)
   if (y_lo > 0 && xin) {
     const SmoothPx up = smooth_load(d, img, n, (unsigned)((y_lo - 1) * w) + ux, true);
-    d_up = sign_of(up.d - cur.d) * smooth_weight(up, cur);
+    d_up = sign_of(up.d - r0.d) * smooth_weight(up, r0);
   }
-  for (int y = y_lo; y < y_hi; ++y) {
+  auto row = [&](int y, const SmoothPx& cur, const SmoothPx& nxt, SmoothPx& nn) {
     const unsigned o = (unsigned)(y * w) + ux;
     const bool has_d = y + 1 < h;
-    const SmoothPx nxt = smooth_load(d, img, n, o + (unsigned)w, xin && has_d);
+    nn = smooth_load(d, img, n, o + 2u * (unsigned)w, xin && y + 2 < h && y + 2 <= y_hi);
     const SmoothPx rgt = smooth_shfl_down(cur);
     const float dr = cur.d - rgt.d, dd = cur.d - nxt.d;
     const float er = has_r ? smooth_weight(cur, rgt) : 0.f;
@@ -188,7 +193,12 @@ __device__ __forceinline__ void smooth_fused_walk(const VslArgs& a, int s, int b
       st[o] = (r_here - r_left) * cx + (d_here - d_up) * cy;
     }
     d_up = d_here;
-    cur = nxt;
+  };
+#pragma unroll 1
+  for (int y = y_lo; y < y_hi; y += 3) {
+    row(y, r0, r1, r2);
+    if (y + 1 < y_hi) row(y + 1, r1, r2, r0);
+    if (y + 2 < y_hi) row(y + 2, r2, r0, r1);
   }
 }
 

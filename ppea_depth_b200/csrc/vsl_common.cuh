@@ -79,14 +79,17 @@ constexpr int kBwdTileH = PPEA_BWD_TILE_H;
 #define PPEA_BWD_THREADS 128
 #endif
 constexpr int kBwdThreads = PPEA_BWD_THREADS;
-constexpr int kSmoothChunks = 32;     // blocks per image in the smoothness kernels
+#ifndef PPEA_SMOOTH_CHUNKS
+#define PPEA_SMOOTH_CHUNKS 64
+#endif
+constexpr int kSmoothChunks = PPEA_SMOOTH_CHUNKS;     // role CTAs per image and scale in the smoothness kernels (column walks: more chunks = shorter walks)
 constexpr int kSmoothThreads = 128;
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 #ifndef PPEA_STREAM_SEG
-#define PPEA_STREAM_SEG 48
+#define PPEA_STREAM_SEG 96
 #endif
 #define PPEA_STREAM_SEG_ROWS PPEA_STREAM_SEG
 inline int fwd_blocks(int B, int H, int W) { return B * ceil_div(W, kFwdTileW) * ceil_div(H, kFwdTileH); }

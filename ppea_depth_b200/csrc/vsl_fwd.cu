@@ -366,12 +366,17 @@ __global__ void __launch_bounds__(kFinishThreads) vsl_finish_kernel(const __grid
     }
   }
   // per-image smoothness sums (kept for the backward): one warp per (scale, image), one lane per chunk
-  static_assert(kSmoothChunks == 32, "one lane per chunk");
+  static_assert(kSmoothChunks % 32 == 0, "a lane owns the chunks lane, lane + 32, ...");
   for (int pair = wid; pair < a.S * a.B; pair += kFinishThreads / 32) {
     const int ps = pair / a.B, b = pair - ps * a.B;
     const ScaleArgs& sc = a.sc[ps];
     const float* sws = a.smooth_ws + ((size_t)ps * a.B + b) * kSmoothChunks * 3;
-    double ds = (double)sws[lane * 3 + 0], sx = (double)sws[lane * 3 + 1], sy = (double)sws[lane * 3 + 2];
+    double ds = 0, sx = 0, sy = 0;
+#pragma unroll
+    for (int k = 0; k < kSmoothChunks / 32; ++k) {       // fixed order
+      const float* q = sws + (k * 32 + lane) * 3;
+      ds += (double)q[0], sx += (double)q[1], sy += (double)q[2];
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       ds += __shfl_xor_sync(0xffffffffu, ds, o);

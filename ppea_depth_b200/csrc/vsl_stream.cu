@@ -51,7 +51,10 @@ namespace ppea {
 #endif
 constexpr int kStreamWarps = PPEA_STREAM_WARPS;
 constexpr int kStreamThreads = 32 * kStreamWarps;
-constexpr int kPrepSegRows = 16;      // rows per warp task of the preparation launch
+#ifndef PPEA_PREP_SEG
+#define PPEA_PREP_SEG 16
+#endif
+constexpr int kPrepSegRows = PPEA_PREP_SEG;      // rows per warp task of the preparation launch
 constexpr int kPrepStripW = 30;       // decided columns per warp there
 
 __device__ __forceinline__ f2 shfl_up2(f2 v) {
@@ -174,12 +177,14 @@ __device__ __forceinline__ void blend_packed(const RowFetch& rf, unsigned k4b, f
 // formed without a division: q = k * fl(1/255), then one Newton correction fma(fma(-q, 255, k), fl(1/255), q),
 // which equals the IEEE quotient for every k in 0..255 (checked exhaustively, tests/test_host.py).
 __device__ __forceinline__ unsigned byte_of(float v, bool& exact) {
-  constexpr float r = 1.f / 255.f;
-  const float k = fminf(fmaxf(rintf(v * 255.f), 0.f), 255.f);
+  constexpr float r = 1.f / 255.f, kMagic = 12582912.f;      // 1.5 * 2^23: adding it rounds to an integer in the low mantissa bits
+  const float t = fma_rn(v, 255.f, kMagic);                  // (no conversion instructions: they run on the quarter-rate pipe)
+  const unsigned ki = __float_as_uint(t) - 0x4B400000u;      // k = round(255 v); out of 0..255 (or NaN) fails the test below
+  const float k = t - kMagic;
   const float q = mul_rn(k, r);
   const float q2 = fma_rn(fma_rn(-q, 255.f, k), r, q);
-  exact = exact && (q2 == v);
-  return (unsigned)__float2int_rn(k);
+  exact = exact && (q2 == v) && (ki <= 255u);
+  return ki & 255u;
 }
 __device__ __forceinline__ unsigned pack_rgb(float r, float g, float b, bool& exact) {
   return byte_of(r, exact) | (byte_of(g, exact) << 8) | (byte_of(b, exact) << 16);
@@ -191,7 +196,7 @@ struct PrepRow {
 };
 
 #ifndef PPEA_PREP_CTAS
-#define PPEA_PREP_CTAS 4
+#define PPEA_PREP_CTAS 3
 #endif
 __global__ void __launch_bounds__(kSmoothThreads, PPEA_PREP_CTAS) vsl_prep_kernel(const __grid_constant__ VslArgs a, int strips, int segs, int n_task_ctas) {
   __shared__ float red[3 * kSmoothThreads / 32];
@@ -567,7 +572,7 @@ __global__ void __launch_bounds__(kStreamThreads, PPEA_STREAM_CTAS) vsl_stream_k
     const float idv = id_pf, nzv = nz_pf, cmv = cm_pf;
     float dup_cur = 0.f;
     if (packed) {
-      fetch_row(gi + 1, disp_value(gi + 1, dup_pf), rf[Q]);
+      fetch_row(gi + 1, disp_value(gi + 1, dup_pf), rf[Q]);      // consumed by the next iteration: a whole row of arithmetic covers the L2 latency
       dup_pf = load_disp(gi + 2);
     } else {
       dup_cur = disp_value(gi, dup_pf);

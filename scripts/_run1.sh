@@ -1,5 +1,4 @@
-set -x
-python -m pytest tests/test_gpu_parity.py -x -q -k "not tiles and not False" 2>&1 | tail -40 > gpurun_out/r2a_tests.log
-python bench.py --steps 100 --warmup 10 --no-e2e --no-cpu-baseline > gpurun_out/r2a_bench.json 2> gpurun_out/r2a_bench.err
-python bench.py --steps 100 --warmup 10 --no-e2e --no-cpu-baseline --tiles > gpurun_out/r2a_bench_tiles.json 2> gpurun_out/r2a_bench_tiles.err
-tail -5 gpurun_out/r2a_tests.log; cat gpurun_out/r2a_bench.json; tail -3 gpurun_out/r2a_bench.err
+python -m pytest tests -x -q -m gpu 2>&1 | tail -8 > gpurun_out/r2_tests.log
+python bench.py --steps 200 --warmup 20 --no-e2e --no-cpu-baseline > gpurun_out/r2_bench.json 2> gpurun_out/r2_bench.err
+python bench.py --steps 200 --warmup 20 --no-e2e --no-cpu-baseline --tiles > gpurun_out/r2_bench_tiles.json 2> gpurun_out/r2_bench_tiles.err
+tail -8 gpurun_out/r2_tests.log; cat gpurun_out/r2_bench.json; cat gpurun_out/r2_bench_tiles.json; tail -3 gpurun_out/r2_bench.err

@@ -1,12 +1,17 @@
 """Top SASS instructions of an .ncu-rep by stall samples, with the dominant reason; usage: ncu_stalls.py rep [top]"""
 import csv, subprocess, sys, io, re
 rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 60
+want = sys.argv[3] if len(sys.argv) > 3 else None      # substring of the kernel name (default: first kernel)
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-hdr = None; data = []
+hdr = None; data = []; take = want is None; nk = 0
 for r in rows:
+    if r and r[0] == "Kernel Name":
+        nk += 1
+        take = (want in r[1]) if want else (nk == 1)
+        continue
     if r and r[0] == "Address": hdr = r; continue
-    if hdr and len(r) == len(hdr) and re.fullmatch(r"0x[0-9a-f]+", r[0]): data.append(r)
+    if take and hdr and len(r) == len(hdr) and re.fullmatch(r"0x[0-9a-f]+", r[0]): data.append(r)
 ix = {k: i for i, k in enumerate(hdr)}
 reasons = [k for k in hdr if k.startswith("stall_") and "Not Issued" not in k]
 tot = sum(int(r[ix["# Samples"]]) for r in data)
