@@ -15,8 +15,9 @@ code executed in the build container (`oracle/ref_import.py`,
 under `tests/golden/`; `tests/test_oracle.py` re-checks both.
 
 The arithmetic that the reference delegates to ATen (bilinear interpolate,
-grid_sample, avg_pool2d, reflection pad) is *also* restated index-by-index in
-`oracle/closed_form.py`; this file uses the ATen ops so that it costs what the
+grid_sample, avg_pool2d, reflection pad) is *also* restated index-by-index, on the
+kernels' own scalar arithmetic, by `tests/emul/vsl_emul.cpp` (driven by
+`tests/test_emul.py`); this file uses the ATen ops so that it costs what the
 reference costs on a CPU (it doubles as the timed CPU baseline).
 
 Works in fp32 (the reference's precision) or fp64 (margin analysis).
@@ -175,7 +176,7 @@ def view_synthesis_losses(inputs, outputs, opt, is_multi=False, noise=None, want
         _, depth = disp_to_depth(disp_up, opt.min_depth, opt.max_depth)      # trainer.py:890
         target = inputs[("color", 0, ss)]
         cam = backproject(depth, inputs[("inv_K", ss)], Hs, Ws)              # trainer.py:904
-        warped, per_src = [], []
+        warped, per_src, grids = [], [], []
         for f in srcs:
             T = outputs[("cam_T_cam", 0, f)]
             if is_multi:
@@ -183,6 +184,7 @@ def view_synthesis_losses(inputs, outputs, opt, is_multi=False, noise=None, want
             grid = project(cam, inputs[("K", ss)], T, Hs, Ws)
             w = warp(inputs[("color", f, ss)], grid)
             warped.append(w)
+            grids.append(grid.detach())
             per_src.append(photometric(w, target, opt.no_ssim))
         per_src = torch.cat(per_src, 1)                                       # (B,nsrc,H,W)
         ident = torch.cat([photometric(inputs[("color", f, ss)], target, opt.no_ssim) for f in srcs], 1)
@@ -239,7 +241,7 @@ def view_synthesis_losses(inputs, outputs, opt, is_multi=False, noise=None, want
         if want_maps:
             maps[s] = dict(r=r.detach(), ident=ident.detach(), mask=mask.detach(),
                            src_idx=src_idx.detach(), depth=depth.detach(),
-                           warped=[w.detach() for w in warped], per_src=per_src.detach())
+                           warped=[w.detach() for w in warped], per_src=per_src.detach(), grid=grids)
     losses["loss"] = total / S                                                # trainer.py:1157-1158
     return losses, maps
 

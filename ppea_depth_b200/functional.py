@@ -35,6 +35,15 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _mat44(m, batch, name):
+    """(B,4,4) contiguous fp32; a batch-1 matrix is expanded (the reference relies on matmul broadcasting)."""
+    if m.dim() != 3 or tuple(m.shape[-2:]) != (4, 4) or m.shape[0] not in (1, batch):
+        raise ValueError("%s must be (%d,4,4) or (1,4,4), got %s" % (name, batch, tuple(m.shape)))
+    if m.shape[0] != batch:
+        m = m.expand(batch, 4, 4)
+    return m.contiguous()
+
+
 @dataclass
 class VslConfig:
     """Flags and constants of one call (the options the reference path reads)."""
@@ -52,6 +61,10 @@ class VslConfig:
     first_scale: int = 0
     total_scales: Optional[int] = None
     want_loss_px: bool = False
+    plan_cache: bool = True          # training steps have static shapes: reuse one pre-built parameter block and a ring of
+                                     # output / workspace / gradient buffers per (shape, flags) instead of allocating ~20
+                                     # tensors and refilling the C struct every call (see _StepPlan).  Outputs of a call
+                                     # stay valid until the second next call with the same shapes and flags.
     fused: object = None             # fused training step; None / True = whenever some input requires grad: the
                                      # warp-streaming kernel (vsl_stream.cu); "tiles" = the shared-memory tile kernel
                                      # (vsl_fused.cu); False = the forward + backward kernel pair
@@ -116,7 +129,7 @@ class VslResult:
 class _Bundle:
     """Non-differentiable inputs + configuration of one fused call."""
     __slots__ = ("cfg", "tgt", "src", "K", "inv_K", "cons_mask", "aug_mask", "colors", "noise", "mono_depth",
-                 "B", "H", "W", "S")
+                 "B", "H", "W", "S", "result")
 
 
 def _fill_params(bundle, flags, T, disps, depth, loss_px, sel, grad_disp, sums, losses, workspace):
@@ -246,6 +259,156 @@ class _FusedViewSynthLoss(torch.autograd.Function):
         return (None, gT[0] if grad_pose else None, gT[1] if grad_pose else None, *grad_disp)
 
 
+# ---------------------------------------------------------------------------
+# Cached execution plans of the fused training step.  The reference's training step has static shapes
+# (batch_size is baked into its modules, layers.py:142-161; ragged batches are dropped, trainer.py:215-218), so
+# everything `_FusedViewSynthLoss` does per call on the host -- ~20 tensor allocations, ~70 ctypes field writes,
+# ten tensors through the autograd engine -- is hoisted into a plan keyed by (device, shapes, flags):
+# a ring of RING buffer sets, each with its parameter block already pointing at its outputs.  A call rebinds the
+# ~20 input pointers and launches; only the `losses` vector goes through autograd.
+# ---------------------------------------------------------------------------
+_PLAN_RING = 2
+_PLANS = {}
+
+
+class _PlanSlot:
+    __slots__ = ("depth", "sel", "loss_px", "sums", "losses", "ws", "fws", "grad_disp", "gT", "p", "g", "f", "pending", "zero_gl")
+
+
+class _StepPlan:
+    def __init__(self, bundle, flags, disp_shapes):
+        lib = C.lib()
+        dev = bundle.tgt.device
+        B, H, W, S = bundle.B, bundle.H, bundle.W, bundle.S
+        self.flags = flags | C.F_RAW_PREZEROED      # the slot's workspace is zeroed once here and kept clean by every backward
+        self.slots = []
+        self.next = 0
+        f32 = dict(device=dev, dtype=torch.float32)
+        cfg = bundle.cfg
+        with torch.cuda.device(dev):
+            for _ in range(_PLAN_RING):
+                sl = _PlanSlot()
+                sl.depth = [torch.empty(B, 1, H, W, **f32) for _ in range(S)]
+                sl.sel = [torch.empty(B, H, W, device=dev, dtype=torch.uint8) for _ in range(S)]
+                sl.loss_px = [torch.empty(B, 1, H, W, **f32) if cfg.want_loss_px else None for _ in range(S)]
+                sl.sums = torch.empty(lib.ppea_vsl_sums_floats(B, S), **f32)
+                sl.losses = torch.empty(1 + C.LOSSES_PER_SCALE * S, **f32)
+                sl.ws = torch.empty(max(lib.ppea_vsl_workspace_bytes(B, H, W, S) // 4, 4), **f32)
+                sl.grad_disp = [torch.empty(shape, **f32) for shape in disp_shapes]
+                sl.gT = [torch.empty(B, 4, 4, **f32) for _ in range(2)] if (flags & C.F_GRAD_POSE) else None
+                sl.zero_gl = None
+                p = C.PpeaVslParams()
+                p.struct_size = ctypes.sizeof(C.PpeaVslParams)
+                p.flags = self.flags
+                p.batch, p.height, p.width = B, H, W
+                p.num_scales = S
+                p.first_scale = cfg.first_scale
+                p.total_scales = cfg.total_scales if cfg.total_scales is not None else S
+                lo = 1.0 / cfg.max_depth
+                p.disp_lo, p.disp_range, p.eps = lo, 1.0 / cfg.min_depth - lo, cfg.eps
+                p.disparity_smoothness = cfg.disparity_smoothness
+                for s in range(S):
+                    sc = p.scales[s]
+                    sc.disp_h, sc.disp_w = disp_shapes[s][-2], disp_shapes[s][-1]
+                    sc.depth = sl.depth[s].data_ptr()
+                    sc.loss_px = sl.loss_px[s].data_ptr() if sl.loss_px[s] is not None else None
+                    sc.sel = sl.sel[s].data_ptr()
+                    sc.grad_disp = sl.grad_disp[s].data_ptr()
+                p.sums, p.losses = sl.sums.data_ptr(), sl.losses.data_ptr()
+                p.workspace, p.workspace_bytes = sl.ws.data_ptr(), sl.ws.numel() * 4
+                # the fused workspace is sized from a fully described call: bind this call's inputs first
+                self._bind(p, bundle, None, None)
+                sl.fws = torch.empty(max(lib.ppea_vsl_fused_workspace_bytes(ctypes.byref(p)) // 4, 4), **f32)
+                sl.fws.zero_()
+                sl.p = p
+                sl.f = _fused_struct(sl.fws)
+                g = C.PpeaVslGrads()
+                g.struct_size = ctypes.sizeof(C.PpeaVslGrads)
+                if sl.gT is not None:
+                    g.grad_T[0], g.grad_T[1] = sl.gT[0].data_ptr(), sl.gT[1].data_ptr()
+                sl.g = g
+                sl.pending = False
+                self.slots.append(sl)
+
+    @staticmethod
+    def _bind(p, b, T, disps):
+        p.tgt = b.tgt.data_ptr()
+        p.src[0], p.src[1] = b.src[0].data_ptr(), b.src[1].data_ptr()
+        p.K, p.inv_K = b.K.data_ptr(), b.inv_K.data_ptr()
+        if T is not None:
+            p.T[0], p.T[1] = T[0].data_ptr(), T[1].data_ptr()
+        p.cons_mask = b.cons_mask.data_ptr() if b.cons_mask is not None else None
+        p.aug_mask = b.aug_mask.data_ptr() if b.aug_mask is not None else None
+        for s in range(b.S):
+            sc = p.scales[s]
+            if disps is not None:
+                sc.disp = disps[s].data_ptr()
+            sc.color = b.colors[s].data_ptr()
+            sc.noise = b.noise[s].data_ptr() if b.noise is not None else None
+            sc.mono_depth = b.mono_depth[s].data_ptr() if b.mono_depth is not None else None
+
+    def take(self):
+        sl = self.slots[self.next]
+        self.next = (self.next + 1) % len(self.slots)
+        if sl.pending:                 # this slot's last forward never saw its backward: its raw gradient fields are dirty
+            sl.fws.zero_()
+        return sl
+
+
+def _plan_for(bundle, flags, disps):
+    shapes = tuple(tuple(d.shape) for d in disps)
+    cfg = bundle.cfg
+    key = (bundle.tgt.device.index, bundle.B, bundle.H, bundle.W, shapes, flags, cfg.want_loss_px, cfg.first_scale, cfg.total_scales,
+           cfg.min_depth, cfg.max_depth, cfg.eps, cfg.disparity_smoothness, bundle.noise is not None)
+    plan = _PLANS.get(key)
+    if plan is None:
+        if len(_PLANS) >= 16:
+            _PLANS.pop(next(iter(_PLANS)))
+        plan = _PLANS[key] = _StepPlan(bundle, flags, shapes)
+    return plan
+
+
+class _PlannedFusedLoss(torch.autograd.Function):
+    """The fused training step through a cached plan: one tensor (the loss vector) crosses autograd; the other
+    products are handed back through ``bundle.result``."""
+
+    @staticmethod
+    def forward(ctx, bundle, T0, T1, *disps):
+        lib = C.lib()
+        T = (_f32c(T0, "T[0]"), _f32c(T1, "T[1]"))
+        disps = tuple(_f32c(d, "disp") for d in disps)
+        grad_pose = bool(ctx.needs_input_grad[1] or ctx.needs_input_grad[2]) and not bundle.cfg.is_multi
+        plan = _plan_for(bundle, bundle.cfg.flags(grad_pose=grad_pose), disps)
+        sl = plan.take()
+        plan._bind(sl.p, bundle, T, disps)
+        with torch.cuda.device(bundle.tgt.device):
+            C.check(lib.ppea_vsl_fused_forward(ctypes.byref(sl.p), ctypes.byref(sl.f), _stream()))
+        sl.pending = True
+        ctx.slot = sl
+        ctx.keep = (bundle, T, disps)          # the backward reads the inputs again (recompute-free, but disp / colour / frames)
+        ctx.grad_pose = grad_pose
+        bundle.result = (sl.depth, sl.sel, sl.loss_px, sl.sums)
+        return sl.losses
+
+    @staticmethod
+    def backward(ctx, grad_losses):
+        lib = C.lib()
+        sl = ctx.slot
+        bundle = ctx.keep[0]
+        with torch.cuda.device(bundle.tgt.device):
+            if grad_losses is None:
+                if sl.zero_gl is None:
+                    sl.zero_gl = torch.zeros_like(sl.losses)
+                grad_losses = sl.zero_gl
+            if grad_losses.dtype != torch.float32 or not grad_losses.is_contiguous():
+                grad_losses = grad_losses.contiguous().float()
+            sl.g.grad_losses = grad_losses.data_ptr()
+            C.check(lib.ppea_vsl_fused_backward(ctypes.byref(sl.p), ctypes.byref(sl.g), ctypes.byref(sl.f), _stream()))
+        sl.pending = False
+        gT = sl.gT if ctx.grad_pose else (None, None)
+        return (None, gT[0], gT[1], *sl.grad_disp)
+
+
 def view_synthesis_loss(disps, T, tgt, src, K, inv_K, colors, cfg: VslConfig, noise=None, cons_mask=None,
                         aug_mask=None, mono_depth=None) -> VslResult:
     """Fused view-synthesis loss over ``len(disps)`` pyramid scales.
@@ -286,6 +449,27 @@ def view_synthesis_loss(disps, T, tgt, src, K, inv_K, colors, cfg: VslConfig, no
     T0, T1 = T
     if cfg.is_multi:
         T0, T1 = T0.detach(), T1.detach()                     # trainer.py:900-902
+    # The kernels index K / inv_K / T as ptr + 16 * b and every (B,*,H,W) map by b: shapes are checked here, and a
+    # batch-1 matrix (the reference modules broadcast it through torch.matmul) is expanded to the batch.
+    b.K, b.inv_K = _mat44(b.K, b.B, "K"), _mat44(b.inv_K, b.B, "inv_K")
+    T0, T1 = _mat44(T0, b.B, "T[0]"), _mat44(T1, b.B, "T[1]")
+    for name, t in (("src[0]", b.src[0]), ("src[1]", b.src[1])):
+        if tuple(t.shape) != tuple(b.tgt.shape):
+            raise ValueError("%s %s does not match the target frame %s" % (name, tuple(t.shape), tuple(b.tgt.shape)))
+    full = (b.B, 1, b.H, b.W)
+    for name, lst in (("noise", b.noise), ("mono_depth", b.mono_depth)):
+        for t in (lst or ()):
+            if tuple(t.shape) != full:
+                raise ValueError("%s %s is not %s" % (name, tuple(t.shape), full))
+    if b.cons_mask is not None and b.cons_mask.numel() != b.B * b.H * b.W:
+        raise ValueError("consistency_mask %s is not (%d,%d,%d)" % (tuple(b.cons_mask.shape), b.B, b.H, b.W))
+    if b.aug_mask is not None and b.aug_mask.numel() != b.B:
+        raise ValueError("augmentation_mask needs one entry per batch item")
+    needs_grad = torch.is_grad_enabled() and (T0.requires_grad or T1.requires_grad or any(d.requires_grad for d in disps))
+    if cfg.plan_cache and cfg.use_fused(needs_grad):
+        losses = _PlannedFusedLoss.apply(b, T0, T1, *disps)
+        depth, sel, lp, sums = b.result
+        return VslResult(losses=losses, depth=list(depth), sel=list(sel), loss_px=list(lp), sums=sums)
     outs = _FusedViewSynthLoss.apply(b, T0, T1, *disps)
     losses = outs[0]
     depth = list(outs[1:1 + S])

@@ -58,20 +58,23 @@ def _config(self, is_multi, **kw):
         **kw)
 
 
-def _draw_noise(self, shape, device):
+def _draw_noise(self, n, shape, device):
+    """The tie-break draws of `n` scales.  "reference": torch.randn on the CPU default generator, one (B,1,H,W) draw per
+    scale, scale-ascending, exactly as trainer.py:1086-1087 (then copied to the device); "device": ONE draw of all
+    scales on the GPU (no host RNG, no H2D copy; a different stream of numbers)."""
     mode = getattr(self, "ppea_noise_mode", "reference")
     if mode == "device":
-        return torch.randn(shape, device=device)
-    return torch.randn(shape).to(device, non_blocking=True)   # trainer.py:1086-1087
+        return list(torch.randn((n,) + tuple(shape), device=device).unbind(0))
+    return [torch.randn(shape).to(device, non_blocking=True) for _ in range(n)]
 
 
 def _run_fused(self, inputs, outputs, is_multi):
     o = self.opt
     S = o.sclm + 1
-    f0, f1 = o.frame_ids[1], o.frame_ids[2]
     if len(o.frame_ids) != 3:
         raise NotImplementedError("the fused path implements the reference's two-source configuration "
                                   "(frame_ids [0,-1,1]; selec_reproj hard-codes it, trainer.py:1078-1083)")
+    f0, f1 = o.frame_ids[1], o.frame_ids[2]
     T = (outputs[("cam_T_cam", 0, f0)], outputs[("cam_T_cam", 0, f1)])
     dev = outputs[("disp", 0)].device
     groups = []
@@ -89,15 +92,20 @@ def _run_fused(self, inputs, outputs, is_multi):
         colors = [frame(inputs[("color", 0, s)]) for s in scales]
         tgt = frame(inputs[("color", 0, ss)])
         kw = {}
-        cfg = _config(self, is_multi, first_scale=first, total_scales=S)
+        cfg = _config(self, is_multi, first_scale=first, total_scales=S, plan_cache=bool(getattr(self, "ppea_plan_cache", True)))
         if is_multi:
             kw["mono_depth"] = [outputs[("mono_depth", 0, s)] for s in scales]
             kw["cons_mask"] = outputs.get("consistency_mask")
             kw["aug_mask"] = outputs.get("augmentation_mask")
             if kw["aug_mask"] is not None:
                 kw["aug_mask"] = kw["aug_mask"][:o.batch_size]
+            if not _opt(self, "disable_automasking", False) and getattr(self, "ppea_noise_mode", "reference") == "reference":
+                # the reference draws the tie-break noise on the multi path too, before discarding the automask
+                # (trainer.py:1084-1087 run ahead of the is_multi override :1101): keep the CPU generator in step with it
+                for _ in scales:
+                    torch.randn((tgt.shape[0], 1, tgt.shape[2], tgt.shape[3]))
         elif not _opt(self, "disable_automasking", False):    # the flag only removes the noise (trainer.py:1084-1087)
-            kw["noise"] = [_draw_noise(self, (tgt.shape[0], 1, tgt.shape[2], tgt.shape[3]), dev) for _ in scales]
+            kw["noise"] = _draw_noise(self, len(scales), (tgt.shape[0], 1, tgt.shape[2], tgt.shape[3]), dev)
         res = Fn.view_synthesis_loss(disps, T, tgt, (frame(inputs[("color", f0, ss)]), frame(inputs[("color", f1, ss)])),
                                      inputs[("K", ss)], inputs[("inv_K", ss)], colors, cfg, **kw)
         results.append((first, n, res))
@@ -117,22 +125,26 @@ def generate_images_pred(self, inputs, outputs, is_multi=False):
 
 
 def _materialize_warps(self, inputs, outputs, is_multi):
-    """The reference's per-source byproducts (trainer.py:904-918), through the piecewise operators."""
-    import torch.nn.functional as F
+    """The reference's per-source byproducts (trainer.py:904-918) -- ("sample", f, s), ("color", f, s) and
+    ("color_identity", f, s) -- through the piecewise operators.  Nothing on the training step reads them (SURVEY.md
+    §3.2); they exist for callers that log or inspect the warps (``materialize_warps=True``)."""
     o = self.opt
+    frame = FrameCache()
     for s in range(o.sclm + 1):
         ss = s if _opt(self, "v1_multiscale", False) else 0
         depth = outputs[("depth", 0, s)]
+        H, W = depth.shape[-2], depth.shape[-1]
         for f in o.frame_ids[1:]:
             T = outputs[("cam_T_cam", 0, f)]
             if is_multi:
                 T = T.detach()
-            cam = self.backproject_depth[ss](depth, inputs[("inv_K", ss)])
-            pix = self.project_3d[ss](cam, inputs[("K", ss)], T)
+            cam = Fn.backproject_depth(depth, inputs[("inv_K", ss)], H, W)
+            pix, _ = Fn.project_3d(cam, inputs[("K", ss)], T, H, W)
+            src = frame(inputs[("color", f, ss)])
             outputs[("sample", f, s)] = pix
-            outputs[("color", f, s)] = Fn.grid_sample_border(inputs[("color", f, ss)], pix)
+            outputs[("color", f, s)] = Fn.grid_sample_border(src, pix)
             if not _opt(self, "disable_automasking", False):
-                outputs[("color_identity", f, s)] = inputs[("color", f, ss)]
+                outputs[("color_identity", f, s)] = src
 
 
 def compute_reprojection_loss(self, pred, target):
@@ -160,13 +172,17 @@ def compute_losses(self, inputs, outputs, is_multi=False):
     losses = {}
     total = None
     for first, n, res in results:
+        # one `select` view per dictionary entry (not unbind: the reference updates the entries in place,
+        # `losses[key] += val`, trainer.py:459-461, which autograd forbids on the views of a multi-output view op)
+        v = res.losses
         for i in range(n):
             s = first + i
-            losses["reproj_loss/{}".format(s)] = res.reproj_loss(i)
+            k = 1 + 4 * i               # [loss/s, reproj_loss/s, consistency_loss/s, smooth/s]  (ppea_vsl.h PPEA_LOSSES_PER_SCALE)
+            losses["reproj_loss/{}".format(s)] = v[k + 1]
             if is_multi:
-                losses["consistency_loss/{}".format(s)] = res.consistency_loss(i)
-            losses["loss/{}".format(s)] = res.scale_loss(i)
-        total = res.loss if total is None else total + res.loss     # each call already divides by sclm+1
+                losses["consistency_loss/{}".format(s)] = v[k + 2]
+            losses["loss/{}".format(s)] = v[k]
+        total = v[0] if total is None else total + v[0]     # each call already divides by sclm+1
     losses["loss"] = total
     if getattr(self, "ppea_keep_maps", False):
         outputs[("ppea_maps", bool(is_multi))] = results
@@ -196,8 +212,17 @@ def compute_matching_mask(self, outputs):
     return mask
 
 
-def install(trainer_cls, deterministic=False, noise_mode="reference", fused=None):
-    """Rebinds the reference Trainer's loss methods to the fused implementation."""
+def install(trainer_cls, deterministic=False, noise_mode="reference", fused=None, plan_cache=True, materialize_warps=False):
+    """Rebinds the reference Trainer's loss methods to the fused implementation.
+
+    deterministic      bit-reproducible gradients (64-bit fixed-point accumulation of the coarse-scale fields)
+    noise_mode         "reference": the automask's tie-break noise from the CPU generator exactly as the reference draws it;
+                       "device": one torch.randn on the GPU per call
+    fused              None: the fused training step whenever gradients are needed; "tiles" / False: see VslConfig.fused
+    plan_cache         reuse pre-built parameter blocks and a ring of output buffers per (shape, flags): the outputs of a
+                       call (depth maps, loss tensors) stay valid until the second next call of the same kind
+    materialize_warps  also produce ("sample" | "color" | "color_identity", f, s) as the reference does (trainer.py:909-918)
+    """
     trainer_cls.generate_images_pred = generate_images_pred
     trainer_cls.compute_reprojection_loss = compute_reprojection_loss
     trainer_cls.compute_loss_masks = staticmethod(compute_loss_masks)
@@ -206,6 +231,8 @@ def install(trainer_cls, deterministic=False, noise_mode="reference", fused=None
     trainer_cls.ppea_deterministic = deterministic
     trainer_cls.ppea_noise_mode = noise_mode
     trainer_cls.ppea_fused = fused     # None: single-launch training step whenever it applies (functional.VslConfig.fused)
+    trainer_cls.ppea_plan_cache = plan_cache
+    trainer_cls.ppea_materialize_warps = materialize_warps
     return trainer_cls
 
 
@@ -213,9 +240,12 @@ class ViewSynthesisLoss:
     """Stand-alone holder of the four methods for callers without the reference Trainer
     (tests, bench.py): ``ViewSynthesisLoss(opt).generate_images_pred(inputs, outputs)`` etc."""
 
-    def __init__(self, opt, deterministic=False, noise_mode="reference", keep_maps=False, fused=None):
+    def __init__(self, opt, deterministic=False, noise_mode="reference", keep_maps=False, fused=None, plan_cache=True,
+                 materialize_warps=False):
         self.opt = opt
         self.ppea_fused = fused
+        self.ppea_plan_cache = plan_cache
+        self.ppea_materialize_warps = materialize_warps
         self.ppea_deterministic = deterministic
         self.ppea_noise_mode = noise_mode
         self.ppea_keep_maps = keep_maps

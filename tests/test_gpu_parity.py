@@ -144,7 +144,22 @@ def test_full_size_kitti_against_oracle(multi, fused):
     noise = make_noise(cfg, 4)
     opt = O.default_opt(sclm=3, height=192, width=640, batch_size=12)
     losses, grads, maps = run_cuda(inputs, outputs, opt, multi, None if multi else noise, fused=fused)
-    n_flip = check_against_oracle(inputs, outputs, opt, multi, noise, losses, grads, maps)
+    report = {}
+    n_flip = check_against_oracle(inputs, outputs, opt, multi, noise, losses, grads, maps, report=report)
+    # at BASELINE's size the PRIMARY bounds decide: every loss within 1e-5 and every gradient within 1e-4 of the fp32
+    # reference-order oracle, or -- disparity gradients -- in the class of the reference's own fp32 (gpu_helpers: "fp32-class")
+    # -- none of the float64 / kink allowances of the small fixtures is needed
+    m64 = report.pop("_m64")
+    # (pose gradients are sums over every pixel, knife-edge samples included: "kink" = at least as close to the float64
+    # gradient as the reference's own fp32 is, factor 2)
+    ok = lambda k, v: v.startswith("fp32") or (k[0] == "cam_T_cam" and v == "kink")
+    assert all(ok(k, v) for k, v in report.items()), {k: v for k, v in report.items() if not ok(k, v)}
+    # ... and the pixels of the full-resolution gradient that do deviate are the knife-edge samples
+    from gpu_helpers import knife_edge_pixels
+    l64g = O.run_fwd_bwd(inputs, outputs, opt, multi, noise, dtype=torch.float64, forced=forced_from(maps))[1]
+    km, n_knife = knife_edge_pixels(m64, inputs, opt)[0]
+    bad = (grads[("disp", 0)].double() - l64g[("disp", 0)]).abs() > 1e-4 * float(l64g[("disp", 0)].abs().max())
+    assert int((bad & km).sum()) >= 0.8 * int(bad.sum()) and int(bad.sum()) <= n_knife, (int(bad.sum()), int((bad & km).sum()), n_knife)
     if not multi:
         # unforced: the loss still agrees with the reference-order oracle to 1e-5 at full size
         l32, _, _ = O.run_fwd_bwd(inputs, outputs, opt, multi, noise)
@@ -187,7 +202,8 @@ def test_full_size_properties(name, det):
             assert torch.equal(grads[k], g2[k]), k
 
 
-def test_unaligned_frames_take_the_non_tma_path():
+@pytest.mark.parametrize("fused", [None, "tiles"])
+def test_unaligned_frames_take_the_non_tma_path(fused):
     """Colour frames whose base address is not 16-byte aligned cannot be described by a TMA tensor map: the fused kernel
     stages them with its reflecting loop instead.  Same per-pixel maps and loss, bit for bit."""
     from gpu_helpers import FeedNoise
@@ -208,7 +224,7 @@ def test_unaligned_frames_take_the_non_tma_path():
                     view.copy_(t)
                     assert view.data_ptr() % 16 == 4
                     ins[k] = view
-        mod = ViewSynthesisLoss(opt, keep_maps=True)
+        mod = ViewSynthesisLoss(opt, keep_maps=True, fused=fused)
         with FeedNoise(noise):
             mod.generate_images_pred(ins, outs, False)
             losses, _ = mod.compute_losses(ins, outs, False)
@@ -267,6 +283,7 @@ def test_no_out_of_bounds_writes(shape, multi, det):
     def guarded_empty_like(t, **kw):
         return guarded_empty(*t.shape, device=t.device, dtype=kw.get("dtype", t.dtype))
 
+    Fn._PLANS.clear()          # (the cached step plan of these shapes would otherwise hand out buffers allocated earlier, unguarded)
     mod = ViewSynthesisLoss(opt, deterministic=det, keep_maps=True)
     with mock.patch.object(Fn.torch, "empty", guarded_empty), mock.patch.object(Fn.torch, "empty_like", guarded_empty_like):
         with FeedNoise(noise):
@@ -282,3 +299,4 @@ def test_no_out_of_bounds_writes(shape, multi, det):
                 assert bool(torch.isnan(guard).all()), (n, dt)
             else:
                 assert bool((guard == SENT[dt]).all()), (n, dt)
+    Fn._PLANS.clear()          # (do not leave plans whose buffers sit inside the guarded allocations)
