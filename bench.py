@@ -6,21 +6,32 @@ One "step" = generate_images_pred + compute_losses + loss.backward() for one KIT
 /root/reference/ppeadepth/trainer.py:871-918, 1032-1160), i.e. BASELINE.json configs[1].
 
   value     Mpixels/s = N_gpus * B*H*W * steps / time, inputs resident in HBM, forward+backward of the
-            C ABI replayed as CUDA graphs, rotating over input sets larger than L2.
+            C ABI replayed as CUDA graphs, rotating over input sets larger than L2.  `loss_check`: after
+            the timed loop the replayed plan's loss is compared with the public API's on the same inputs.
   e2e       the same metric through the public host API (ppea_depth_b200.loss.ViewSynthesisLoss) with
-            pinned HOST inputs: H2D of every input, forward, backward, D2H of the loss, every step.
-  roofline  the dominant kernel's algorithmic bytes / its CUDA-event duration / measured HBM peak.
-  cpu_baseline / --impl reference   the reference algorithm (oracle port, PyTorch CPU ops exactly as
-            the reference calls them) timed on this box's host cores on a bounded sample.
+            pinned HOST inputs: H2D of every input, forward, backward, D2H of the loss, every step; colour
+            frames as the dataset's uint8 planes (expanded on the device, bit-identical to ToTensor), noise
+            drawn on the device; median of the repetitions.  `e2e.float32_frames`: the same with fp32 frames.
+  roofline  SURVEY.md §8d algorithmic bytes of the step / the dominant kernel's CUDA-event duration /
+            measured HBM peak (MEASURED_PEAKS.json).
+  cpu_baseline / --impl reference   the reference's own CPU implementation (the unmodified ppeadepth loss
+            methods from oracle/_ref when present -- kind "reference" -- else the oracle port) timed on
+            this box's host cores on a bounded sample; `threads_1` is the reference-faithful single-thread
+            number (trainer.py:8-10 pins the pools to one thread), `torch_cuda_eager` the same ATen op
+            sequence run by PyTorch on this GPU (what a user of the reference has today).
+  N > 1     weak scaling (every rank owns its own 12-image batch; the loss path has no data-path collective,
+            SURVEY.md §8e) is the headline; the line also carries the STRONG-scaling point of BASELINE
+            configs[4] (`sharded_sweep96`: global batch 96 split over the ranks) and one NCCL all-reduce of a
+            0.3 GB fp32 stand-in for the adapter gradients (trainer.py:350), alone and overlapped with the step.
 
-Launch: `python bench.py` (1 GPU) or torchrun --nproc-per-node N bench.py --gpus N (weak scaling: every
-rank owns its own 12-image batch; the loss path has no data-path collective).
+Launch: `python bench.py` (1 GPU) or torchrun --nproc-per-node N bench.py --gpus N.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import statistics
 import subprocess
 import sys
 import threading
@@ -38,6 +49,7 @@ WORKLOADS = {
     "sweep96": dict(batch=96, height=192, width=640, num_scales=4),
 }
 L2_BYTES = 126 * 1024 * 1024
+ALLREDUCE_FLOATS = 75_000_000        # 0.3 GB fp32: the adapter / decoder-adapter gradients of RepLKNet-31B stage 1
 
 
 def parse():
@@ -49,19 +61,18 @@ def parse():
     ap.add_argument("--workload", default="kitti", choices=sorted(WORKLOADS))
     ap.add_argument("--path", default="mono", choices=["mono", "multi"])
     ap.add_argument("--deterministic", action="store_true")
-    ap.add_argument("--no-fused", action="store_true", help="forward + backward kernel pair instead of the single-launch step")
+    ap.add_argument("--shard", action="store_true", help="strong scaling: the workload's batch is split over the ranks")
+    ap.add_argument("--no-fused", action="store_true", help="forward + backward kernel pair instead of the fused step")
     ap.add_argument("--tiles", action="store_true", help="fused step by the shared-memory tile kernel (round 1) instead of the streaming kernel")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the sharded sweep / all-reduce legs (N > 1) and the torch-CUDA eager leg (N = 1)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of one repetition of the e2e leg (default: min(steps, 100))")
     return ap.parse_args()
 
 
 def dist_env():
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    return rank, world, local
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -120,15 +131,14 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- workload
-def make_sets(wl, n_sets, seed0, device, is_multi):
-    """n_sets independent synthetic batches resident on `device` (+ their pinned host copies)."""
+def make_sets(wl, n_sets, seed0, is_multi):
+    """n_sets independent synthetic batches (host tensors)."""
     from ppea_depth_b200.synth import SynthConfig, make_batch, make_noise
     sets = []
     for i in range(n_sets):
         cfg = SynthConfig(seed=seed0 + i, **wl)
         inputs, outputs = make_batch(cfg)
-        noise = make_noise(cfg, wl["num_scales"])
-        sets.append((inputs, outputs, noise))
+        sets.append((inputs, outputs, make_noise(cfg, wl["num_scales"])))
     return sets
 
 
@@ -168,7 +178,6 @@ def build_plan(tset, wl, device, is_multi, deterministic, fused=None):
     S = wl["num_scales"]
     d = lambda x: x.to(device)
     cfg = VslConfig(is_multi=is_multi, deterministic=deterministic)
-    kw = {}
     if is_multi:
         kw = dict(cons_mask=d(outputs["consistency_mask"]), aug_mask=d(outputs["augmentation_mask"]),
                   mono_depth=[d(outputs[("mono_depth", 0, s)]) for s in range(S)])
@@ -194,13 +203,47 @@ def max_over_ranks(ms, world, device):
     return float(t.item())
 
 
+def time_replays(plans, K, Wm, world, device):
+    """Wm warm-up + K timed graph replays rotating over `plans`; ms per step, max over ranks."""
+    n = len(plans)
+    for i in range(Wm):
+        plans[i % n].replay()
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        plans[i % n].replay()
+    e1.record()
+    barrier(world)
+    return max_over_ranks(e0.elapsed_time(e1), world, device) / K
+
+
+def api_opt(B, H, W, S):
+    from types import SimpleNamespace
+    return SimpleNamespace(sclm=S - 1, v1_multiscale=False, height=H, width=W, min_depth=0.1, max_depth=100.0,
+                           frame_ids=[0, -1, 1], disable_automasking=False, no_ssim=False, selec_reproj=True,
+                           disable_motion_masking=False, no_matching_augmentation=False, batch_size=B,
+                           disparity_smoothness=1e-3)
+
+
 # ----------------------------------------------------------------------------- CPU reference arm
-def time_cpu_reference(wl, is_multi, steps, warmup, budget_s=150.0):
-    """The reference algorithm (oracle port = the same ATen CPU ops the reference dispatches) on the host
-    cores: fwd+bwd on a bounded sample of the workload's batch."""
+def time_cpu_reference(wl, is_multi, steps, warmup, budget_s=150.0, threads=None):
+    """The reference's CPU implementation on the host cores: fwd+bwd on a bounded sample of the workload's batch.
+    kind "reference": the UNMODIFIED ppeadepth.trainer.Trainer loss methods (oracle/_ref or /root/reference through
+    oracle/ref_import.py); kind "port": the oracle restatement (the same ATen CPU ops in the same order)."""
+    from oracle import ref_import as R
     from oracle import vsl_oracle as O
     from ppea_depth_b200.synth import SynthConfig, make_batch, make_noise
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    if threads is not None:
+        cores = threads
+    kind = "port"
+    if R.available():
+        try:
+            R.load_reference()
+            kind = "reference"
+        except Exception:                    # (an import the stubs do not cover: fall back to the port)
+            kind = "port"
     torch.set_num_threads(cores)
     H, W, S = wl["height"], wl["width"], wl["num_scales"]
 
@@ -212,7 +255,10 @@ def time_cpu_reference(wl, is_multi, steps, warmup, budget_s=150.0):
         ts = []
         for i in range(n_warm + n_steps):
             t0 = time.perf_counter()
-            O.run_fwd_bwd(inputs, outputs, opt, is_multi, noise)
+            if kind == "reference":
+                R.run_reference(inputs, outputs, opt, is_multi, None if is_multi else noise)
+            else:
+                O.run_fwd_bwd(inputs, outputs, opt, is_multi, noise)
             if i >= n_warm:
                 ts.append(time.perf_counter() - t0)
         return ts
@@ -223,30 +269,84 @@ def time_cpu_reference(wl, is_multi, steps, warmup, budget_s=150.0):
     ts = run(n_items, steps, warmup)
     mean_t = sum(ts) / len(ts)
     mpix = n_items * H * W / mean_t / 1e6
-    sample = "%d of %d images per step (%dx%d, %d scales, %s path), %d steps after %d warm-up, mean %.3f s/step" % (
-        n_items, wl["batch"], H, W, S, "multi" if is_multi else "mono", steps, warmup, mean_t)
-    return mpix, mean_t * 1e3, cores, sample
+    sample = "%d of %d images per step (%dx%d, %d scales, %s path), %d steps after %d warm-up, mean %.3f s/step, %d threads" % (
+        n_items, wl["batch"], H, W, S, "multi" if is_multi else "mono", steps, warmup, mean_t, cores)
+    return mpix, mean_t * 1e3, cores, sample, kind
+
+
+def time_torch_cuda_eager(wl, device, steps=10):
+    """The reference's ATen op sequence (oracle port) run by PyTorch eager on THIS GPU: what a user of the reference has
+    today (minus its nonzero() host syncs and its CPU noise).  Resident inputs, device noise."""
+    from oracle import vsl_oracle as O
+    from ppea_depth_b200.synth import SynthConfig, make_batch
+    B, H, W, S = wl["batch"], wl["height"], wl["width"], wl["num_scales"]
+    inputs, outputs = make_batch(SynthConfig(seed=7, **wl))
+    ins = {k: v.to(device) for k, v in inputs.items()}
+    base = {k: v.to(device) for k, v in outputs.items()}
+    opt = O.default_opt(sclm=S - 1, height=H, width=W, batch_size=B)
+
+    def step():
+        outs = dict(base)
+        for s in range(S):
+            outs[("disp", s)] = base[("disp", s)].detach().requires_grad_(True)
+        for f in (-1, 1):
+            outs[("cam_T_cam", 0, f)] = base[("cam_T_cam", 0, f)].detach().requires_grad_(True)
+        noise = [torch.randn(B, 1, H, W, device=device) for _ in range(S)]
+        losses, _ = O.view_synthesis_losses(ins, outs, opt, False, noise)
+        losses["loss"].backward()
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"ms_per_step": ms, "value": B * H * W / ms / 1e3, "unit": "Mpixels/s", "steps": steps,
+            "what": "reference op sequence (oracle port of trainer.py:871-918 + 1032-1160) in PyTorch CUDA eager on this GPU, resident inputs, device noise"}
+
+
+def pin_rank_to_cores(rank, world):
+    """Every rank gets its own slice of the host cores (the box reports one NUMA node and one affinity mask for all
+    GPUs): the ranks' enqueue threads and pinned-memory copies stop competing for the same cores."""
+    if world <= 1 or not hasattr(os, "sched_getaffinity"):
+        return None
+    cpus = sorted(os.sched_getaffinity(0))
+    per = max(1, len(cpus) // world)
+    mine = cpus[rank * per:(rank + 1) * per] or cpus
+    try:
+        os.sched_setaffinity(0, mine)
+        torch.set_num_threads(max(1, min(4, len(mine))))
+    except OSError:
+        return None
+    return mine
 
 
 def main():
     args = parse()
     rank, world, local = dist_env()
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload])
     is_multi = args.path == "multi"
+    global_batch = wl["batch"]
+    if args.shard and world > 1:
+        wl["batch"] = max(1, wl["batch"] // world)
     B, H, W, S = wl["batch"], wl["height"], wl["width"], wl["num_scales"]
-    cfg_desc = {"workload": "%s %dx3x%dx%d, frame_ids [0,-1,1], %d scales, %s path (generate_images_pred + compute_losses + backward)"
-                % (args.workload, B, H, W, S, args.path), "pixels_per_step_per_gpu": B * H * W, "scales": S,
-                "path": args.path, "deterministic_backward": bool(args.deterministic)}
+    cfg_desc = {"workload": "%s %dx3x%dx%d%s, frame_ids [0,-1,1], %d scales, %s path (generate_images_pred + compute_losses + backward)"
+                % (args.workload, global_batch if args.shard else B, H, W, " split over the ranks" if args.shard else "", S, args.path),
+                "pixels_per_step_per_gpu": B * H * W, "scales": S, "path": args.path, "deterministic_backward": bool(args.deterministic)}
 
     if args.impl == "reference":
         if rank != 0:
             return
-        mpix, ms, cores, sample = time_cpu_reference(wl, is_multi, max(1, args.steps), max(0, args.warmup))
+        mpix, ms, cores, sample, kind = time_cpu_reference(wl, is_multi, max(1, args.steps), max(0, args.warmup))
         line = {"impl": "reference", "metric": "view-synthesis loss fwd+bwd throughput", "value": mpix, "unit": "Mpixels/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "higher_is_better": True, "scaling": "strong" if args.shard else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": cfg_desc,
-                "cpu_baseline": {"value": mpix, "unit": "Mpixels/s", "cores": cores, "kind": "port", "sample": sample},
+                "cpu_baseline": {"value": mpix, "unit": "Mpixels/s", "cores": cores, "kind": kind, "sample": sample},
                 "e2e": {"value": mpix, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -256,9 +356,9 @@ def main():
                          "use --impl reference for the CPU reference arm")
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    cores_mine = pin_rank_to_cores(rank, world)
     if world > 1:
-        # NCCL's version banner / warnings off stdout (rank 0 prints ONE JSON line): NCCL honours NCCL_DEBUG_FILE only above
-        # the VERSION level, which is what this image sets
+        # NCCL's version banner / warnings off stdout (rank 0 prints ONE JSON line)
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
@@ -266,23 +366,25 @@ def main():
     from ppea_depth_b200 import _cabi
     from ppea_depth_b200.synth import algorithmic_bytes
     _cabi.lib()          # fail loudly if the extension is missing
+    fused_arg = False if args.no_fused else ("tiles" if args.tiles else None)
 
     # ---- resident input sets, sized to exceed L2
-    probe = make_sets(wl, 1, 1000 * rank, device, is_multi)
+    probe = make_sets(wl, 1, 1000 * rank, is_multi)
     step_bytes = sum(v.numel() * v.element_size() for v in tensors_of_step(*probe[0], S, is_multi).values())
-    n_sets = max(4, int(2.5 * L2_BYTES // step_bytes) + 1)
-    n_sets = min(n_sets, 12)
-    sets = probe + make_sets(wl, n_sets - 1, 1000 * rank + 1, device, is_multi)
-    plans = [build_plan(t, wl, device, is_multi, args.deterministic, fused=False if args.no_fused else ("tiles" if args.tiles else None)) for t in sets]
-    fused = plans[0].fused
-    tiles = plans[0].tiles
-    cfg_desc["kernels"] = ("single-launch fused step (vsl_fused_kernel, TMA-staged tiles) + finish + gradient finish (tails launched programmatically)" if fused
-                           else "vsl_forward_kernel + finish + vsl_backward_kernel + pose finish")
+    n_sets = min(12, max(4, int(2.5 * L2_BYTES // step_bytes) + 1))
+    if step_bytes > 2 * L2_BYTES:
+        n_sets = 2
+    sets = probe + make_sets(wl, n_sets - 1, 1000 * rank + 1, is_multi)
+    plans = [build_plan(t, wl, device, is_multi, args.deterministic, fused=fused_arg) for t in sets]
+    fused, tiles = plans[0].fused, plans[0].tiles
+    kernels = ("fused step: preparation launch (packed sources, identity loss, smoothness CTAs) + warp-streaming kernel + finish + gradient finish "
+               "(tails launched programmatically)" if fused and not tiles else
+               "fused step: tile kernel (TMA-staged tiles) + finish + gradient finish" if fused else
+               "vsl_forward_kernel + finish + vsl_backward_kernel + pose finish")
     for p in plans:
         p.capture()
     launches_per_step = plans[0].launches_forward + plans[0].launches_backward
-    cfg_desc["l2"] = "rotating %d resident input sets (%.0f MB read per step, %.0f MB total) > 126 MB L2" % (
-        n_sets, step_bytes / 1e6, n_sets * step_bytes / 1e6)
+    l2_note = "rotating %d resident input sets (%.0f MB read per step, %.0f MB total) > 126 MB L2" % (n_sets, step_bytes / 1e6, n_sets * step_bytes / 1e6)
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -291,19 +393,38 @@ def main():
 
     # ---- value: HBM-resident, graph replay
     K, Wm = max(1, args.steps), max(3, args.warmup)
-    for i in range(Wm):
-        plans[i % n_sets].replay()
-    barrier(world)
     t_clock0 = time.time()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(K):
-        plans[i % n_sets].replay()
-    e1.record()
-    barrier(world)
-    ms_total = max_over_ranks(e0.elapsed_time(e1), world, device)
-    ms_step = ms_total / K
+    ms_step = time_replays(plans, K, Wm, world, device)
     value = world * B * H * W / (ms_step * 1e-3) / 1e6
+
+    # ---- loss_check: the replayed plan against the public API on the same inputs
+    from ppea_depth_b200.loss import ViewSynthesisLoss
+    loss_check = None
+    if rank == 0:
+        plans[0].replay()
+        torch.cuda.synchronize()
+        loss_plan = float(plans[0].losses[0])
+        inputs0, outputs0, noise0 = sets[0]
+        ins = {k: v.to(device) for k, v in inputs0.items()}
+        outs = {k: v.to(device) for k, v in outputs0.items()}
+        for s in range(S):
+            outs[("disp", s)].requires_grad_(True)
+        mod = ViewSynthesisLoss(api_opt(B, H, W, S), deterministic=args.deterministic, fused=fused_arg)
+        real_randn = torch.randn
+        draws = iter(noise0)
+        torch.randn = lambda *a, **k: next(draws).clone() if k.get("device") is None else real_randn(*a, **k)
+        try:
+            mod.generate_images_pred(ins, outs, is_multi)
+            losses, _ = mod.compute_losses(ins, outs, is_multi)
+        finally:
+            torch.randn = real_randn
+        losses["loss"].backward()
+        loss_api = float(losses["loss"])
+        g_api, g_plan = outs[("disp", 0)].grad, plans[0].grad_disp[0]
+        gerr = float((g_api - g_plan).abs().max() / g_api.abs().max())
+        loss_check = {"graph_replay_loss": loss_plan, "api_loss": loss_api, "rel_diff": abs(loss_plan - loss_api) / abs(loss_api),
+                      "grad_disp0_rel_diff": gerr, "ok": abs(loss_plan - loss_api) <= 1e-6 * abs(loss_api) and gerr <= 1e-5}
+        assert loss_check["ok"], loss_check
 
     # ---- roofline: per-kernel CUDA events (eager launches with the library's trace events), same rotation
     roof = None
@@ -312,8 +433,10 @@ def main():
         n_tr = min(K, 60)
         for p in plans:
             p.enable_trace()
+        # (two steps in flight before the first trace is read: the host's launch latency stays out of the stage times)
         for i in range(n_tr):
             p = plans[i % n_sets]
+            p.step()
             p.step()
             for k, v in p.trace_ms().items():
                 acc[k] = acc.get(k, 0.0) + v
@@ -326,44 +449,38 @@ def main():
         else:
             peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
         n_px = B * H * W
-        # SURVEY.md §8d per-pixel algorithmic bytes, split per launch: forward 49 + 16/4^s (mono) and backward 37 + 8/4^s,
-        # multi: forward 53 + 16/4^s, backward 45 + 8/4^s; deterministic backward +8.
-        fwd_b = sum((53.0 if is_multi else 49.0) + 16.0 / 4 ** s for s in range(S)) * n_px
-        bwd_b = sum((45.0 if is_multi else 37.0) + (8.0 if args.deterministic else 0.0) + 8.0 / 4 ** s for s in range(S)) * n_px
-        assert abs((fwd_b + bwd_b) - algorithmic_bytes(B, H, W, S, is_multi, args.deterministic)) < 1.0
+        # 86 + 24/4^s bytes per full-resolution pixel and scale on the mono path (forward 49 + 16/4^s,
+        # backward 37 + 8/4^s), 98 + 24/4^s on the multi path, +8 with the deterministic backward: 375.9 B/px for 4 scales.
+        step_bytes_alg = algorithmic_bytes(B, H, W, S, is_multi, args.deterministic)
         if fused:
-            # The fused launch does the forward AND the backward work of every pixel.scale but has to move less than the
-            # two-launch figure of SURVEY.md §8d: target/sources are read once, sel never round-trips.  Its own compulsory
-            # bytes: tgt 12 + src 24 + noise 4 + depth 4 + sel 1 + loss 4 + (disp 4 + colour 12 + raw grad 4 + stencil 4)/4^s;
-            # multi path: cons_mask 4 + mono_depth 4 instead of the noise, + consistency field 4/4^s.
             dom = "vsl_fused_kernel" if tiles else "vsl_stream_kernel"
-            dom_bytes = sum((53.0 if is_multi else 49.0) + (28.0 if is_multi else 24.0) / 4 ** s for s in range(S)) * n_px
         else:
             dom = "vsl_backward_kernel" if stage_ms["vsl_backward_kernel"] >= stage_ms["vsl_forward_kernel"] else "vsl_forward_kernel"
-            dom_bytes = bwd_b if dom == "vsl_backward_kernel" else fwd_b
+        # the fused kernels do the forward AND backward work of every pixel and scale in one launch: the §8d step bytes are
+        # the algorithmic bytes of that launch (the pair path splits them between its two kernels)
+        if fused:
+            dom_bytes = step_bytes_alg
+        else:
+            fwd_b = sum((53.0 if is_multi else 49.0) + 16.0 / 4 ** s for s in range(S)) * n_px
+            dom_bytes = step_bytes_alg - fwd_b if dom == "vsl_backward_kernel" else fwd_b
         achieved = dom_bytes / (stage_ms[dom] * 1e-3) / 1e9
         traffic = None            # DRAM bytes of one launch of that kernel from the committed ncu capture (same workload only)
-        tpath = os.path.join(ROOT, "profiles", "r1j_traffic.json" if fused else "r1f_traffic.json")
-        if os.path.exists(tpath) and args.workload == "kitti" and not is_multi and not args.deterministic:
+        tpath = os.path.join(ROOT, "profiles", "r2_traffic.json" if (fused and not tiles) else ("r1j_traffic.json" if fused else "r1f_traffic.json"))
+        if os.path.exists(tpath) and args.workload == "kitti" and not is_multi and not args.deterministic and not args.shard:
             traffic = json.load(open(tpath)).get(dom)
         roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
-                "kernel_ms": stage_ms[dom], "stage_ms": stage_ms,
-                "step_algorithmic_bytes": fwd_b + bwd_b,
-                "kernel_frac_at_survey_step_bytes": (fwd_b + bwd_b) / (stage_ms[dom] * 1e-3) / 1e9 / peak if fused else None,
-                "step_frac_of_peak": (fwd_b + bwd_b) / (ms_step * 1e-3) / 1e9 / peak,
-                "frac_of_8TBs_nominal": achieved / 8000.0}
+                "bytes_per_pixel": dom_bytes / n_px, "kernel_ms": stage_ms[dom], "stage_ms": stage_ms,
+                "step_frac_of_peak": step_bytes_alg / (ms_step * 1e-3) / 1e9 / peak,
+                "frac_of_8TBs_nominal": achieved / 8000.0,
+                "note": "the step is bound by instruction issue and dependent-issue latency, not by HBM (profiles/README.md): "
+                        "DRAM traffic of the launch is far below the algorithmic bytes"}
 
     # ---- e2e: public host API, pinned host inputs, H2D + fwd + bwd + D2H(loss) every step
     e2e = None
     if not args.no_e2e:
-        from types import SimpleNamespace
-        from ppea_depth_b200.loss import ViewSynthesisLoss
-        opt = SimpleNamespace(sclm=S - 1, v1_multiscale=False, height=H, width=W, min_depth=0.1, max_depth=100.0,
-                              frame_ids=[0, -1, 1], disable_automasking=False, no_ssim=False, selec_reproj=True,
-                              disable_motion_masking=False, no_matching_augmentation=False, batch_size=B,
-                              disparity_smoothness=1e-3)
-        mod = ViewSynthesisLoss(opt, deterministic=args.deterministic, noise_mode="device", fused=False if args.no_fused else ("tiles" if args.tiles else None))
+        mod = ViewSynthesisLoss(api_opt(B, H, W, S), deterministic=args.deterministic, noise_mode="device", fused=fused_arg)
+
         def collate(t):
             """One pinned arena per batch (what a collate_fn writing into a pinned buffer gives): a step's inputs cross
             PCIe as ONE copy.  Returns (arena, layout) with layout[key] = (byte offset, shape, dtype); uint8 frames first,
@@ -382,11 +499,8 @@ def main():
         step_tensors = []
         for (inputs, outputs, noise) in sets[:4]:
             t = tensors_of_step(inputs, outputs, noise, S, is_multi)
-            step_tensors.append({k: v for k, v in t.items() if k[0] != "noise"})   # e2e draws the noise on the device (noise_mode="device")
-        host_sets = [collate(t) for t in step_tensors]
-        h2d = sum(v.numel() * v.element_size() for v in step_tensors[0].values())
+            step_tensors.append({k: v for k, v in t.items() if k[0] != "noise"})   # the noise is drawn on the device (noise_mode="device")
         Ke = args.e2e_steps or min(K, 100)    # (the two-batch pipeline fill at the start is inside the timed region)
-
         copy_stream = torch.cuda.Stream(device=device)
 
         def start_h2d(hs):
@@ -430,63 +544,118 @@ def main():
         loss_ev = [torch.cuda.Event() for _ in range(2)]
         DEPTH = 2     # batches in flight on the copy stream (a pin_memory DataLoader's prefetch_factor)
 
-        def e2e_run(n):
-            """n steps; the inputs of steps i+1 .. i+DEPTH are copied on the copy stream while step i computes (the copy
-            engine never waits for the host: one step of host-side enqueue is ~0.6 ms, close to the copy time
-            of a batch); every step ends with the D2H of its loss."""
+        def e2e_run(host_sets, n):
+            """n steps; the inputs of steps i+1 .. i+DEPTH are copied on the copy stream while step i computes; every
+            step ends with the D2H of its loss, which the host reads one step later (as a training loop logs it)."""
             from collections import deque
             q = deque(start_h2d(host_sets[j % len(host_sets)]) for j in range(min(DEPTH, n)))
-            last = 0.0
             for i in range(n):
                 cur = q.popleft()
                 if i + DEPTH < n:
                     q.append(start_h2d(host_sets[(i + DEPTH) % len(host_sets)]))
                 loss = e2e_compute(*cur)
-                # D2H of the step's result into pinned memory, every step; the host looks at it one step later (as a
-                # training loop logs its loss), so the GPU is not left idle while the host enqueues the next step
                 slot = i % 2
                 loss_host[slot].copy_(loss.detach().reshape(1), non_blocking=True)
                 loss_ev[slot].record()
                 if i >= 1:
                     loss_ev[1 - slot].synchronize()
-                    last = float(loss_host[1 - slot][0])
+                    float(loss_host[1 - slot][0])
             loss_ev[(n - 1) % 2].synchronize()
             return float(loss_host[(n - 1) % 2][0])
 
-        def time_e2e(repeats=3):
-            """Ke steps, `repeats` times; the PCIe / host side of this leg is noisy on a shared box (single runs between
-            1.22 and 1.85 ms/step were seen), so the best repetition is reported and every repetition is listed."""
-            e2e_run(3)
+        def time_e2e(host_sets, repeats=3):
+            """Ke steps, `repeats` times: the MEDIAN repetition is reported, every repetition is listed."""
+            e2e_run(host_sets, 3)
             ms = []
             for _ in range(repeats):
                 barrier(world)
                 f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 f0.record()
-                e2e_run(Ke)
+                e2e_run(host_sets, Ke)
                 f1.record()
                 barrier(world)
                 ms.append(max_over_ranks(f0.elapsed_time(f1), world, device) / Ke)
-            return min(ms), ms
+            return statistics.median(ms), ms
 
-        ms_e2e, rep_f32 = time_e2e()
-        e2e = {"value": world * B * H * W / (ms_e2e * 1e-3) / 1e6, "unit": "Mpixels/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e, "steps": Ke, "repeats_ms_per_step": rep_f32,
-               "api": "ppea_depth_b200.loss.ViewSynthesisLoss.generate_images_pred + compute_losses + backward (noise_mode=device); "
-                      "a step's inputs sit in one pinned arena and cross PCIe as one copy; the next two steps are copied on a second "
-                      "stream while step i computes; the loss is copied "
-                      "to pinned host memory every step and read by the host one step later"}
-        # Same call, colour frames handed over as the dataset's uint8 planes (SURVEY.md §8f rank 3) and expanded on the device
-        # (ppea_images_u8_to_f32, bit-identical to ToTensor): a quarter of the image bytes cross PCIe.  Reported beside the
-        # reference-facing float32 number, not instead of it.
-        for t in step_tensors:
-            for k in list(t):
-                if k[0] == "in" and k[1] == "color":
-                    t[k] = torch.round(t[k] * 255).to(torch.uint8)
-        host_sets = [collate(t) for t in step_tensors]
-        h2d_u8 = sum(v.numel() * v.element_size() for v in step_tensors[0].values())
-        ms_u8, rep_u8 = time_e2e()
-        e2e["uint8_frames"] = {"value": world * B * H * W / (ms_u8 * 1e-3) / 1e6, "unit": "Mpixels/s", "h2d_bytes_per_step": h2d_u8,
-                               "d2h_bytes_per_step": 4, "ms_per_step": ms_u8, "steps": Ke, "repeats_ms_per_step": rep_u8}
+        def leg(tensors):
+            host_sets = [collate(t) for t in tensors]
+            h2d = sum(v.numel() * v.element_size() for v in tensors[0].values())
+            ms, reps = time_e2e(host_sets)
+            return {"value": world * B * H * W / (ms * 1e-3) / 1e6, "unit": "Mpixels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms, "steps": Ke, "repeats_ms_per_step": reps, "h2d_gb_per_s": h2d / (ms * 1e-3) / 1e9}
+
+        f32_leg = leg(step_tensors)
+        # the dataset's frames are uint8 (ToTensor divides them by 255 on the CPU, mono_dataset.py:62,106): handed over as
+        # uint8 planes and expanded on the device (ppea_images_u8_to_f32, bit-identical), a quarter of the image bytes cross PCIe
+        u8_tensors = [{k: (torch.round(v * 255).to(torch.uint8) if (k[0] == "in" and k[1] == "color") else v) for k, v in t.items()} for t in step_tensors]
+        e2e = leg(u8_tensors)
+        e2e["frames"] = "uint8"
+        e2e["float32_frames"] = f32_leg
+        e2e["api"] = ("ppea_depth_b200.loss.ViewSynthesisLoss.generate_images_pred + compute_losses + backward (noise_mode=device, cached step "
+                      "plans); colour frames cross PCIe as the dataset's uint8 planes and are expanded on the device (images_to_float); a "
+                      "step's inputs sit in one pinned arena and cross as one copy; the next two steps are copied on a second stream while "
+                      "step i computes; the loss is copied to pinned host memory every step and read by the host one step later.  With "
+                      "the reference's own CPU noise (noise_mode=reference: 4 torch.randn of (B,1,H,W) on the host + 23.6 MB H2D) a step "
+                      "is bound by ~50 ms of host RNG instead.")
+
+    # ---- N > 1: strong-scaling point of BASELINE configs[4] and the adapter-gradient all-reduce; N = 1: context numbers
+    extras = {}
+    if not args.no_extras and not args.shard and args.workload == "kitti":
+        del plans
+        torch.cuda.empty_cache()
+        per = max(1, WORKLOADS["sweep96"]["batch"] // world)
+        wl96 = dict(WORKLOADS["sweep96"], batch=per)
+        sets96 = make_sets(wl96, 2, 5000 + 10 * rank, is_multi)
+        plans96 = [build_plan(t, wl96, device, is_multi, args.deterministic, fused=fused_arg) for t in sets96]
+        for p in plans96:
+            p.capture()
+        K96 = max(10, min(K, 50))
+        ms96 = time_replays(plans96, K96, 5, world, device)
+        extras["sharded_sweep96"] = {"global_batch": per * world, "batch_per_gpu": per, "ms_per_step": ms96, "steps": K96,
+                                     "value": per * world * H * W / (ms96 * 1e-3) / 1e6, "unit": "Mpixels/s", "scaling": "strong",
+                                     "note": "BASELINE configs[4]: global batch 96 at 192x640 split over the ranks, per-rank normalisation "
+                                             "(what the reference's DDP does), no data-path collective"}
+        if world > 1:
+            buf = torch.zeros(ALLREDUCE_FLOATS, device=device, dtype=torch.float32)
+            dist = torch.distributed
+
+            def timed(fn, n):
+                barrier(world)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for i in range(n):
+                    fn(i)
+                e1.record()
+                barrier(world)
+                return max_over_ranks(e0.elapsed_time(e1), world, device) / n
+
+            for _ in range(3):
+                dist.all_reduce(buf)
+            ar_ms = timed(lambda i: dist.all_reduce(buf), 10)
+
+            def overlapped(i):
+                work = dist.all_reduce(buf, async_op=True)      # NCCL's own stream: runs beside the step's kernels
+                plans96[i % 2].replay()
+                work.wait()
+
+            for i in range(3):
+                overlapped(i)
+            ov_ms = timed(overlapped, 10)
+            nbytes = ALLREDUCE_FLOATS * 4
+            extras["allreduce"] = {"bytes": nbytes, "allreduce_ms": ar_ms, "step_ms": ms96, "overlap_ms": ov_ms,
+                                   "serial_ms": ar_ms + ms96, "bus_gb_per_s": 2.0 * (world - 1) / world * nbytes / (ar_ms * 1e-3) / 1e9,
+                                   "limiter": "the all-reduce (%.2f ms for 0.3 GB) is %s than the sharded step (%.2f ms): overlapped they take %.2f ms "
+                                              "= %.0f %% of the longer one" % (ar_ms, "longer" if ar_ms > ms96 else "shorter", ms96, ov_ms,
+                                                                                100.0 * ov_ms / max(ar_ms, ms96)),
+                                   "what": "one flat-bucket NCCL all-reduce of a 0.3 GB fp32 stand-in for the adapter / decoder-adapter "
+                                           "gradients (trainer.py:350, size from SURVEY.md §2.2) on NCCL's stream, beside the sharded step"}
+            del buf
+        del plans96
+        if world == 1 and rank == 0:
+            try:
+                extras["torch_cuda_eager"] = time_torch_cuda_eager(WORKLOADS["kitti"], device)
+            except Exception as exc:         # (context only: never fail the bench for it)
+                extras["torch_cuda_eager"] = {"error": repr(exc)[:200]}
     t_clock1 = time.time()
 
     if rank != 0:
@@ -497,14 +666,19 @@ def main():
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        mpix, ms, cores, sample = time_cpu_reference(wl, is_multi, steps=3, warmup=1, budget_s=20.0)
-        cpu = {"value": mpix, "unit": "Mpixels/s", "cores": cores, "kind": "port", "sample": sample}
+        mpix, ms, cores, sample, kind = time_cpu_reference(wl, is_multi, steps=3, warmup=1, budget_s=20.0)
+        cpu = {"value": mpix, "unit": "Mpixels/s", "cores": cores, "kind": kind, "sample": sample}
+        mpix1, ms1, _, sample1, _ = time_cpu_reference(wl, is_multi, steps=2, warmup=1, budget_s=12.0, threads=1)
+        cpu["threads_1"] = {"value": mpix1, "unit": "Mpixels/s", "cores": 1, "sample": sample1,
+                            "note": "the reference pins OMP / MKL / NUMEXPR to one thread at import (trainer.py:8-10)"}
 
     line = {"metric": "view-synthesis loss fwd+bwd throughput", "value": value, "unit": "Mpixels/s", "n_gpus": world,
-            "steps": K, "warmup": Wm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "steps": K, "warmup": Wm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if args.shard else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg_desc,
             "mpixel_scales_per_s": value * S, "gpu_launches": launches_per_step * K, "launches_per_step": launches_per_step,
-            "clocks": clocks, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu}
+            "kernels": kernels, "l2": l2_note, "host_cores_of_rank0": cores_mine,
+            "clocks": clocks, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "loss_check": loss_check}
+    line.update(extras)
     print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()

@@ -20,7 +20,16 @@ import types
 
 import torch
 
-REFERENCE_ROOT = os.environ.get("PPEA_REFERENCE_ROOT", "/root/reference")
+def _reference_root():
+    """/root/reference in the build container; on the GPU box the copy that `oracle/build_ref.py` left under
+    `oracle/_ref/` (git-ignored, ships with the gpurun snapshot)."""
+    for root in (os.environ.get("PPEA_REFERENCE_ROOT"), "/root/reference", os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")):
+        if root and os.path.isfile(os.path.join(root, "ppeadepth", "trainer.py")):
+            return root
+    return os.environ.get("PPEA_REFERENCE_ROOT", "/root/reference")
+
+
+REFERENCE_ROOT = _reference_root()
 
 
 def available() -> bool:
