@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define PPEA_ABI_VERSION 6
+#define PPEA_ABI_VERSION 7
 
 /* error codes (negative) */
 #define PPEA_OK 0
@@ -249,6 +249,19 @@ int ppea_match_features(const float* current_feats, const float* lookup_feats, c
                         const float* inv_K, const float* depth_bins, float* cost_volume, float* missing_mask, int batch,
                         int num_lookup, int channels, int height, int width, int num_bins, int set_missing_to_max, float eps,
                         void* stream);
+
+/* `match_features_dyn`, networks/replk_matching_adapter.py:163-258 -- the variant the encoder takes when it is given a teacher
+ * depth (:400, :439-442; no caller inside the reference does): the same plane sweep with (a) an occlusion map of the lookup image
+ * (occlusion (N,h,w), 1 where sum_c RGB < 0.15 nearest-resized to the matching resolution, :166; indexed by batch item) projected
+ * into every layer; where its sample exceeds pool_threshold and aug_mask[b] == 0 (:196) the warped features become 1 (set_1, :202-203)
+ * or the 3-D max over the (2 pool_radius + 1)^3 neighbourhood of the un-occluded warped features (pool, :204-209; radius <= 2);
+ * (b) cv_min: the lookup frames are combined by minimum (zeros count as 1 before, ones become 0 after, :238-246) instead of averaged.
+ * occlusion / aug_mask may be NULL when neither set_1 nor pool is given. */
+int ppea_match_features_dyn(const float* current_feats, const float* lookup_feats, const float* relative_poses, const float* K,
+                            const float* inv_K, const float* depth_bins, const float* occlusion, const float* aug_mask,
+                            float* cost_volume, float* missing_mask, int batch, int num_lookup, int channels, int height, int width,
+                            int num_bins, int set_missing_to_max, int cv_min, int set_1, int pool, int pool_radius,
+                            float pool_threshold, float eps, void* stream);
 
 /* Tail of the matching block (replk_matching_adapter.py:380-387 compute_confidence_mask, :439-453 in forward), one sweep:
  * confidence (B,h,w) = [#(cost * (1 - missing) > 0 over the bins) == threshold] (missing may be NULL: cost is taken as is);

@@ -242,6 +242,168 @@ __global__ void __launch_bounds__(256) match_tail_kernel(float* __restrict__ cos
     for (int d = 0; d < D; ++d) c[(size_t)d * plane] = mul_rn(c[(size_t)d * plane], 0.f);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// match_features_dyn (replk_matching_adapter.py:163-258), the variant the encoder takes when it is handed a teacher depth
+// (:400, :439-442): the same plane sweep, plus (a) an occlusion map of the lookup image projected into every layer of the
+// volume -- where it exceeds pool_th, and the item is not augmented, the warped features become 1 (set_1) or the 3-D max
+// over the (2 pool_r + 1)^3 neighbourhood of the un-occluded warped features (pool, F.max_pool3d :206, out-of-volume
+// neighbours ignored like its -inf padding) -- and (b) the lookup frames combined by minimum instead of the average
+// (cv_min :238-246).  The reference materialises the (D,C,h,w) warped volume to pool it; here an occluded cell re-derives
+// the samples of its neighbours (their own projections, their own occlusion decision) on the fly -- occluded cells are few.
+// A thread owns one pixel and walks the depth bins of its CTA's chunk one at a time.
+// ---------------------------------------------------------------------------------------------------------------
+struct MatchDynArgs {
+  MatchArgs m;
+  const float* occ;       // (N,h,w) 0/1 occlusion map of the lookup images at the matching resolution, indexed by batch item (:166, :198)
+  const float* aug;       // (B) augmentation mask (item skipped when != 0, :196)
+  int cv_min, set_1, pool, pool_r;
+  float pool_th;
+};
+
+__device__ __forceinline__ float match_sample(const float* __restrict__ plane_ptr, const MatchTap& t, int w) {
+  const float* q = plane_ptr + t.off;
+  return fmaf(t.wse, __ldg(q + w + 1), fmaf(t.wsw, __ldg(q + w), fmaf(t.wne, __ldg(q + 1), t.wnw * __ldg(q))));
+}
+
+constexpr int kMatchDynMaxR = 2;
+
+__global__ void __launch_bounds__(kMatchThreads) match_features_dyn_kernel(const MatchDynArgs da) {
+  const MatchArgs& a = da.m;
+  __shared__ float sP[12];
+  __shared__ float siK[9];
+  __shared__ int s_skip;
+  const int b = blockIdx.y;
+  const int h = a.h, w = a.w, D = a.D, C = a.C;
+  const unsigned plane = (unsigned)(h * w);
+  const unsigned pix = blockIdx.x * kMatchThreads + threadIdx.x;
+  const bool live = pix < plane;
+  const int y = live ? (int)(pix / (unsigned)w) : 0, x = live ? (int)(pix - (unsigned)y * (unsigned)w) : 0;
+  if (threadIdx.x < 9) siK[threadIdx.x] = a.invK[b * 16 + (threadIdx.x / 3) * 4 + threadIdx.x % 3];
+  __syncthreads();
+  float ray[3];
+  pixel_ray(siK, (float)x, (float)y, ray);
+  const float cur_mask = (y >= 2 && y < h - 2 && x >= 2 && x < w - 2) ? 1.f : 0.f;
+  const float* cur_b = a.cur + (size_t)b * C * plane + pix;
+  float* cost_b = a.cost + (size_t)b * D * plane + pix;
+  float* miss_b = a.missing + (size_t)b * D * plane + pix;
+  const float fC = (float)C;
+  const bool occl = (da.set_1 || da.pool) && (__ldg(da.aug + b) == 0.f);
+  const float* occ_b = da.occ + (size_t)b * plane;
+  const int r = da.pool_r;
+  const int d_lo = blockIdx.z * kMatchChunk, d_hi = min(D, d_lo + kMatchChunk);
+
+  for (int d = d_lo; d < d_hi; ++d) {
+    float cost = da.cv_min ? 1.f : 0.f, cnt = 0.f;
+    for (int f = 0; f < a.F; ++f) {
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const float* T = a.poses + ((size_t)b * a.F + f) * 16;
+        float s = 0.f;
+        for (int e = 0; e < 16; ++e) s += T[e];
+        s_skip = (s == 0.f) ? 1 : 0;
+        compose_P(a.K + b * 16, T, sP);
+      }
+      __syncthreads();
+      if (s_skip) continue;
+      const MatchTap tap = match_setup(sP, ray, __ldg(a.bins + d), h, w, a.eps, cur_mask);
+      float acc = 0.f;
+      if (live) {
+        const float* look_f = a.look + ((size_t)b * a.F + f) * C * plane;
+        const bool masked = occl && match_sample(occ_b, tap, w) > da.pool_th;
+        if (!masked) {
+          for (int c = 0; c < C; ++c) acc += fabsf(match_sample(look_f + (size_t)c * plane, tap, w) - __ldg(cur_b + (size_t)c * plane));
+        } else if (da.set_1) {
+          for (int c = 0; c < C; ++c) acc += fabsf(1.f - __ldg(cur_b + (size_t)c * plane));
+        } else {
+          // pooled: the un-occluded neighbours' own samples (the occluded ones, this cell included, count as 0)
+          MatchTap nb[(2 * kMatchDynMaxR + 1) * (2 * kMatchDynMaxR + 1) * (2 * kMatchDynMaxR + 1)];
+          int n_nb = 0;
+          bool any_zero = false;         // some in-volume neighbour is occluded (contributes the value 0), e.g. this cell
+          for (int dd = -r; dd <= r; ++dd)
+            for (int dy = -r; dy <= r; ++dy)
+              for (int dx = -r; dx <= r; ++dx) {
+                const int d2 = d + dd, y2 = y + dy, x2 = x + dx;
+                if (d2 < 0 || d2 >= D || y2 < 0 || y2 >= h || x2 < 0 || x2 >= w) continue;
+                float ray2[3];
+                pixel_ray(siK, (float)x2, (float)y2, ray2);
+                const MatchTap t2 = match_setup(sP, ray2, __ldg(a.bins + d2), h, w, a.eps, 1.f);
+                if (match_sample(occ_b, t2, w) > da.pool_th)
+                  any_zero = true;
+                else
+                  nb[n_nb++] = t2;
+              }
+          for (int c = 0; c < C; ++c) {
+            const float* lp = look_f + (size_t)c * plane;
+            float vmax = any_zero ? 0.f : -INFINITY;
+            for (int k = 0; k < n_nb; ++k) vmax = fmaxf(vmax, match_sample(lp, nb[k], w));
+            acc += fabsf(vmax - __ldg(cur_b + (size_t)c * plane));
+          }
+        }
+      }
+      float diff = mul_rn(div_rn(acc, fC), tap.edge);
+      if (da.cv_min) {
+        if (diff == 0.f) diff = 1.f;                       // :238-240
+        cost = fminf(diff, cost);
+      } else {
+        cost += diff;
+        cnt += diff > 0.f ? 1.f : 0.f;
+      }
+    }
+    if (live) {
+      const float v = da.cv_min ? (cost == 1.f ? 0.f : cost) : cost / (cnt + 1e-7f);     // :245-248
+      cost_b[(size_t)d * plane] = v;
+      miss_b[(size_t)d * plane] = (v == 0.f) ? 1.f : 0.f;
+    }
+  }
+}
+
+extern "C" int ppea_match_features_dyn(const float* current_feats, const float* lookup_feats, const float* relative_poses, const float* K,
+                                       const float* inv_K, const float* depth_bins, const float* occlusion, const float* aug_mask,
+                                       float* cost_volume, float* missing_mask, int batch, int num_lookup, int channels, int height,
+                                       int width, int num_bins, int set_missing_to_max, int cv_min, int set_1, int pool, int pool_radius,
+                                       float pool_threshold, float eps, void* stream) {
+  if (!current_feats || !lookup_feats || !relative_poses || !K || !inv_K || !depth_bins || !cost_volume || !missing_mask) return PPEA_E_NULL;
+  if ((set_1 || pool) && (!occlusion || !aug_mask)) return PPEA_E_FLAGS;
+  if (batch <= 0 || batch > 65535 || num_lookup < 0 || channels <= 0 || height < 2 || width < 2 || num_bins <= 0 || num_bins > kMatchMaxBins ||
+      ceil_div(num_bins, kMatchChunk) > 65535 || (long long)height * width >= (1ll << 30) || pool_radius < 0 || pool_radius > kMatchDynMaxR)
+    return PPEA_E_SHAPE;
+  MatchDynArgs da;
+  MatchArgs& a = da.m;
+  a.cur = current_feats;
+  a.look = lookup_feats;
+  a.poses = relative_poses;
+  a.K = K;
+  a.invK = inv_K;
+  a.bins = depth_bins;
+  a.cost = cost_volume;
+  a.missing = missing_mask;
+  a.B = batch;
+  a.F = num_lookup;
+  a.C = channels;
+  a.h = height;
+  a.w = width;
+  a.D = num_bins;
+  a.set_missing_to_max = set_missing_to_max;
+  a.eps = eps;
+  da.occ = occlusion;
+  da.aug = aug_mask;
+  da.cv_min = cv_min;
+  da.set_1 = set_1;
+  da.pool = set_1 ? 0 : pool;          // (`if set_1 ... elif pool`, :202-205)
+  da.pool_r = pool_radius;
+  da.pool_th = pool_threshold;
+  const dim3 grid((unsigned)ceil_div(height * width, kMatchThreads), (unsigned)batch, (unsigned)ceil_div(num_bins, kMatchChunk));
+  match_features_dyn_kernel<<<grid, kMatchThreads, 0, (cudaStream_t)stream>>>(da);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  if (set_missing_to_max) {
+    const dim3 g2((unsigned)ceil_div(height * width, 256), (unsigned)batch);
+    match_fill_missing_kernel<<<g2, 256, 0, (cudaStream_t)stream>>>(cost_volume, num_bins, (unsigned)(height * width));
+    e = cudaGetLastError();
+  }
+  return (int)e;
+}
+
 extern "C" int ppea_match_tail(float* cost_volume, const float* missing_mask_or_null, float* confidence_or_null, float* mins_or_null,
                                long long* argmin_or_null, int batch, int num_bins, int height, int width, int threshold,
                                int mask_volume, void* stream) {

@@ -42,6 +42,43 @@ def match_features(current_feats, lookup_feats, relative_poses, K, invK, depth_b
     return cost, missing
 
 
+def match_features_dyn(current_feats, lookup_feats, relative_poses, K, invK, depth_bins, lookup_images, cv_min, aug_mask, set_1, pool,
+                       pool_r, pool_th, set_missing_to_max=True, eps=1e-7):
+    """`match_features_dyn` (replk_matching_adapter.py:163-258): match_features with the occlusion handling of the dynamic-scene
+    stage -- `lookup_images` (N,3,H,W) give the occlusion map (sum of RGB < 0.15, nearest-resized to the matching resolution; the
+    reference hard-codes 48x128, :166), `aug_mask` (B,1,1,1) switches it off per item, `set_1` / `pool` (radius `pool_r`, threshold
+    `pool_th`) choose the replacement, `cv_min` the combination of the lookup frames.  Same two outputs as match_features."""
+    import torch.nn.functional as Fnn
+    cur = _f32c(current_feats, "current_feats")
+    look = _f32c(lookup_feats, "lookup_feats")
+    poses = _f32c(relative_poses, "relative_poses")
+    K, invK = _f32c(K, "K"), _f32c(invK, "invK")
+    B, Cn, h, w = cur.shape
+    F = look.shape[1]
+    if look.shape != (B, F, Cn, h, w) or poses.shape != (B, F, 4, 4) or K.shape != (B, 4, 4) or invK.shape != (B, 4, 4):
+        raise ValueError("match_features_dyn: inconsistent shapes")
+    if int(pool_r) > 2:
+        raise ValueError("match_features_dyn: pool radius <= 2")
+    bins = torch.as_tensor(depth_bins, dtype=torch.float32).reshape(-1).to(cur.device).contiguous()
+    D = bins.numel()
+    occ = aug = None
+    if set_1 or pool:
+        imgs = _f32c(lookup_images, "lookup_images")
+        if imgs.shape[0] < B:
+            raise ValueError("match_features_dyn: one lookup image per batch item expected")
+        occ = (Fnn.interpolate((imgs.sum(1).unsqueeze(1) < 0.15).float(), [h, w])[:, 0] > 0).float().contiguous()      # :166, :198
+        aug = _f32c(aug_mask, "aug_mask").reshape(aug_mask.shape[0], -1)[:B, 0].contiguous()                            # aug_mask[b][0][0][0]
+    with torch.cuda.device(cur.device):
+        cost = torch.empty(B, D, h, w, device=cur.device, dtype=torch.float32)
+        missing = torch.empty(B, D, h, w, device=cur.device, dtype=torch.float32)
+        C.check(C.lib().ppea_match_features_dyn(cur.data_ptr(), look.data_ptr(), poses.data_ptr(), K.data_ptr(), invK.data_ptr(), bins.data_ptr(),
+                                                occ.data_ptr() if occ is not None else None, aug.data_ptr() if aug is not None else None,
+                                                cost.data_ptr(), missing.data_ptr(), B, F, Cn, h, w, D, 1 if set_missing_to_max else 0,
+                                                1 if cv_min else 0, 1 if set_1 else 0, 1 if pool else 0, int(pool_r), float(pool_th), float(eps),
+                                                torch.cuda.current_stream().cuda_stream))
+    return cost, missing
+
+
 def cost_volume_tail(cost_volume, missing_mask=None, num_bins_threshold=None, mask_volume=True):
     """The rest of the reference's matching block in one sweep (replk_matching_adapter.py:380-387, :439-453):
     confidence_mask = compute_confidence_mask(cost_volume * (1 - missing_mask)); mins, argmin = torch.min over the bins of
@@ -81,8 +118,19 @@ def match_features_method(self, current_feats, lookup_feats, relative_poses, K, 
     return match_features(current_feats, lookup_feats, relative_poses, K, invK, bins, bool(self.set_missing_to_max))
 
 
+def match_features_dyn_method(self, current_feats, lookup_feats, relative_poses, K, invK, lookup_images, cv_min, aug_mask, set_1, pool,
+                              pool_r, pool_th):
+    """Bound-method form with the reference's signature (replk_matching_adapter.py:163)."""
+    bins = self.warp_depths.reshape(self.warp_depths.shape[0], -1)[:, 0]
+    return match_features_dyn(current_feats, lookup_feats, relative_poses, K, invK, bins, lookup_images, cv_min, aug_mask, set_1, pool,
+                              pool_r, pool_th, bool(self.set_missing_to_max))
+
+
 def install_matching(encoder_cls):
-    """Rebinds `match_features` and `compute_confidence_mask` of a reference matching encoder class (RepLKMatchingAdapter, RepLKMatching, ResnetEncoderMatching)."""
+    """Rebinds `match_features`, `match_features_dyn` (where the class has it) and `compute_confidence_mask` of a reference matching
+    encoder class (RepLKMatchingAdapter, RepLKMatching, ResnetEncoderMatching)."""
     encoder_cls.match_features = match_features_method
+    if hasattr(encoder_cls, "match_features_dyn"):
+        encoder_cls.match_features_dyn = match_features_dyn_method
     encoder_cls.compute_confidence_mask = compute_confidence_mask_method
     return encoder_cls

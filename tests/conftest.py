@@ -28,7 +28,7 @@ def pytest_collection_modifyitems(config, items):
 
 def golden_names():
     # (the matching_*.pt / pose_*.pt fixtures belong to tests/test_matching.py / tests/test_pose.py)
-    return sorted(f[:-3] for f in os.listdir(GOLDEN_DIR) if f.endswith(".pt") and not f.startswith(("matching_", "pose_")))
+    return sorted(f[:-3] for f in os.listdir(GOLDEN_DIR) if f.endswith(".pt") and not f.startswith(("matching_", "matchdyn_", "pose_")))
 
 
 def load_golden(name):

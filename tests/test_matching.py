@@ -152,3 +152,119 @@ def test_matching_no_out_of_bounds_writes():
     for buf, n, dt, sent in tracked:
         for guard in (buf[:G], buf[G + n:]):
             assert bool(torch.isnan(guard).all()) if dt == torch.float32 else bool((guard == sent).all())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# match_features_dyn (replk_matching_adapter.py:163-258)
+# ---------------------------------------------------------------------------------------------------------------
+GOLDEN_DYN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "matchdyn_*.pt")))
+
+
+def _unpack_dyn(fx):
+    import numpy as np
+    B, _, h, w = fx["cur"].shape
+    D = fx["bins"].numel()
+    missing = torch.from_numpy(np.unpackbits(fx["missing_bits"].numpy())[:B * D * h * w].reshape(B, D, h, w).astype(np.float32))
+    return fx["images_u8"].float() / 255.0, missing
+
+
+@pytest.mark.parametrize("path", GOLDEN_DYN, ids=[os.path.basename(p)[:-3] for p in GOLDEN_DYN])
+def test_oracle_dyn_matches_reference_fixture(path):
+    """The restatement against the outputs of the reference's own method (kept layers, whole missing mask, float64 checksums
+    of the whole volume)."""
+    fx = _load(path)
+    img, missing = _unpack_dyn(fx)
+    cost, miss = M.match_features_dyn(fx["cur"], fx["look"], fx["poses"], fx["K"], fx["invK"], fx["bins"].numpy(), img, aug_mask=fx["aug"], **fx["opts"])
+    assert torch.equal(miss, missing)
+    assert float((cost[:, fx["kept_bins"]] - fx["cost"]).abs().max()) <= 1e-6
+    assert abs(float(cost.double().sum()) - fx["cost_sum"]) <= 1e-9 * abs(fx["cost_sum"])
+    assert abs(float((cost.double() ** 2).sum()) - fx["cost_sq"]) <= 1e-9 * abs(fx["cost_sq"])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/ppeadepth"), reason="reference not mounted")
+def test_oracle_dyn_matches_reference_live():
+    cur, look, poses, K, invK, bins, img, aug = M.synthetic_dyn_case(B=1, C=3, seed=5)
+    opts = dict(cv_min=False, set_1=False, pool=True, pool_r=1, pool_th=0.5)
+    want = M.run_reference_match_features_dyn(cur, look, poses, K, invK, bins, img, aug_mask=aug, **opts)
+    got = M.match_features_dyn(cur, look, poses, K, invK, bins, img, aug_mask=aug, **opts)
+    assert torch.equal(got[1], want[1])
+    assert float((got[0] - want[0]).abs().max()) <= 1e-6
+
+
+def _check_dyn_kernel(cur, look, poses, K, invK, bins, img, aug, opts, want_cost, want_missing, stm=True):
+    import ppea_depth_b200 as P
+    d = lambda t: t.to("cuda")
+    cost, missing = P.match_features_dyn(d(cur), d(look), d(poses), d(K), d(invK), bins, d(img), aug_mask=d(aug), set_missing_to_max=stm, **opts)
+    cost, missing = cost.cpu(), missing.cpu()
+    # border masks and the occlusion test (sample > pool_th) are decisions on fp32 coordinates: entries within rounding
+    # distance of a threshold may fall the other way; they must be rare, and every other entry must agree
+    same = missing == want_missing
+    assert float((~same).float().mean()) <= 2e-3, float((~same).float().mean())
+    ok_px = same.all(1, keepdim=True).expand_as(same) if stm else same
+    err = (cost - want_cost).abs()
+    flipped = (err > 2e-6 * max(1.0, float(want_cost.abs().max()))) & ok_px
+    assert float(flipped.float().mean()) <= 1e-3, (float(flipped.float().mean()), float(err[ok_px].max()))      # occlusion decisions at the threshold
+    return cost, missing
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", GOLDEN_DYN, ids=[os.path.basename(p)[:-3] for p in GOLDEN_DYN])
+def test_cuda_dyn_matches_reference_fixture(path):
+    fx = _load(path)
+    img, missing = _unpack_dyn(fx)
+    want_cost, _ = M.match_features_dyn(fx["cur"], fx["look"], fx["poses"], fx["K"], fx["invK"], fx["bins"].numpy(), img, aug_mask=fx["aug"], **fx["opts"])
+    cost, _ = _check_dyn_kernel(fx["cur"], fx["look"], fx["poses"], fx["K"], fx["invK"], fx["bins"].numpy(), img, fx["aug"], fx["opts"], want_cost, missing)
+    # ... and directly against the layers the reference itself produced
+    bad = (cost[:, fx["kept_bins"]] - fx["cost"]).abs() > 2e-6
+    assert float(bad.float().mean()) <= 3e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("opts", [dict(cv_min=True, set_1=False, pool=True, pool_r=2, pool_th=0.7),
+                                  dict(cv_min=False, set_1=False, pool=True, pool_r=1, pool_th=0.3),
+                                  dict(cv_min=True, set_1=True, pool=True, pool_r=1, pool_th=0.7),
+                                  dict(cv_min=False, set_1=False, pool=False, pool_r=1, pool_th=0.7)])
+@pytest.mark.parametrize("stm", [True, False])
+def test_cuda_dyn_matches_oracle(opts, stm):
+    """Sizes the reference method cannot run at (it hard-codes 48x128x96), two lookup frames, one augmented item."""
+    cur, look, poses, K, invK, bins = M.synthetic_case(B=2, Fr=2, C=6, h=30, w=52, D=20, seed=23, min_bin=0.4, max_bin=25.0)
+    g = torch.Generator().manual_seed(9)
+    img = torch.round((0.2 + 0.6 * torch.rand(2, 3, 120, 208, generator=g)) * 255) / 255
+    img[0, :, 20:60, 30:110] = 0.0
+    img[1, :, 50:100, 100:190] = 0.0
+    aug = torch.tensor([0.0, 0.0]).view(2, 1, 1, 1)
+    want_cost, want_missing = M.match_features_dyn(cur, look, poses, K, invK, bins, img, aug_mask=aug, set_missing_to_max=stm, **opts)
+    _check_dyn_kernel(cur, look, poses, K, invK, bins, img, aug, opts, want_cost, want_missing, stm)
+    if opts["pool"] or opts["set_1"]:      # the occlusion handling changed something
+        plain, _ = M.match_features_dyn(cur, look, poses, K, invK, bins, img, aug_mask=aug, set_missing_to_max=stm, **dict(opts, set_1=False, pool=False))
+        assert float((plain - want_cost).abs().max()) > 1e-3
+    aug1 = torch.tensor([1.0, 0.0]).view(2, 1, 1, 1)              # item 0 augmented: its occlusion handling is skipped (:196)
+    want_cost, want_missing = M.match_features_dyn(cur, look, poses, K, invK, bins, img, aug_mask=aug1, set_missing_to_max=stm, **opts)
+    _check_dyn_kernel(cur, look, poses, K, invK, bins, img, aug1, opts, want_cost, want_missing, stm)
+
+
+@pytest.mark.gpu
+def test_install_matching_rebinds_the_dyn_method():
+    import types
+    import ppea_depth_b200 as P
+
+    class Enc:
+        def match_features(self, *a):
+            return "reference"
+
+        def match_features_dyn(self, *a, **k):
+            return "reference"
+
+        def compute_confidence_mask(self, *a):
+            return "reference"
+
+    P.install_matching(Enc)
+    cur, look, poses, K, invK, bins, img, aug = M.synthetic_dyn_case(B=1, C=4, seed=3)
+    me = Enc()
+    me.warp_depths = torch.stack([torch.ones((1, 48, 128)) * float(d) for d in bins], 0).float().cuda()
+    me.set_missing_to_max = True
+    d = lambda t: t.cuda()
+    cost, missing = me.match_features_dyn(d(cur), d(look), d(poses), d(K), d(invK), d(img), cv_min=True, aug_mask=d(aug), set_1=False, pool=True,
+                                          pool_r=1, pool_th=0.7)
+    want_cost, want_missing = M.match_features_dyn(cur, look, poses, K, invK, bins, img, aug_mask=aug, cv_min=True, set_1=False, pool=True, pool_r=1, pool_th=0.7)
+    assert float((missing.cpu() != want_missing).float().mean()) <= 2e-3
