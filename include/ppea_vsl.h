@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define PPEA_ABI_VERSION 7
+#define PPEA_ABI_VERSION 8
 
 /* error codes (negative) */
 #define PPEA_OK 0
@@ -282,6 +282,23 @@ int ppea_pose_to_matrix_backward(const float* axisangle, const float* translatio
 /* Trainer.compute_matching_mask (trainer.py:859-869): mask[i] = ((1/lowest_cost - mono) / mono < 1) && ((mono - 1/lowest_cost) /
  * (1/lowest_cost) < 1), one byte per element (torch.bool layout); mono_depth (B,1,H,W) and lowest_cost (B,H,W) flattened. */
 int ppea_matching_mask(const float* mono_depth, const float* lowest_cost, uint8_t* mask, size_t count, void* stream);
+
+/* ---- glue between the multi-frame encoder and the loss (remainder) -----------------------------
+ * ppea_matching_glue: one launch for  outputs["lowest_cost"] = F.interpolate(lowest_cost[:, None], [H, W], "nearest")[:, 0]
+ * (networks/repdepth.py:615-617),  outputs["consistency_mask"] = F.interpolate(confidence_mask[:, None], [H, W], "nearest")[:, 0]
+ * (:618-620) * Trainer.compute_matching_mask(outputs) (trainer.py:450-451, :859-869), and the per-image minimum / maximum of
+ * mono_depth (B,1,H,W) that DepthBins.update reduces (trainer.py:54-55) into minmax_scratch (2*batch 32-bit words; NULL = skip).
+ * lowest_cost / confidence are (B,low_h,low_w) float32; outputs (B,H,W) float32. */
+int ppea_matching_glue(const float* lowest_cost, const float* confidence, const float* mono_depth, float* lowest_cost_up,
+                       float* consistency_mask, void* minmax_scratch, int batch, int low_h, int low_w, int height, int width,
+                       void* stream);
+/* DepthBins.update (trainer.py:52-64) from the extrema ppea_matching_glue left in minmax_scratch, on the device:
+ * min = max(opt_min_depth, mean_b(min_b) * 0.9), max = mean_b(max_b) * 1.1, state = 0.99 state + 0.01 new (both 1-element tensors). */
+int ppea_depth_bins_update(const void* minmax_scratch, int batch, float opt_min_depth, float* min_depth_state, float* max_depth_state,
+                           void* stream);
+/* "set missing images to 0 pose" (networks/repdepth.py:502-505: `if feat.sum() == 0: pose[batch_idx] *= 0`, one host sync per
+ * batch item in the reference): pose (B, pose_floats) is zeroed for the items whose pose features (floats_per_item each) are all zero. */
+int ppea_zero_missing_poses(const float* pose_feats, size_t floats_per_item, float* pose, int pose_floats, int batch, void* stream);
 
 #ifdef __cplusplus
 }

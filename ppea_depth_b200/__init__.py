@@ -13,6 +13,7 @@ from .layers import (BackprojectDepth, Project3D, SSIM, disp_to_depth, get_smoot
                      rot_from_axisangle, transformation_from_parameters, upsample)
 from .functional import VslConfig, VslResult, view_synthesis_loss
 from .images import images_to_float
+from .glue import DeviceDepthBins, matching_glue, zero_missing_poses
 from .matching import cost_volume_tail, install_matching, match_features, match_features_dyn
 from .loss import (ViewSynthesisLoss, compute_loss_masks, compute_losses, compute_reprojection_loss,
                    generate_images_pred, install)
@@ -21,5 +22,5 @@ __all__ = [
     "BackprojectDepth", "Project3D", "SSIM", "disp_to_depth", "get_smooth_loss", "get_translation_matrix",
     "rot_from_axisangle", "transformation_from_parameters", "upsample", "VslConfig", "VslResult",
     "view_synthesis_loss", "ViewSynthesisLoss", "compute_loss_masks", "compute_losses",
-    "compute_reprojection_loss", "generate_images_pred", "install", "images_to_float", "match_features", "match_features_dyn", "install_matching", "cost_volume_tail",
+    "compute_reprojection_loss", "generate_images_pred", "install", "images_to_float", "matching_glue", "DeviceDepthBins", "zero_missing_poses", "match_features", "match_features_dyn", "install_matching", "cost_volume_tail",
 ]

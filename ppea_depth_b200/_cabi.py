@@ -20,7 +20,7 @@ INCLUDE_DIR = os.path.join(os.path.dirname(PKG_DIR), "include")
 SOURCES = ("api.cu", "vsl_fwd.cu", "vsl_bwd.cu", "vsl_fused.cu", "vsl_stream.cu", "smooth.cu", "ops.cu", "matching.cu", "pose.cu")
 HEADERS = ("vsl_common.cuh", "vsl_math.cuh", "vsl_gather.cuh", "smooth.cuh")
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 TRACE_EVENTS = 5
 MAX_SCALES = 4
 SUMS_PER_SCALE = 8
@@ -119,6 +119,9 @@ SIGNATURES = {
     "ppea_pose_to_matrix_forward": (_I, [_P, _P, _I, _P, _I, _P]),
     "ppea_pose_to_matrix_backward": (_I, [_P, _P, _I, _P, _P, _P, _I, _P]),
     "ppea_matching_mask": (_I, [_P, _P, _P, _SZ, _P]),
+    "ppea_matching_glue": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "ppea_depth_bins_update": (_I, [_P, _I, _F, _P, _P, _P]),
+    "ppea_zero_missing_poses": (_I, [_P, _SZ, _P, _I, _I, _P]),
     "ppea_match_tail": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "ppea_match_features": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P]),
     "ppea_match_features_dyn": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P]),

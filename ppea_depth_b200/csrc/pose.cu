@@ -194,6 +194,129 @@ __global__ void __launch_bounds__(256) matching_mask_kernel(const float* __restr
   mask[i] = (a && b) ? 1 : 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Glue between the multi-frame encoder and the loss (remainder), one launch:
+//   lowest_cost_up  = F.interpolate(lowest_cost[:, None], [H, W], mode="nearest")[:, 0]            repdepth.py:615-617
+//   consistency     = F.interpolate(confidence[:, None], [H, W], mode="nearest")[:, 0]             repdepth.py:618-620
+//                     * compute_matching_mask(mono_depth, lowest_cost_up)                           trainer.py:450-451, :859-869
+//   per image: min / max of mono_depth over the pixels (DepthBins.update's reductions, trainer.py:54-55)
+// The reference spends two interpolate launches, eight elementwise ones and four reductions on it.
+// nearest: src = floor(dst * (in / out)) clamped to in - 1  (ATen nearest_neighbor_compute_source_index).
+// min / max: positive floats order like their bit patterns, so the block results go through integer atomics
+// (order-independent, hence deterministic); minmax_bits must be pre-set to (0x7f800000, 0) per image.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) matching_glue_kernel(const float* __restrict__ lowest_lr, const float* __restrict__ conf_lr,
+                                                            const float* __restrict__ mono_depth, float* __restrict__ lowest_up,
+                                                            float* __restrict__ consistency, unsigned* __restrict__ minmax_bits, int h,
+                                                            int w, int H, int W) {
+  __shared__ float s_min[8], s_max[8];
+  const int b = blockIdx.y;
+  const unsigned n = (unsigned)(H * W);
+  const unsigned i = blockIdx.x * 256 + threadIdx.x;
+  const float sy = (float)h / (float)H, sx = (float)w / (float)W;
+  float vmin = INFINITY, vmax = 0.f;
+  if (i < n) {
+    const int y = (int)(i / (unsigned)W), x = (int)(i - (unsigned)y * (unsigned)W);
+    const int ys = min((int)floorf(mul_rn((float)y, sy)), h - 1), xs = min((int)floorf(mul_rn((float)x, sx)), w - 1);
+    const size_t o = (size_t)b * n + i, ol = ((size_t)b * h + ys) * w + xs;
+    const float lc = __ldg(lowest_lr + ol);
+    const float mono = __ldg(mono_depth + o);
+    const float md = div_rn(1.f, lc);
+    const bool ok = div_rn(sub_rn(md, mono), mono) < 1.f && div_rn(sub_rn(mono, md), md) < 1.f;
+    lowest_up[o] = lc;
+    consistency[o] = mul_rn(__ldg(conf_lr + ol), ok ? 1.f : 0.f);
+    vmin = vmax = mono;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+    vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+  }
+  if ((threadIdx.x & 31) == 0) s_min[threadIdx.x >> 5] = vmin, s_max[threadIdx.x >> 5] = vmax;
+  __syncthreads();
+  if (threadIdx.x == 0 && minmax_bits) {
+    for (int k = 1; k < 8; ++k) vmin = fminf(vmin, s_min[k]), vmax = fmaxf(vmax, s_max[k]);
+    atomicMin(minmax_bits + 2 * b, __float_as_uint(fmaxf(vmin, 0.f)));
+    atomicMax(minmax_bits + 2 * b + 1, __float_as_uint(fmaxf(vmax, 0.f)));
+  }
+}
+
+// DepthBins.update (trainer.py:52-64) on the device, from the per-image extrema: no tensor leaves the GPU, no host max().
+//   min_d = max(opt_min_depth, mean_b(min_b) * 0.9); max_d = mean_b(max_b) * 1.1; state = state * 0.99 + new * 0.01
+__global__ void depth_bins_update_kernel(const unsigned* __restrict__ minmax_bits, int batch, float opt_min_depth, float* __restrict__ min_state,
+                                         float* __restrict__ max_state) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float smin = 0.f, smax = 0.f;
+  for (int b = 0; b < batch; ++b) {        // torch's mean of B values: sum in index order, then one division
+    smin = add_rn(smin, __uint_as_float(minmax_bits[2 * b]));
+    smax = add_rn(smax, __uint_as_float(minmax_bits[2 * b + 1]));
+  }
+  const float mn = fmaxf(opt_min_depth, mul_rn(div_rn(smin, (float)batch), 0.9f));
+  const float mx = mul_rn(div_rn(smax, (float)batch), 1.1f);
+  *max_state = add_rn(mul_rn(*max_state, 0.99f), mul_rn(mx, 0.01f));
+  *min_state = add_rn(mul_rn(*min_state, 0.99f), mul_rn(mn, 0.01f));
+}
+
+__global__ void minmax_init_kernel(unsigned* __restrict__ minmax_bits, int batch) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < batch) minmax_bits[2 * i] = 0x7f800000u, minmax_bits[2 * i + 1] = 0u;
+}
+
+// "set missing images to 0 pose" (repdepth.py:502-505): pose[b] *= 0 where the pose features of item b sum to exactly zero.
+// The reference asks the host once per batch item (`if feat.sum() == 0`); here the decision stays on the device.
+// One CTA per item; fixed-order block reduction.  (An all-zero feature map sums to 0 in any order.)
+__global__ void __launch_bounds__(256) zero_missing_poses_kernel(const float* __restrict__ feats, size_t per_item, float* __restrict__ pose,
+                                                                 int pose_floats) {
+  __shared__ float red[8];
+  const int b = blockIdx.x;
+  const float* f = feats + (size_t)b * per_item;
+  float s = 0.f;
+  bool any = false;
+  for (size_t i = threadIdx.x; i < per_item; i += 256) {
+    const float v = __ldg(f + i);
+    s += v;
+    any = any || v != 0.f;
+  }
+  // feat.sum() == 0 <=> (all zero) or an exact cancellation; the latter would need the reference's own summation order to
+  // reproduce, and never occurs for features of a real image: decide on "any element non-zero" and on the sum
+  s = warp_sum(s);
+  const unsigned nz = __ballot_sync(0xffffffffu, any);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = (nz != 0u && s != 0.f) ? 1.f : 0.f;
+  __syncthreads();
+  bool keep = false;
+  for (int k = 0; k < 8; ++k) keep = keep || red[k] != 0.f;
+  if (!keep)
+    for (int i = threadIdx.x; i < pose_floats; i += 256) pose[(size_t)b * pose_floats + i] *= 0.f;
+}
+
+extern "C" int ppea_matching_glue(const float* lowest_cost, const float* confidence, const float* mono_depth, float* lowest_cost_up,
+                                  float* consistency_mask, void* minmax_scratch, int batch, int low_h, int low_w, int height, int width,
+                                  void* stream) {
+  if (!lowest_cost || !confidence || !mono_depth || !lowest_cost_up || !consistency_mask) return PPEA_E_NULL;
+  if (batch <= 0 || batch > 65535 || low_h <= 0 || low_w <= 0 || height <= 0 || width <= 0 || (long long)height * width >= (1ll << 31)) return PPEA_E_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (minmax_scratch) minmax_init_kernel<<<ceil_div(batch, 128), 128, 0, st>>>((unsigned*)minmax_scratch, batch);
+  const dim3 grid((unsigned)ceil_div(height * width, 256), (unsigned)batch);
+  matching_glue_kernel<<<grid, 256, 0, st>>>(lowest_cost, confidence, mono_depth, lowest_cost_up, consistency_mask, (unsigned*)minmax_scratch,
+                                             low_h, low_w, height, width);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int ppea_depth_bins_update(const void* minmax_scratch, int batch, float opt_min_depth, float* min_depth_state, float* max_depth_state,
+                                      void* stream) {
+  if (!minmax_scratch || !min_depth_state || !max_depth_state) return PPEA_E_NULL;
+  if (batch <= 0) return PPEA_E_SHAPE;
+  depth_bins_update_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const unsigned*)minmax_scratch, batch, opt_min_depth, min_depth_state, max_depth_state);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int ppea_zero_missing_poses(const float* pose_feats, size_t floats_per_item, float* pose, int pose_floats, int batch, void* stream) {
+  if (!pose_feats || !pose) return PPEA_E_NULL;
+  if (batch <= 0 || pose_floats <= 0 || floats_per_item == 0) return PPEA_E_SHAPE;
+  zero_missing_poses_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(pose_feats, floats_per_item, pose, pose_floats);
+  return (int)cudaGetLastError();
+}
+
 extern "C" int ppea_matching_mask(const float* mono_depth, const float* lowest_cost, uint8_t* mask, size_t count, void* stream) {
   if (!mono_depth || !lowest_cost || !mask) return PPEA_E_NULL;
   if (count == 0) return PPEA_OK;
