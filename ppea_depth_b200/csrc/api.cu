@@ -4,6 +4,7 @@
 #include "vsl_common.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 using namespace ppea;
 
@@ -231,7 +232,7 @@ static_assert(kFusedTileWc == kFwdTileW && kFusedTileHc >= kFwdTileH, "the fused
 
 struct FusedWorkspace {
   size_t off_pose, off_pose_sums, off_raw[kMaxScales], off_raw2[kMaxScales], off_st[kMaxScales], raw_floats[kMaxScales], total_floats;
-  size_t off_flag, off_ident, off_pk[2];       // streaming step: format flag (4 floats), identity-loss map, packed sources
+  size_t off_flag, off_ident, off_pk[2], off_ystat;       // streaming step: format flag (4 floats), identity-loss map, packed sources, target window sums
 };
 // Layout (floats): [pose partials: nblk*S*24][per-image pose sums: B*S*24 doubles][raw photometric gradient of disp_s][multi path: raw consistency
 // gradient of disp_s][smoothness stencil field of disp_s].  A coarse-scale raw field takes 2 floats per pixel:
@@ -239,7 +240,7 @@ struct FusedWorkspace {
 static FusedWorkspace fused_workspace(const PpeaVslParams* p) {
   FusedWorkspace w;
   w.off_pose = 0;
-  const size_t n_tiles = (size_t)std::max(fused_blocks(p->batch, p->height, p->width), stream_tiles(p->batch, p->height, p->width));
+  const size_t n_tiles = (size_t)std::max(fused_blocks(p->batch, p->height, p->width), stream_tiles_max(p->batch, p->height, p->width));
   size_t off = align_up(n_tiles * p->num_scales * 24, 4);
   w.off_pose_sums = off;                                             // [B][S][24] doubles
   off += align_up((size_t)p->batch * p->num_scales * 24 * 2, 4);
@@ -272,6 +273,8 @@ static FusedWorkspace fused_workspace(const PpeaVslParams* p) {
   off += n_px;
   w.off_pk[1] = off;
   off += n_px;
+  w.off_ystat = off;
+  off += 6 * n_px;
   w.total_floats = off;
   return w;
 }
@@ -317,8 +320,28 @@ static bool frame_tensor_map(CUtensorMap* tm, const float* base, int B, int H, i
 }
 
 static bool use_tiles(const PpeaVslParams* p) { return p->flags & PPEA_F_FUSED_TILES; }
+// rows per warp task of the streaming step on the current device (vsl_common.cuh stream_seg_rows)
+static int stream_rows_for(const PpeaVslParams* p) {
+  static int sm_count[64] = {};
+  static int forced = -1;
+  int dev = 0;
+  (void)cudaGetDevice(&dev);
+  if (forced < 0) {
+    const char* e = getenv("PPEA_STREAM_SEG_ROWS");
+    forced = e ? atoi(e) : 0;
+  }
+  int sms = 0;
+  if (dev >= 0 && dev < 64 && sm_count[dev] > 0) {
+    sms = sm_count[dev];
+  } else {
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148, (void)cudaGetLastError();
+    if (dev >= 0 && dev < 64) sm_count[dev] = sms;
+  }
+  return stream_seg_rows(p->batch, p->height, p->width, p->num_scales, sms, forced);
+}
 static int fused_tiles(const PpeaVslParams* p) {
-  return use_tiles(p) ? fused_blocks(p->batch, p->height, p->width) : stream_tiles(p->batch, p->height, p->width);
+  return use_tiles(p) ? fused_blocks(p->batch, p->height, p->width)
+                      : p->batch * stream_strips(p->width) * ceil_div(p->height, stream_rows_for(p));
 }
 
 static void fused_args(const PpeaVslParams* p, const PpeaVslFused* f, VslArgs& a, bool forward) {
@@ -331,11 +354,13 @@ static void fused_args(const PpeaVslParams* p, const PpeaVslFused* f, VslArgs& a
   const FusedWorkspace fw = fused_workspace(p);
   const FwdWorkspace ws = fwd_workspace(p->batch, p->height, p->width, p->num_scales);
   a.tiles_x = tiles ? ceil_div(a.W, kFusedTileWc) : stream_strips(a.W);
-  a.tiles_y = tiles ? ceil_div(a.H, kFusedTileHc) : stream_segs(a.H);
+  a.seg_rows = stream_rows_for(p);
+  a.tiles_y = tiles ? ceil_div(a.H, kFusedTileHc) : ceil_div(a.H, a.seg_rows);
   a.fmt_flag = reinterpret_cast<unsigned*>((float*)f->workspace + fw.off_flag);
   a.ident = (float*)f->workspace + fw.off_ident;
   a.pk[0] = reinterpret_cast<uint32_t*>((float*)f->workspace + fw.off_pk[0]);
   a.pk[1] = reinterpret_cast<uint32_t*>((float*)f->workspace + fw.off_pk[1]);
+  a.ystat = reinterpret_cast<float2*>((float*)f->workspace + fw.off_ystat);
   a.partials = (float*)p->workspace + ws.off_partials;
   a.smooth_ws = (float*)p->workspace + ws.off_smooth;
   a.pose_partials = (float*)f->workspace + fw.off_pose;

@@ -39,6 +39,7 @@ struct VslArgs {
   unsigned flags;
   float disp_lo, disp_range, eps, disparity_smoothness;
   int tiles_x, tiles_y; // tiles per image (of the kernel being launched)
+  int seg_rows;         // streaming step: output rows per warp task (tiles_y = ceil(H / seg_rows))
   const float* tgt;
   const float* src[2];
   const float* K;
@@ -63,6 +64,7 @@ struct VslArgs {
   uint32_t* pk[2];      // (B,H,W) source frames packed to one RGBA8 word per pixel (exact when the frames are k/255)
   float* ident;         // (B,H,W) identity loss min_f photo(src_f, tgt) (trainer.py:1060-1069), scale-invariant
   unsigned* fmt_flag;   // != 0 after the preparation launch: some source value is not exactly k/255 -> planar fp32 gathers
+  float2* ystat;        // [3][B*H*W] 3x3 window sums (Sy, Syy) of the target per channel (layers.py:243-247), scale-invariant
   alignas(64) CUtensorMap tm_tgt;
   alignas(64) CUtensorMap tm_src[2];
 };
@@ -88,10 +90,9 @@ constexpr int kSmoothThreads = 128;
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-#ifndef PPEA_STREAM_SEG
-#define PPEA_STREAM_SEG 96
-#endif
-#define PPEA_STREAM_SEG_ROWS PPEA_STREAM_SEG
+// Streaming step (vsl_stream.cu): a warp task walks a segment of rows of one 28-column strip.  The segment length is chosen
+// per launch (stream_seg_rows below); workspaces are sized for the shortest one.
+#define PPEA_STREAM_MIN_SEG_ROWS 16
 inline int fwd_blocks(int B, int H, int W) { return B * ceil_div(W, kFwdTileW) * ceil_div(H, kFwdTileH); }
 inline int bwd_blocks(int B, int H, int W) { return B * ceil_div(W, kBwdTileW) * ceil_div(H, kBwdTileH); }
 __host__ __device__ inline int sums_stride(int B) { return PPEA_SUMS_PER_SCALE + 4 * B; }
@@ -103,7 +104,7 @@ struct FwdWorkspace {
 inline FwdWorkspace fwd_workspace(int B, int H, int W, int S) {
   FwdWorkspace w;
   w.off_partials = 0;
-  const int stream = B * ceil_div(W, 28) * ceil_div(H, PPEA_STREAM_SEG_ROWS);     // warp tasks of the streaming step (vsl_stream.cu)
+  const int stream = B * ceil_div(W, 28) * ceil_div(H, PPEA_STREAM_MIN_SEG_ROWS);     // warp tasks of the streaming step (vsl_stream.cu)
   const int nblk = fwd_blocks(B, H, W) > stream ? fwd_blocks(B, H, W) : stream;
   w.off_smooth = align_up((size_t)nblk * S * 4, 4);
   w.total_floats = w.off_smooth + (size_t)S * B * kSmoothChunks * 3;
@@ -141,10 +142,32 @@ cudaError_t launch_pose_finish(const VslArgs& a, int nblk_bwd, cudaStream_t stre
 cudaError_t launch_vsl_fused(const VslArgs& a, cudaStream_t stream);
 // streaming step (vsl_stream.cu): warp-per-strip row walk, no CTA barriers; tiles_x/tiles_y = strips / row segments
 constexpr int kStripW = 28;           // output columns per warp (32 gathered, 30 decided)
-constexpr int kSegRows = PPEA_STREAM_SEG;   // output rows per warp task
+#ifndef PPEA_STREAM_CTAS
+#define PPEA_STREAM_CTAS 12
+#endif
+constexpr int kStreamCtasPerSm = PPEA_STREAM_CTAS;   // resident one-warp CTAs per SM (168 registers, 17 KB of shared memory each)
 inline int stream_strips(int W) { return ceil_div(W, kStripW); }
-inline int stream_segs(int H) { return ceil_div(H, kSegRows); }
-inline int stream_tiles(int B, int H, int W) { return B * stream_strips(W) * stream_segs(H); }
+inline int stream_tiles_max(int B, int H, int W) { return B * stream_strips(W) * ceil_div(H, PPEA_STREAM_MIN_SEG_ROWS); }
+// Output rows per warp task.  A task costs rows + 4 iterations (two rows of run-in, two of run-out) and the grid runs in
+// waves of sm_count * kStreamCtasPerSm tasks, so the best segment length trades the run-in against a well-filled last
+// wave: efficiency = rows / (rows + 4) * waves / ceil(waves).  `forced` > 0 (environment PPEA_STREAM_SEG_ROWS, tuning only)
+// overrides the choice.
+inline int stream_seg_rows(int B, int H, int W, int S, int sm_count, int forced) {
+  if (forced > 0) return forced < PPEA_STREAM_MIN_SEG_ROWS ? PPEA_STREAM_MIN_SEG_ROWS : forced;
+  const double slots = (double)(sm_count > 0 ? sm_count : 148) * kStreamCtasPerSm;
+  int best_rows = H;
+  double best = -1.0;
+  for (int segs = 1; segs <= ceil_div(H, PPEA_STREAM_MIN_SEG_ROWS); ++segs) {
+    const int rows = ceil_div(H, segs);
+    if (rows < PPEA_STREAM_MIN_SEG_ROWS) break;
+    const double tasks = (double)B * stream_strips(W) * S * ceil_div(H, rows);
+    const double waves = tasks / slots;
+    const double full = (double)(long long)waves;
+    const double eff = (double)rows / (rows + 4) * waves / (waves > full ? full + 1.0 : full);
+    if (eff > best + 1e-9) best = eff, best_rows = rows;
+  }
+  return best_rows;
+}
 cudaError_t launch_vsl_prep(const VslArgs& a, cudaStream_t stream);
 cudaError_t launch_vsl_stream(const VslArgs& a, cudaStream_t stream);
 cudaError_t launch_vsl_grad_finish(const VslArgs& a, cudaStream_t stream);
@@ -181,9 +204,25 @@ struct SmemAttrCache {
   unsigned long long devmask[16];
   int n;
 };
+inline cudaError_t ensure_func_attr_impl(SmemAttrCache& cache, std::mutex& mu, const void* fn, cudaFuncAttribute attr, int value);
 inline cudaError_t ensure_dynamic_smem_impl(const void* fn, int bytes) {
   static SmemAttrCache cache = {};
   static std::mutex mu;
+  return ensure_func_attr_impl(cache, mu, fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+// Ask for the largest shared-memory carve-out once per device: a kernel whose residency is limited by its STATIC shared
+// memory (the streaming step: 12 one-warp CTAs x 17 KB per SM) must not be given a smaller carve-out by the driver's
+// heuristic.
+inline cudaError_t ensure_max_carveout_impl(const void* fn) {
+  static SmemAttrCache cache = {};
+  static std::mutex mu;
+  return ensure_func_attr_impl(cache, mu, fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+}
+template <typename Kern>
+inline cudaError_t ensure_max_carveout(Kern kern) {
+  return ensure_max_carveout_impl(reinterpret_cast<const void*>(kern));
+}
+inline cudaError_t ensure_func_attr_impl(SmemAttrCache& cache, std::mutex& mu, const void* fn, cudaFuncAttribute attr, int bytes) {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
@@ -192,7 +231,7 @@ inline cudaError_t ensure_dynamic_smem_impl(const void* fn, int bytes) {
   for (int i = 0; i < cache.n; ++i)
     if (cache.fn[i] == fn) slot = i;
   if (slot >= 0 && dev < 64 && (cache.devmask[slot] >> dev) & 1ull) return cudaSuccess;
-  e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  e = cudaFuncSetAttribute(fn, attr, bytes);
   if (e != cudaSuccess) return e;
   if (slot < 0 && cache.n < 16) {
     slot = cache.n++;

@@ -46,16 +46,14 @@ namespace ppea {
 #ifndef PPEA_STREAM_WARPS
 #define PPEA_STREAM_WARPS 1
 #endif
-#ifndef PPEA_STREAM_CTAS
-#define PPEA_STREAM_CTAS 8
-#endif
 constexpr int kStreamWarps = PPEA_STREAM_WARPS;
 constexpr int kStreamThreads = 32 * kStreamWarps;
 #ifndef PPEA_PREP_SEG
-#define PPEA_PREP_SEG 16
+#define PPEA_PREP_SEG 48
 #endif
 constexpr int kPrepSegRows = PPEA_PREP_SEG;      // rows per warp task of the preparation launch
 constexpr int kPrepStripW = 30;       // decided columns per warp there
+constexpr int kRingK = 12;            // float4 words per lane and ring slot of the main kernel (48 floats, see there)
 
 __device__ __forceinline__ f2 shfl_up2(f2 v) {
   return mk2(__shfl_up_sync(0xffffffffu, v.x, 1), __shfl_up_sync(0xffffffffu, v.y, 1));
@@ -252,7 +250,9 @@ __global__ void __launch_bounds__(kSmoothThreads, PPEA_PREP_CTAS) vsl_prep_kerne
       r.x[c] = mk2(__ldg(s0_b + (c * plane + o)), __ldg(s1_b + (c * plane + o)));
     }
   };
-  const int g_lo = automask ? y0 - 1 : y0, g_hi = automask ? y1 : y1 - 1;
+  const int g_lo = y0 - 1, g_hi = y1;      // one halo row above and below: the window sums of rows y0 .. y1-1
+  float2* ys_b = a.ystat + (size_t)b * plane;
+  const size_t ys_plane = (size_t)a.B * plane;
   PrepRow nxt;
   load_row(g_lo, nxt);
 
@@ -267,29 +267,36 @@ __global__ void __launch_bounds__(kSmoothThreads, PPEA_PREP_CTAS) vsl_prep_kerne
         pk1[(unsigned)gi * (unsigned)W + (unsigned)gx] = w1;
       }
     }
-    if (!automask) return;
     f2 hxn[9];
     float yhn[6];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const float yl = __shfl_up_sync(0xffffffffu, cur.y[c], 1), yr = __shfl_down_sync(0xffffffffu, cur.y[c], 1);
       row_sums_y<float>(yl, cur.y[c], yr, yhn[2 * c], yhn[2 * c + 1]);
-      const f2 xl = shfl_up2(cur.x[c]), xrt = shfl_down2(cur.x[c]);
-      row_sums_x<f2>(xl, cur.x[c], xrt, dup2(yl), dup2(cur.y[c]), dup2(yr), hxn[3 * c], hxn[3 * c + 1], hxn[3 * c + 2]);
+      if (automask) {
+        const f2 xl = shfl_up2(cur.x[c]), xrt = shfl_down2(cur.x[c]);
+        row_sums_x<f2>(xl, cur.x[c], xrt, dup2(yl), dup2(cur.y[c]), dup2(yr), hxn[3 * c], hxn[3 * c + 1], hxn[3 * c + 2]);
+      } else {
+        hxn[3 * c] = hxn[3 * c + 1] = hxn[3 * c + 2] = dup2(0.f);
+      }
     }
     const int qi = gi - 1;
     if (qi >= y0) {                                    // (qi < y1 by the loop bounds)
       f2 L = dup2(0.f), cs = dup2(0.f);
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        const f2 Sx = vadd(vadd(hx[P][3 * c], hx[Q][3 * c]), hxn[3 * c]);
-        const f2 Sxx = vadd(vadd(hx[P][3 * c + 1], hx[Q][3 * c + 1]), hxn[3 * c + 1]);
-        const f2 Sxy = vadd(vadd(hx[P][3 * c + 2], hx[Q][3 * c + 2]), hxn[3 * c + 2]);
+        // target window sums: the streaming kernel reads them at every scale instead of re-forming them
         const float Sy = add_rn(add_rn(yh[P][2 * c], yh[Q][2 * c]), yhn[2 * c]);
         const float Syy = add_rn(add_rn(yh[P][2 * c + 1], yh[Q][2 * c + 1]), yhn[2 * c + 1]);
-        photo_channel<false>(Sx, Sxx, Sxy, Sy, Syy, xr[Q][c], ycr[Q][c], w_ssim, l1w, L, cs, nullptr);
+        if (own_col) ys_b[c * ys_plane + ((unsigned)qi * (unsigned)W + (unsigned)gx)] = make_float2(Sy, Syy);
+        if (automask) {
+          const f2 Sx = vadd(vadd(hx[P][3 * c], hx[Q][3 * c]), hxn[3 * c]);
+          const f2 Sxx = vadd(vadd(hx[P][3 * c + 1], hx[Q][3 * c + 1]), hxn[3 * c + 1]);
+          const f2 Sxy = vadd(vadd(hx[P][3 * c + 2], hx[Q][3 * c + 2]), hxn[3 * c + 2]);
+          photo_channel<false>(Sx, Sxx, Sxy, Sy, Syy, xr[Q][c], ycr[Q][c], w_ssim, l1w, L, cs, nullptr);
+        }
       }
-      if (own_col) ident_b[(unsigned)qi * (unsigned)W + (unsigned)gx] = fminf(L.x, L.y);
+      if (automask && own_col) ident_b[(unsigned)qi * (unsigned)W + (unsigned)gx] = fminf(L.x, L.y);
     }
 #pragma unroll
     for (int e = 0; e < 9; ++e) hx[P][e] = hxn[e];
@@ -394,6 +401,7 @@ template <bool POSE, bool MULTI, bool DET>
 __global__ void __launch_bounds__(kStreamThreads, PPEA_STREAM_CTAS) vsl_stream_kernel(const __grid_constant__ VslArgs a, int n_task_ctas) {
   // per warp: ring of three rows of bilinear derivatives (d warped_c / d(u,v), 12 floats per lane and row) and the
   // folded projection of the image (vsl_math.cuh Geom, lanes = sources)
+  __shared__ float4 s_ring[kStreamWarps][2][kRingK][32];
   __shared__ float4 s_dd[kStreamWarps][3][3][32];
   __shared__ f2 s_G[kStreamWarps][12];
 
@@ -435,7 +443,7 @@ __global__ void __launch_bounds__(kStreamThreads, PPEA_STREAM_CTAS) vsl_stream_k
   const bool col_in = gx >= 0 && gx < W;
   const bool q_lane = col_in && lane >= 1 && lane <= 30;
   const bool own_col = lane >= 2 && lane <= 29 && gx < W;
-  const int y0 = seg * kSegRows, y1 = min(y0 + kSegRows, H);
+  const int y0 = seg * a.seg_rows, y1 = min(y0 + a.seg_rows, H);
   ColCtx cc = make_col(G, gx, W);
   if (!same_res) cc.cx = up_coef(cc.px, ws, sc.up_sx);
   const float wmax = coord_max(W), hmax = coord_max(H);
@@ -455,27 +463,21 @@ __global__ void __launch_bounds__(kStreamThreads, PPEA_STREAM_CTAS) vsl_stream_k
   // spend a register move per byte selector): B > 0, so the shifted term is zero
   const unsigned k4b = 0x4B000000u | ((unsigned)a.B >> 31);
 
-  // ---- register rings (slot = parity of the iteration that produced the row)
-  f2 hx[2][9];        // horizontal 3-tap sums of (x, x^2, x y) per channel, both sources
-  f2 xr[2][3];        // warped samples
-  float yh[2][6];     // horizontal sums of (y, y^2) per channel
-  float ycr[2][3];    // target values
-  f2 hc[2][9];        // horizontal (multiplicity-weighted) sums of the masked adjoint coefficients
-  f2 indr[2];         // mask(q) * [sel(q) == lane]
-  float dep[2];
-  RowFetch rf[2];     // gather of the row blended by iteration parity p
+  // ---- per-lane rings in shared memory.  Everything a row hands to the two iterations after it goes through them;
+  // a lane only ever touches its own column, so program order is the only synchronisation.  Slot = parity of the
+  // iteration that wrote it: iteration gi reads slot Q = (gi-1)&1 (previous iteration) and slot P = gi&1 (two
+  // iterations ago), then overwrites slot P group by group once the group's old content has been read.
+  //   k 0..3  hx[0..7]          horizontal 3-tap sums (x, x^2, x y per channel, both sources) of row gi
+  //   k 4     hx[8], ycr[2], depth                                                              of row gi
+  //   k 5..6  xr[0..2], ycr[0..1]   warped samples / target values                              of row gi
+  //   k 7..10 hc[0..7]          horizontal (multiplicity-weighted) sums of the masked adjoint coefficients of row gi-1
+  //   k 11    hc[8], ind        mask(q) * [sel(q) == lane]                                       of row gi-1
+  float4* const ring = &s_ring[wid][0][0][lane];
+  float4* const ddr = &s_dd[wid][0][0][lane];
 #pragma unroll
-  for (int p = 0; p < 2; ++p) {
+  for (int i = 0; i < 2 * kRingK; ++i) ring[i * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int e = 0; e < 9; ++e) hx[p][e] = hc[p][e] = dup2(0.f);
-#pragma unroll
-    for (int e = 0; e < 3; ++e) xr[p][e] = dup2(0.f), ycr[p][e] = 0.f;
-#pragma unroll
-    for (int e = 0; e < 6; ++e) yh[p][e] = 0.f;
-    indr[p] = dup2(0.f);
-    dep[p] = 0.f;
-    rf[p] = RowFetch{};
-  }
+  for (int i = 0; i < 9; ++i) ddr[i * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
   const f2 mL = dup2((gx == 1) ? 2.f : 1.f), mR = dup2((gx == W - 2) ? 2.f : 1.f);   // reflection multiplicities (layers.py:238)
 
   float s_rm = 0.f, s_m = 0.f, s_c = 0.f;
@@ -534,8 +536,15 @@ __global__ void __launch_bounds__(kStreamThreads, PPEA_STREAM_CTAS) vsl_stream_k
 #pragma unroll
     for (int c = 0; c < 3; ++c) y[c] = __ldg(tgt_b + (c * plane + o));
   };
-  // identity loss (+ tie-break noise) / consistency mask of the row decided by the NEXT iteration
-  auto load_decide = [&](int qi, float& idv, float& nzv, float& cmv) {
+  // what the NEXT iteration needs to decide row qi: the target's window sums (preparation launch; rows outside the
+  // image are decided with mask 0, they only need finite numbers: the reflected row), identity loss (+ tie-break
+  // noise) / consistency mask
+  const float2* ys_b = a.ystat + (img0 + upx);
+  const unsigned ys_plane = (unsigned)a.B * plane;
+  auto load_decide = [&](int qi, float2 (&ys)[3], float& idv, float& nzv, float& cmv) {
+    const unsigned orow = (unsigned)reflect_index(qi, H) * uW;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) ys[c] = __ldg(ys_b + (c * ys_plane + orow));
     idv = nzv = 0.f;
     cmv = 1.f;
     if (q_lane && qi >= 0 && qi < H) {
@@ -546,40 +555,59 @@ __global__ void __launch_bounds__(kStreamThreads, PPEA_STREAM_CTAS) vsl_stream_k
     }
   };
 
-  // The row loop, specialised on the gather format and on full / coarse resolution of disp_s: only the executed copy
-  // occupies the instruction cache, and the compiler sees straight-line code.
+  // The row loop, specialised on the gather format: only the executed copy occupies the instruction cache.
   auto run_rows = [&](auto packed_c) {
   constexpr bool packed = decltype(packed_c)::value;
   DispTaps dup_pf = load_disp(y0 - 2);
-  if (packed) {                 // (the planar gathers are not prefetched: they keep the disparity of the row itself)
-    fetch_row(y0 - 2, disp_value(y0 - 2, dup_pf), rf[0]);
+  RowFetch rf = RowFetch{};       // gather of the row blended by the coming iteration
+  if (packed) {                   // (the planar gathers are not prefetched: they keep the disparity of the row itself)
+    fetch_row(y0 - 2, disp_value(y0 - 2, dup_pf), rf);
     dup_pf = load_disp(y0 - 1);
   }
   float y_pf[3];
   load_tgt(y0 - 2, y_pf);
-  float id_pf = 0.f, nz_pf = 0.f, cm_pf = 1.f;       // (the first two iterations decide nothing that is kept)
+  float2 ys_pf[3];
+  float id_pf, nz_pf, cm_pf;
+  load_decide(y0 - 3, ys_pf, id_pf, nz_pf, cm_pf);   // (the first two iterations decide nothing that is kept)
   int dslot = 0;                                     // ring slot the derivatives of the current row go to
 
-  // One loop body for every row (no unrolling: the body must stay inside the instruction cache; the two-row rings are
-  // (older, newer) slot pairs P / Q rotated by register moves, which issue in the shadow of the dependent arithmetic).
-  constexpr int P = 0, Q = 1;
+  // One loop body for every row (no unrolling: the body must stay inside the instruction cache).
 #pragma unroll 1
   for (int gi = y0 - 2; gi <= y1 + 1; ++gi) {
-    // ---- loads of the next iteration
+    float4* const sP = ring + (gi & 1) * (kRingK * 32);
+    float4* const sQ = ring + ((gi & 1) ^ 1) * (kRingK * 32);
     float yv[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) yv[c] = y_pf[c];
-    const float idv = id_pf, nzv = nz_pf, cmv = cm_pf;
-    float dup_cur = 0.f;
-    if (packed) {
-      fetch_row(gi + 1, disp_value(gi + 1, dup_pf), rf[Q]);      // consumed by the next iteration: a whole row of arithmetic covers the L2 latency
-      dup_pf = load_disp(gi + 2);
-    } else {
-      dup_cur = disp_value(gi, dup_pf);
-      dup_pf = load_disp(gi + 1);
+
+    // ---- blend row gi from the words fetched one iteration ago (bilinear samples of both sources, derivatives to
+    // their ring), THEN issue the gather of row gi + 1 into the same registers: a whole row of arithmetic covers its
+    // L2 latency and no fetch state is ever copied
+    f2 xn[3];
+    float d;
+    {
+      f2 dx[3], dy[3];
+      if (packed) {
+        blend_packed(rf, k4b, xn, dx, dy);
+        d = rf.d;
+        fetch_row(gi + 1, disp_value(gi + 1, dup_pf), rf);
+        dup_pf = load_disp(gi + 2);
+      } else {
+        const float dup_cur = disp_value(gi, dup_pf);
+        dup_pf = load_disp(gi + 1);
+        const int py = reflect_index(gi, H);
+        d = depth_from_disp_fast(dup_cur, a.disp_lo, a.disp_range);
+        f2 A[3];
+        const ProjT<f2> pr = project_cell(G, cc, py, d, a.eps, wmax, hmax, A);
+        sample_sources<true, false>(sp, W, pr, wm1, hm1, xn, dx, dy);
+      }
+      float4* dst = ddr + dslot * (3 * 32);
+      dst[0] = make_float4(dx[0].x, dx[0].y, dx[1].x, dx[1].y);
+      dst[32] = make_float4(dx[2].x, dx[2].y, dy[0].x, dy[0].y);
+      dst[64] = make_float4(dy[1].x, dy[1].y, dy[2].x, dy[2].y);
     }
     load_tgt(gi + 1, y_pf);
-    load_decide(gi, id_pf, nz_pf, cm_pf);
+    if (gi >= y0 && gi < y1 && own_col) sc.depth[img0 + (unsigned)gi * uW + ugx] = d;   // trainer.py:893
     const int pi = gi - 2;
     float md = 0.f, cmf = 1.f;                        // fold row: mono depth / consistency mask (multi path)
     if (MULTI && own_col && pi >= y0) {
@@ -588,50 +616,41 @@ __global__ void __launch_bounds__(kStreamThreads, PPEA_STREAM_CTAS) vsl_stream_k
       if (motion) cmf = __ldg(a.cons_mask + o);
     }
 
-    // ---- the ring slot that this iteration replaces is folded into partial sums FIRST, so that it is dead before its
-    // successor is born and the two share registers (no moves at the loop edge)
-    f2 T[9], Vp[9];
-    float Ty[6];
-    const f2 mU = dup2((pi == 1) ? 2.f : 1.f), mD = dup2((pi == H - 2) ? 2.f : 1.f);
-#pragma unroll
-    for (int e = 0; e < 9; ++e) {
-      T[e] = vadd(hx[P][e], hx[Q][e]);                 // rows gi-2, gi-1 of the window of row gi-1
-      Vp[e] = vfma(mU, hc[P][e], hc[Q][e]);            // coefficient rows gi-3 (weighted), gi-2 of the box around row gi-2
-    }
-#pragma unroll
-    for (int e = 0; e < 6; ++e) Ty[e] = add_rn(yh[P][e], yh[Q][e]);
-
-    // ---- blend row gi: bilinear samples of both sources, derivatives to the ring
-    f2 xn[3];
-    float d;
-    {
-      f2 dx[3], dy[3];
-      if (packed) {
-        blend_packed(rf[P], k4b, xn, dx, dy);
-        d = rf[P].d;
-      } else {
-        const int py = reflect_index(gi, H);
-        d = depth_from_disp_fast(dup_cur, a.disp_lo, a.disp_range);
-        f2 A[3];
-        const ProjT<f2> pr = project_cell(G, cc, py, d, a.eps, wmax, hmax, A);
-        sample_sources<true, false>(sp, W, pr, wm1, hm1, xn, dx, dy);
-      }
-      float4* ring = &s_dd[wid][dslot][0][lane];
-      ring[0] = make_float4(dx[0].x, dx[0].y, dx[1].x, dx[1].y);
-      ring[32] = make_float4(dx[2].x, dx[2].y, dy[0].x, dy[0].y);
-      ring[64] = make_float4(dy[1].x, dy[1].y, dy[2].x, dy[2].y);
-    }
-    if (gi >= y0 && gi < y1 && own_col) sc.depth[img0 + (unsigned)gi * uW + ugx] = d;   // trainer.py:893
-
     // ---- horizontal 3-tap sums of this row
     f2 hxn[9];
-    float yhn[6];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const float yl = __shfl_up_sync(0xffffffffu, yv[c], 1), yrt = __shfl_down_sync(0xffffffffu, yv[c], 1);
-      row_sums_y<float>(yl, yv[c], yrt, yhn[2 * c], yhn[2 * c + 1]);
       const f2 xl = shfl_up2(xn[c]), xrt = shfl_down2(xn[c]);
       row_sums_x<f2>(xl, xn[c], xrt, dup2(yl), dup2(yv[c]), dup2(yrt), hxn[3 * c], hxn[3 * c + 1], hxn[3 * c + 2]);
+    }
+
+    // ---- window sums of row qi = gi - 1: rows gi-2 (slot P) + gi-1 (slot Q) from the ring, + this row
+    f2 S[9];
+    float ycP2, depP, ycQ[3];
+    f2 xq[3];
+    {
+      const float4 p0 = sP[0], p1 = sP[32], p2 = sP[64], p3 = sP[96], p4 = sP[128];
+      const float4 q0 = sQ[0], q1 = sQ[32], q2 = sQ[64], q3 = sQ[96], q4 = sQ[128];
+      S[0] = vadd(vadd(mk2(p0.x, p0.y), mk2(q0.x, q0.y)), hxn[0]);
+      S[1] = vadd(vadd(mk2(p0.z, p0.w), mk2(q0.z, q0.w)), hxn[1]);
+      S[2] = vadd(vadd(mk2(p1.x, p1.y), mk2(q1.x, q1.y)), hxn[2]);
+      S[3] = vadd(vadd(mk2(p1.z, p1.w), mk2(q1.z, q1.w)), hxn[3]);
+      S[4] = vadd(vadd(mk2(p2.x, p2.y), mk2(q2.x, q2.y)), hxn[4]);
+      S[5] = vadd(vadd(mk2(p2.z, p2.w), mk2(q2.z, q2.w)), hxn[5]);
+      S[6] = vadd(vadd(mk2(p3.x, p3.y), mk2(q3.x, q3.y)), hxn[6]);
+      S[7] = vadd(vadd(mk2(p3.z, p3.w), mk2(q3.z, q3.w)), hxn[7]);
+      S[8] = vadd(vadd(mk2(p4.x, p4.y), mk2(q4.x, q4.y)), hxn[8]);
+      ycP2 = p4.z, depP = p4.w, ycQ[2] = q4.z;
+      // the sums of this row take the place of row gi-2
+      sP[0] = make_float4(hxn[0].x, hxn[0].y, hxn[1].x, hxn[1].y);
+      sP[32] = make_float4(hxn[2].x, hxn[2].y, hxn[3].x, hxn[3].y);
+      sP[64] = make_float4(hxn[4].x, hxn[4].y, hxn[5].x, hxn[5].y);
+      sP[96] = make_float4(hxn[6].x, hxn[6].y, hxn[7].x, hxn[7].y);
+      sP[128] = make_float4(hxn[8].x, hxn[8].y, yv[2], d);
+      const float4 q5 = sQ[160], q6 = sQ[192];
+      xq[0] = mk2(q5.x, q5.y), xq[1] = mk2(q5.z, q5.w), xq[2] = mk2(q6.x, q6.y);
+      ycQ[0] = q6.z, ycQ[1] = q6.w;
     }
 
     // ---- decide row qi = gi - 1: loss of both sources, selection, mask, masked adjoint coefficients.
@@ -643,19 +662,16 @@ __global__ void __launch_bounds__(kStreamThreads, PPEA_STREAM_CTAS) vsl_stream_k
       f2 L = dup2(0.f), cs = dup2(0.f);
       f2 co[9];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const f2 Sx = vadd(T[3 * c], hxn[3 * c]), Sxx = vadd(T[3 * c + 1], hxn[3 * c + 1]), Sxy = vadd(T[3 * c + 2], hxn[3 * c + 2]);
-        const float Sy = add_rn(Ty[2 * c], yhn[2 * c]), Syy = add_rn(Ty[2 * c + 1], yhn[2 * c + 1]);
-        photo_channel<true>(Sx, Sxx, Sxy, Sy, Syy, xr[Q][c], ycr[Q][c], w_ssim, l1w, L, cs, &co[3 * c]);
-      }
+      for (int c = 0; c < 3; ++c)
+        photo_channel<true>(S[3 * c], S[3 * c + 1], S[3 * c + 2], ys_pf[c].x, ys_pf[c].y, xq[c], ycQ[c], w_ssim, l1w, L, cs, &co[3 * c]);
       const Select sl = select_source(L.x, L.y, cs.x, cs.y, selec);
       bool on = true;
       float mq = 1.f;
       if (MULTI) {
-        mq = cmv * one_minus_aug;
+        mq = cm_pf * one_minus_aug;
       } else if (automask) {
-        const float idl = use_noise ? add_rn(idv, mul_rn(nzv, 0.00001f)) : idv;      // trainer.py:1086-1087
-        on = sl.r <= idl;                                                            // argmin([r, id]) == 0
+        const float idl = use_noise ? add_rn(id_pf, mul_rn(nz_pf, 0.00001f)) : id_pf;   // trainer.py:1086-1087
+        on = sl.r <= idl;                                                               // argmin([r, id]) == 0
         mq = on ? 1.f : 0.f;
       }
       const bool q_ok = q_lane && qi >= 0 && qi < H;
@@ -668,6 +684,8 @@ __global__ void __launch_bounds__(kStreamThreads, PPEA_STREAM_CTAS) vsl_stream_k
         s_rm = fmaf(sl.r, mq, s_rm);
         s_m += mq;
       }
+      // (everything the decision read is dead: fetch what the next iteration decides with)
+      load_decide(gi, ys_pf, id_pf, nz_pf, cm_pf);
       // horizontal box sums of the masked coefficients, with the reflection multiplicities of the columns
 #pragma unroll
       for (int e = 0; e < 9; ++e) {
@@ -679,26 +697,42 @@ __global__ void __launch_bounds__(kStreamThreads, PPEA_STREAM_CTAS) vsl_stream_k
     // ---- fold + chain row pi = gi - 2
     if (gi >= y0 + 2 && pi < y1) {
       const int rslot = dslot == 2 ? 0 : dslot + 1;        // (dslot + 1) % 3 == (dslot - 2) % 3
-      const float4* ring = &s_dd[wid][rslot][0][lane];
-      const float4 r0 = ring[0], r1 = ring[32], r2 = ring[64];
+      const float4* src = ddr + rslot * (3 * 32);
+      const float4 r0 = src[0], r1 = src[32], r2 = src[64];
       const f2 ddx[3] = {mk2(r0.x, r0.y), mk2(r0.z, r0.w), mk2(r1.x, r1.y)};
       const f2 ddy[3] = {mk2(r1.z, r1.w), mk2(r2.x, r2.y), mk2(r2.z, r2.w)};
-      const f2 wl = vmul(indr[Q], dup2(l1w));        // (decided by the previous iteration)
+      const float4 p5 = sP[160], p6 = sP[192];
+      const f2 xp[3] = {mk2(p5.x, p5.y), mk2(p5.z, p5.w), mk2(p6.x, p6.y)};
+      const float ycP[3] = {p6.z, p6.w, ycP2};
+      const float4 a0 = sP[224], a1 = sP[256], a2 = sP[288], a3 = sP[320], a4 = sP[352];      // coefficient row gi-3
+      const float4 b0 = sQ[224], b1 = sQ[256], b2 = sQ[288], b3 = sQ[320], b4 = sQ[352];      // coefficient row gi-2 (+ its indicator)
+      const f2 mU = dup2((pi == 1) ? 2.f : 1.f), mD = dup2((pi == H - 2) ? 2.f : 1.f);
+      // 3x3 box sums of the coefficients around row pi:  mU * row(pi-1) + row(pi) + mD * row(pi+1)
+      f2 V[9];
+      V[0] = vfma(mD, hcn[0], vfma(mU, mk2(a0.x, a0.y), mk2(b0.x, b0.y)));
+      V[1] = vfma(mD, hcn[1], vfma(mU, mk2(a0.z, a0.w), mk2(b0.z, b0.w)));
+      V[2] = vfma(mD, hcn[2], vfma(mU, mk2(a1.x, a1.y), mk2(b1.x, b1.y)));
+      V[3] = vfma(mD, hcn[3], vfma(mU, mk2(a1.z, a1.w), mk2(b1.z, b1.w)));
+      V[4] = vfma(mD, hcn[4], vfma(mU, mk2(a2.x, a2.y), mk2(b2.x, b2.y)));
+      V[5] = vfma(mD, hcn[5], vfma(mU, mk2(a2.z, a2.w), mk2(b2.z, b2.w)));
+      V[6] = vfma(mD, hcn[6], vfma(mU, mk2(a3.x, a3.y), mk2(b3.x, b3.y)));
+      V[7] = vfma(mD, hcn[7], vfma(mU, mk2(a3.z, a3.w), mk2(b3.z, b3.w)));
+      V[8] = vfma(mD, hcn[8], vfma(mU, mk2(a4.x, a4.y), mk2(b4.x, b4.y)));
+      const f2 wl = vmul(mk2(b4.z, b4.w), dup2(l1w));        // indicator of row pi (decided by the previous iteration)
       f2 gu = dup2(0.f), gv = dup2(0.f);
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        const f2 xv = xr[P][c], yv2 = dup2(ycr[P][c]);
+        const f2 xv = xp[c], yv2 = dup2(ycP[c]);
         const f2 dd = vsub(yv2, xv);
         // L1 term:  -ind * l1w * sign(y - x);  SSIM term from the 3x3 box sums of the coefficients (zero with no_ssim)
-        const f2 Ac = vfma(mD, hcn[3 * c], Vp[3 * c]), Bc = vfma(mD, hcn[3 * c + 1], Vp[3 * c + 1]), Cc = vfma(mD, hcn[3 * c + 2], Vp[3 * c + 2]);
-        const f2 Gc = vadd(mk2(neg_signed(wl.x, dd.x), neg_signed(wl.y, dd.y)), vfma(Bc, xv, vfma(Cc, yv2, Ac)));   // d L / d warped_c(p)
+        const f2 Gc = vadd(mk2(neg_signed(wl.x, dd.x), neg_signed(wl.y, dd.y)), vfma(V[3 * c + 1], xv, vfma(V[3 * c + 2], yv2, V[3 * c])));   // d L / d warped_c(p)
         gu = vfma(Gc, ddx[c], gu);
         gv = vfma(Gc, ddy[c], gv);
       }
       float g_dup = 0.f, c_dup = 0.f;
       if (own_col) {       // (pi in [y0, y1) by the loop bounds)
         f2 A[3];
-        const float depk = dep[P];
+        const float depk = depP;
         const ProjT<f2> pr = project_cell(G, cc, pi, depk, a.eps, wmax, hmax, A);
         const f2 gc0 = vmul(gu, pr.rz), gc1 = vmul(gv, pr.rz);
         const f2 gc2 = vneg(vmul(vfma(gu, pr.u, vmul(gv, pr.v)), pr.rz));
@@ -740,16 +774,14 @@ __global__ void __launch_bounds__(kStreamThreads, PPEA_STREAM_CTAS) vsl_stream_k
       }
     }
 
-    // ---- rotate the rings: newer -> older, this row -> newer
-#pragma unroll
-    for (int e = 0; e < 9; ++e) hx[P][e] = hx[Q][e], hx[Q][e] = hxn[e], hc[P][e] = hc[Q][e], hc[Q][e] = hcn[e];
-#pragma unroll
-    for (int e = 0; e < 6; ++e) yh[P][e] = yh[Q][e], yh[Q][e] = yhn[e];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) xr[P][c] = xr[Q][c], xr[Q][c] = xn[c], ycr[P][c] = ycr[Q][c], ycr[Q][c] = yv[c];
-    dep[P] = dep[Q], dep[Q] = d;
-    indr[P] = indr[Q], indr[Q] = indn;
-    if (packed) rf[P] = rf[Q];
+    // ---- the rest of this iteration's products take the place of what slot P held
+    sP[160] = make_float4(xn[0].x, xn[0].y, xn[1].x, xn[1].y);
+    sP[192] = make_float4(xn[2].x, xn[2].y, yv[0], yv[1]);
+    sP[224] = make_float4(hcn[0].x, hcn[0].y, hcn[1].x, hcn[1].y);
+    sP[256] = make_float4(hcn[2].x, hcn[2].y, hcn[3].x, hcn[3].y);
+    sP[288] = make_float4(hcn[4].x, hcn[4].y, hcn[5].x, hcn[5].y);
+    sP[320] = make_float4(hcn[6].x, hcn[6].y, hcn[7].x, hcn[7].y);
+    sP[352] = make_float4(hcn[8].x, hcn[8].y, indn.x, indn.y);
     dslot = dslot == 2 ? 0 : dslot + 1;
   }
   if (!same_res) {
@@ -793,6 +825,8 @@ template <bool POSE, bool MULTI, bool DET>
 static cudaError_t launch_vsl_stream_as(const VslArgs& a, cudaStream_t stream) {
   const int tasks = a.B * a.tiles_x * a.tiles_y * a.S;
   const int n_task_ctas = ceil_div(tasks, kStreamWarps);
+  const cudaError_t e = ensure_max_carveout(vsl_stream_kernel<POSE, MULTI, DET>);
+  if (e != cudaSuccess) return e;
   return launch_pdl(vsl_stream_kernel<POSE, MULTI, DET>, dim3(n_task_ctas), dim3(kStreamThreads), 0, stream, a, n_task_ctas);
 }
 
