@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define PPEA_ABI_VERSION 8
+#define PPEA_ABI_VERSION 9
 
 /* error codes (negative) */
 #define PPEA_OK 0
@@ -299,6 +299,21 @@ int ppea_depth_bins_update(const void* minmax_scratch, int batch, float opt_min_
 /* "set missing images to 0 pose" (networks/repdepth.py:502-505: `if feat.sum() == 0: pose[batch_idx] *= 0`, one host sync per
  * batch item in the reference): pose (B, pose_floats) is zeroed for the items whose pose features (floats_per_item each) are all zero. */
 int ppea_zero_missing_poses(const float* pose_feats, size_t floats_per_item, float* pose, int pose_floats, int batch, void* stream);
+
+/* ---- decoder tail: the disparity head -----------------------------------------------------------
+ * `self.outputs[("disp", 0)] = self.sigmoid(self.disp_convs[0](x))` (networks/depth_decoder_v2.py:123-129, :239) with
+ * Conv3x3 = nn.ReflectionPad2d(1) + nn.Conv2d(C, 1, 3) (layers.py:119-135): x (B,C,H,W), weight (1,C,3,3), bias (1) ->
+ * disp (B,1,H,W); with depth_or_null also depth = 1 / (1/max_depth + (1/min_depth - 1/max_depth) disp) (disp_to_depth,
+ * layers.py:14-23, what trainer.py:888 evaluates next).  One launch; the padded copy of x never exists.  C <= 256.
+ * Backward (any of the three outputs may be NULL; x and the workspace are only needed for grad_weight / grad_bias):
+ * grad_disp (B,1,H,W) -> grad_x (B,C,H,W) (adjoint of the reflection padding folded in), grad_weight (1,C,3,3), grad_bias (1);
+ * fixed-order reductions (bit-reproducible). */
+int ppea_disp_head_forward(const float* x, const float* weight, const float* bias, float* disp, float* depth_or_null, int batch,
+                           int channels, int height, int width, float min_depth, float max_depth, void* stream);
+size_t ppea_disp_head_workspace_bytes(int batch, int channels, int height, int width);
+int ppea_disp_head_backward(const float* x, const float* weight, const float* disp, const float* grad_disp, float* grad_x_or_null,
+                            float* grad_weight_or_null, float* grad_bias_or_null, void* workspace, int batch, int channels,
+                            int height, int width, void* stream);
 
 #ifdef __cplusplus
 }

@@ -13,6 +13,7 @@ from .layers import (BackprojectDepth, Project3D, SSIM, disp_to_depth, get_smoot
                      rot_from_axisangle, transformation_from_parameters, upsample)
 from .functional import VslConfig, VslResult, view_synthesis_loss
 from .images import images_to_float
+from .decoder import FusedDispHead, disp_head, disp_head_with_depth, install_decoder
 from .glue import DeviceDepthBins, matching_glue, zero_missing_poses
 from .matching import cost_volume_tail, install_matching, match_features, match_features_dyn
 from .loss import (ViewSynthesisLoss, compute_loss_masks, compute_losses, compute_reprojection_loss,
@@ -23,4 +24,5 @@ __all__ = [
     "rot_from_axisangle", "transformation_from_parameters", "upsample", "VslConfig", "VslResult",
     "view_synthesis_loss", "ViewSynthesisLoss", "compute_loss_masks", "compute_losses",
     "compute_reprojection_loss", "generate_images_pred", "install", "images_to_float", "matching_glue", "DeviceDepthBins", "zero_missing_poses", "match_features", "match_features_dyn", "install_matching", "cost_volume_tail",
+    "disp_head", "disp_head_with_depth", "FusedDispHead", "install_decoder",
 ]

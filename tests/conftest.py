@@ -27,8 +27,8 @@ def pytest_collection_modifyitems(config, items):
 
 
 def golden_names():
-    # (the matching_*.pt / pose_*.pt fixtures belong to tests/test_matching.py / tests/test_pose.py)
-    return sorted(f[:-3] for f in os.listdir(GOLDEN_DIR) if f.endswith(".pt") and not f.startswith(("matching_", "matchdyn_", "pose_")))
+    # (the matching_*.pt / pose_*.pt / decoder_*.pt / pyramid_*.pt fixtures belong to their own test files)
+    return sorted(f[:-3] for f in os.listdir(GOLDEN_DIR) if f.endswith(".pt") and not f.startswith(("matching_", "matchdyn_", "pose_", "decoder_", "pyramid_")))
 
 
 def load_golden(name):
