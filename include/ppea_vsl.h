@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define PPEA_ABI_VERSION 9
+#define PPEA_ABI_VERSION 10
 
 /* error codes (negative) */
 #define PPEA_OK 0
@@ -314,6 +314,25 @@ size_t ppea_disp_head_workspace_bytes(int batch, int channels, int height, int w
 int ppea_disp_head_backward(const float* x, const float* weight, const float* disp, const float* grad_disp, float* grad_x_or_null,
                             float* grad_weight_or_null, float* grad_bias_or_null, void* workspace, int batch, int channels,
                             int height, int width, void* stream);
+
+/* ---- input format, remainder: the dataset's LANCZOS pyramid and packed RGBx frames on the device ----
+ * MonoDataset.preprocess (datasets/mono_dataset.py:96-112) resizes every colour frame with transforms.Resize((h >> i, w >> i),
+ * interpolation=Image.LANCZOS) (:79-85), scale i from scale i - 1, on the CPU workers.  PIL's 8-bit resampler is an exact integer
+ * algorithm (libImaging/Resample.c: windowed taps, double-precision Lanczos-3 weights normalised and rounded to 22-bit fixed point,
+ * int32 accumulation from 2^21, shift, clip; horizontal pass into an 8-bit intermediate, then vertical); these entry points
+ * reproduce it bit for bit.
+ *   ppea_lanczos_ksize / ppea_lanczos_table   HOST functions: the tap table of one direction (in_size -> out_size):
+ *       bounds[2*out_size] = (first tap, tap count) per output coordinate, coeffs[out_size * ksize] fixed-point weights; returns ksize.
+ *   ppea_resize_lanczos_u8    src (n_planes,in_h,in_w) -> dst (n_planes,out_h,out_w), uint8 planes on the device; the tables are
+ *       device copies of the two host tables; tmp = n_planes*in_h*out_w bytes (needed when both directions change).
+ *   ppea_pack_rgbx_u8         planar (N,3,H,W) or interleaved (N,H,W,3) uint8 frames -> (N,H,W) words r | g << 8 | b << 16, the
+ *       gather format of the streaming loss kernel. */
+int ppea_lanczos_ksize(int in_size, int out_size);
+int ppea_lanczos_table(int in_size, int out_size, int* bounds, int* coeffs);
+int ppea_resize_lanczos_u8(const uint8_t* src, uint8_t* dst, uint8_t* tmp, size_t n_planes, int in_h, int in_w, int out_h, int out_w,
+                           const int* bounds_x, const int* coeffs_x, int ksize_x, const int* bounds_y, const int* coeffs_y, int ksize_y,
+                           void* stream);
+int ppea_pack_rgbx_u8(const uint8_t* src, uint32_t* dst, size_t n_images, int height, int width, int interleaved, void* stream);
 
 #ifdef __cplusplus
 }

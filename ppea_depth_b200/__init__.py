@@ -14,6 +14,7 @@ from .layers import (BackprojectDepth, Project3D, SSIM, disp_to_depth, get_smoot
 from .functional import VslConfig, VslResult, view_synthesis_loss
 from .images import images_to_float
 from .decoder import FusedDispHead, disp_head, disp_head_with_depth, install_decoder
+from .pyramid import ImagePyramid, pack_rgbx, resize_lanczos_u8
 from .glue import DeviceDepthBins, matching_glue, zero_missing_poses
 from .matching import cost_volume_tail, install_matching, match_features, match_features_dyn
 from .loss import (ViewSynthesisLoss, compute_loss_masks, compute_losses, compute_reprojection_loss,
@@ -25,4 +26,5 @@ __all__ = [
     "view_synthesis_loss", "ViewSynthesisLoss", "compute_loss_masks", "compute_losses",
     "compute_reprojection_loss", "generate_images_pred", "install", "images_to_float", "matching_glue", "DeviceDepthBins", "zero_missing_poses", "match_features", "match_features_dyn", "install_matching", "cost_volume_tail",
     "disp_head", "disp_head_with_depth", "FusedDispHead", "install_decoder",
+    "ImagePyramid", "pack_rgbx", "resize_lanczos_u8",
 ]

@@ -17,10 +17,10 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = (os.environ.get("PPEA_LIB") and os.path.abspath(os.environ["PPEA_LIB"])) or os.path.join(PKG_DIR, "libppea_vsl.so")
 INCLUDE_DIR = os.path.join(os.path.dirname(PKG_DIR), "include")
-SOURCES = ("api.cu", "vsl_fwd.cu", "vsl_bwd.cu", "vsl_fused.cu", "vsl_stream.cu", "smooth.cu", "ops.cu", "matching.cu", "pose.cu", "decoder_tail.cu")
+SOURCES = ("api.cu", "vsl_fwd.cu", "vsl_bwd.cu", "vsl_fused.cu", "vsl_stream.cu", "smooth.cu", "ops.cu", "matching.cu", "pose.cu", "decoder_tail.cu", "pyramid.cu")
 HEADERS = ("vsl_common.cuh", "vsl_math.cuh", "vsl_gather.cuh", "smooth.cuh")
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 TRACE_EVENTS = 5
 MAX_SCALES = 4
 SUMS_PER_SCALE = 8
@@ -125,6 +125,10 @@ SIGNATURES = {
     "ppea_disp_head_forward": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P]),
     "ppea_disp_head_workspace_bytes": (_SZ, [_I, _I, _I, _I]),
     "ppea_disp_head_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "ppea_lanczos_ksize": (_I, [_I, _I]),
+    "ppea_lanczos_table": (_I, [_I, _I, _P, _P]),
+    "ppea_resize_lanczos_u8": (_I, [_P, _P, _P, _SZ, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P]),
+    "ppea_pack_rgbx_u8": (_I, [_P, _P, _SZ, _I, _I, _I, _P]),
     "ppea_match_tail": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "ppea_match_features": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P]),
     "ppea_match_features_dyn": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P]),
