@@ -20,10 +20,16 @@
 namespace ppea {
 
 constexpr int kHeadStripW = 30;      // output columns per warp
-constexpr int kHeadRows = 16;        // output rows per warp task (forward, dx)
+constexpr int kHeadRows = 8;         // output rows per warp task (forward, dx)
 constexpr int kHeadThreads = 128;
 constexpr int kHeadMaxC = 256;       // weights live in shared memory: C * 12 floats
-constexpr int kDwGroup = 4;          // channels per warp task of the weight-gradient kernel
+#ifndef PPEA_DW_GROUP
+#define PPEA_DW_GROUP 4
+#endif
+#ifndef PPEA_DW_BLOCK
+#define PPEA_DW_BLOCK 8
+#endif
+constexpr int kDwGroup = PPEA_DW_GROUP;   // channels per warp task of the weight-gradient kernel
 constexpr int kDwRows = 64;          // rows per warp task there
 
 __device__ __forceinline__ float sigmoid_ref(float v) { return div_rn(1.f, add_rn(1.f, expf(-v))); }
@@ -66,7 +72,7 @@ __global__ void __launch_bounds__(kHeadThreads) disp_head_forward_kernel(const f
   const int r0 = t.seg * kHeadRows;
   const unsigned plane = (unsigned)(H * W);
   const float* xb = x + (size_t)t.b * C * plane;
-  // row offsets of the 18 input rows (reflected: nn.ReflectionPad2d(1))
+  // row offsets of the kHeadRows + 2 input rows (reflected: nn.ReflectionPad2d(1))
   unsigned off[kHeadRows + 2];
 #pragma unroll
   for (int j = 0; j < kHeadRows + 2; ++j) off[j] = (unsigned)reflect_index(r0 - 1 + j, H) * (unsigned)W + (unsigned)t.px;
@@ -74,12 +80,20 @@ __global__ void __launch_bounds__(kHeadThreads) disp_head_forward_kernel(const f
   const float bv = __ldg(bias);
 #pragma unroll
   for (int i = 0; i < kHeadRows; ++i) acc[i] = bv;
+  // the kernel is a stream of x through 9 FMAs per value: what bounds it is the number of loads in flight, so the rows of
+  // channel c + 1 are requested before channel c is accumulated (two register sets), and tasks are short (many warps)
+  float v[kHeadRows + 2], vn[kHeadRows + 2];
+#pragma unroll
+  for (int j = 0; j < kHeadRows + 2; ++j) vn[j] = __ldg(xb + off[j]);
 #pragma unroll 1
   for (int c = 0; c < C; ++c) {
-    const float* xc = xb + (size_t)c * plane;
-    float v[kHeadRows + 2];
 #pragma unroll
-    for (int j = 0; j < kHeadRows + 2; ++j) v[j] = __ldg(xc + off[j]);          // 18 independent loads in flight
+    for (int j = 0; j < kHeadRows + 2; ++j) v[j] = vn[j];
+    if (c + 1 < C) {
+      const float* xc = xb + (size_t)(c + 1) * plane;
+#pragma unroll
+      for (int j = 0; j < kHeadRows + 2; ++j) vn[j] = __ldg(xc + off[j]);
+    }
     const float4 w0 = s_w[c * 3], w1 = s_w[c * 3 + 1], w2 = s_w[c * 3 + 2];
 #pragma unroll
     for (int j = 0; j < kHeadRows + 2; ++j) {
@@ -135,7 +149,7 @@ __global__ void __launch_bounds__(kHeadThreads) disp_head_dx_kernel(const float*
   const int r0 = t.seg * kHeadRows;
   const unsigned plane = (unsigned)(H * W);
   const unsigned img = (unsigned)t.b * plane;
-  // rows r0 - 1 .. r0 + 16 of g (zero outside the image); window row ky of q reads row q.y + ky - 1, so output row y collects
+  // rows r0 - 1 .. r0 + kHeadRows of g (zero outside the image); window row ky of q reads row q.y + ky - 1, so output row y collects
   // ky = 0 from row y + 1, ky = 2 from row y - 1, and rows 1 / H - 2 also what the padding mirrored from rows 0 / H - 1
   GRow G[kHeadRows + 2];
 #pragma unroll
@@ -198,32 +212,57 @@ __global__ void __launch_bounds__(kHeadThreads) disp_head_dw_kernel(const float*
   const GRow zero = {0.f, 0.f, 0.f};
   GRow up = grad_row(grad_disp, disp, r0 - 1, H, W, t, img), cur = grad_row(grad_disp, disp, r0, H, W, t, img);
   const GRow top = grad_row(grad_disp, disp, 0, H, W, t, img), bot = grad_row(grad_disp, disp, H - 1, H, W, t, img);
+  const bool in_col = t.gx >= 0 && t.gx < W;
+  const float* gd_c = grad_disp + (size_t)img + (unsigned)(in_col ? t.gx : 0);
+  const float* sd_c = disp + (size_t)img + (unsigned)(in_col ? t.gx : 0);
+  const float* x_c = xb + (unsigned)(t.own ? t.gx : 0);
+  constexpr int R = PPEA_DW_BLOCK;      // rows per block: R x (kDwGroup + 2) loads in flight per lane (the kernel is bound by loads in flight)
 #pragma unroll 1
-  for (int y = r0; y < r1; ++y) {
-    const GRow dn = grad_row(grad_disp, disp, y + 1, H, W, t, img);
-    float xv[kDwGroup];
+  for (int yb = r0; yb < r1; yb += R) {
+    float xv[R][kDwGroup], gr[R], sr[R];
 #pragma unroll
-    for (int k = 0; k < kDwGroup; ++k)
-      xv[k] = (t.own && c0 + k < C) ? __ldg(xb + (size_t)k * plane + (unsigned)y * (unsigned)W + (unsigned)t.gx) : 0.f;
-    // taps of pixel (y, gx): ky = 0 <- row y + 1 (+ row 0 at y == 1), ky = 1 <- row y, ky = 2 <- row y - 1 (+ row H - 1 at y == H - 2)
-    const GRow e0 = (y == 1) ? top : zero, e2 = (y == H - 2) ? bot : zero;
-    const float t0 = dn.k0 + e0.k0, t1 = dn.k1 + e0.k1, t2 = dn.k2 + e0.k2;
-    const float t6 = up.k0 + e2.k0, t7 = up.k1 + e2.k1, t8 = up.k2 + e2.k2;
+    for (int i = 0; i < R; ++i) {
+      const int y = yb + i;
+      const bool row_ok = y < r1;
+      const unsigned orow = (unsigned)(row_ok ? y : r1 - 1) * (unsigned)W;
 #pragma unroll
-    for (int k = 0; k < kDwGroup; ++k) {
-      acc[k][0] = fmaf(xv[k], t0, acc[k][0]);
-      acc[k][1] = fmaf(xv[k], t1, acc[k][1]);
-      acc[k][2] = fmaf(xv[k], t2, acc[k][2]);
-      acc[k][3] = fmaf(xv[k], cur.k0, acc[k][3]);
-      acc[k][4] = fmaf(xv[k], cur.k1, acc[k][4]);
-      acc[k][5] = fmaf(xv[k], cur.k2, acc[k][5]);
-      acc[k][6] = fmaf(xv[k], t6, acc[k][6]);
-      acc[k][7] = fmaf(xv[k], t7, acc[k][7]);
-      acc[k][8] = fmaf(xv[k], t8, acc[k][8]);
+      for (int k = 0; k < kDwGroup; ++k) xv[i][k] = (row_ok && t.own && c0 + k < C) ? __ldg(x_c + (size_t)k * plane + orow) : 0.f;
+      const bool dn_ok = row_ok && y + 1 < H && in_col;      // row y + 1 of g (zero outside the image)
+      const unsigned odn = (unsigned)(dn_ok ? y + 1 : 0) * (unsigned)W;
+      gr[i] = dn_ok ? __ldg(gd_c + odn) : 0.f;
+      sr[i] = dn_ok ? __ldg(sd_c + odn) : 0.f;
     }
-    if (t.own) accb += cur.k1;
-    up = cur;
-    cur = dn;
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const int y = yb + i;
+      if (y < r1) {      // (warp-uniform)
+        const float g = gr[i] * sr[i] * (1.f - sr[i]);
+        const float gl = __shfl_up_sync(0xffffffffu, g, 1), grt = __shfl_down_sync(0xffffffffu, g, 1);
+        GRow dn;
+        dn.k1 = g;
+        dn.k0 = grt + (t.gx == 1 ? gl : 0.f);
+        dn.k2 = gl + (t.gx == W - 2 ? grt : 0.f);
+        // taps of pixel (y, gx): ky = 0 <- row y + 1 (+ row 0 at y == 1), ky = 1 <- row y, ky = 2 <- row y - 1 (+ row H - 1 at y == H - 2)
+        const GRow e0 = (y == 1) ? top : zero, e2 = (y == H - 2) ? bot : zero;
+        const float t0 = dn.k0 + e0.k0, t1 = dn.k1 + e0.k1, t2 = dn.k2 + e0.k2;
+        const float t6 = up.k0 + e2.k0, t7 = up.k1 + e2.k1, t8 = up.k2 + e2.k2;
+#pragma unroll
+        for (int k = 0; k < kDwGroup; ++k) {
+          acc[k][0] = fmaf(xv[i][k], t0, acc[k][0]);
+          acc[k][1] = fmaf(xv[i][k], t1, acc[k][1]);
+          acc[k][2] = fmaf(xv[i][k], t2, acc[k][2]);
+          acc[k][3] = fmaf(xv[i][k], cur.k0, acc[k][3]);
+          acc[k][4] = fmaf(xv[i][k], cur.k1, acc[k][4]);
+          acc[k][5] = fmaf(xv[i][k], cur.k2, acc[k][5]);
+          acc[k][6] = fmaf(xv[i][k], t6, acc[k][6]);
+          acc[k][7] = fmaf(xv[i][k], t7, acc[k][7]);
+          acc[k][8] = fmaf(xv[i][k], t8, acc[k][8]);
+        }
+        if (t.own) accb += cur.k1;
+        up = cur;
+        cur = dn;
+      }
+    }
   }
   float* out = partials + (size_t)task * (kDwGroup * 9 + 1);
 #pragma unroll

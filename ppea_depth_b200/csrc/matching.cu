@@ -33,11 +33,24 @@ constexpr int kMatchThreads = PPEA_MATCH_THREADS;
 #define PPEA_MATCH_BINS 4
 #endif
 #ifndef PPEA_MATCH_CHUNK
-#define PPEA_MATCH_CHUNK 4
+#define PPEA_MATCH_CHUNK 8
 #endif
 constexpr int kMatchBins = PPEA_MATCH_BINS;        // depth hypotheses in flight per thread
 constexpr int kMatchChunk = PPEA_MATCH_CHUNK;     // depth bins per CTA (grid.z = ceil(D / kMatchChunk))
 constexpr int kMatchMaxBins = 4096;
+#ifndef PPEA_MATCH_TILE_W
+#define PPEA_MATCH_TILE_W 32
+#endif
+// A CTA covers a kMatchTileW x (kMatchThreads / kMatchTileW) pixel tile (lane == column inside a row of the tile): the footprint
+// of a hypothesis in the lookup features is then ~(TW+1) x (TH+1) cells instead of the 2 x 129 of a 128-pixel row segment, so
+// fewer sectors come from L2 per CTA.
+#if PPEA_MATCH_TILE_W == 0
+constexpr int kMatchTileW = 0, kMatchTileH = 0;
+inline int match_tiles(int h, int w) { return ceil_div(h * w, kMatchThreads); }
+#else
+constexpr int kMatchTileW = PPEA_MATCH_TILE_W, kMatchTileH = kMatchThreads / kMatchTileW;
+inline int match_tiles(int h, int w) { return ceil_div(w, kMatchTileW) * ceil_div(h, kMatchTileH); }
+#endif
 
 struct MatchArgs {
   const float* cur;     // (B,C,h,w)
@@ -117,9 +130,16 @@ __global__ void __launch_bounds__(kMatchThreads) match_features_kernel(const Mat
   const int b = blockIdx.y;
   const int h = a.h, w = a.w, D = a.D, C = a.C;
   const unsigned plane = (unsigned)(h * w);
-  const unsigned pix = blockIdx.x * kMatchThreads + threadIdx.x;
-  const bool live = pix < plane;
-  const int y = live ? (int)(pix / (unsigned)w) : 0, x = live ? (int)(pix - (unsigned)y * (unsigned)w) : 0;
+#if PPEA_MATCH_TILE_W == 0      // (tuning reference: 128 consecutive pixels of the flattened image)
+  const unsigned lin = blockIdx.x * kMatchThreads + threadIdx.x;
+  const int tx0 = (int)(lin % (unsigned)w), ty0 = (int)(lin / (unsigned)w);
+#else
+  const int tiles_x = (w + kMatchTileW - 1) / kMatchTileW;
+  const int tx0 = (blockIdx.x % tiles_x) * kMatchTileW + (threadIdx.x % kMatchTileW), ty0 = (blockIdx.x / tiles_x) * kMatchTileH + (threadIdx.x / kMatchTileW);
+#endif
+  const bool live = tx0 < w && ty0 < h;
+  const int y = live ? ty0 : 0, x = live ? tx0 : 0;
+  const unsigned pix = (unsigned)y * (unsigned)w + (unsigned)x;
   if (threadIdx.x < 9) siK[threadIdx.x] = a.invK[b * 16 + (threadIdx.x / 3) * 4 + threadIdx.x % 3];
   __syncthreads();
   float ray[3];
@@ -275,9 +295,16 @@ __global__ void __launch_bounds__(kMatchThreads) match_features_dyn_kernel(const
   const int b = blockIdx.y;
   const int h = a.h, w = a.w, D = a.D, C = a.C;
   const unsigned plane = (unsigned)(h * w);
-  const unsigned pix = blockIdx.x * kMatchThreads + threadIdx.x;
-  const bool live = pix < plane;
-  const int y = live ? (int)(pix / (unsigned)w) : 0, x = live ? (int)(pix - (unsigned)y * (unsigned)w) : 0;
+#if PPEA_MATCH_TILE_W == 0      // (tuning reference: 128 consecutive pixels of the flattened image)
+  const unsigned lin = blockIdx.x * kMatchThreads + threadIdx.x;
+  const int tx0 = (int)(lin % (unsigned)w), ty0 = (int)(lin / (unsigned)w);
+#else
+  const int tiles_x = (w + kMatchTileW - 1) / kMatchTileW;
+  const int tx0 = (blockIdx.x % tiles_x) * kMatchTileW + (threadIdx.x % kMatchTileW), ty0 = (blockIdx.x / tiles_x) * kMatchTileH + (threadIdx.x / kMatchTileW);
+#endif
+  const bool live = tx0 < w && ty0 < h;
+  const int y = live ? ty0 : 0, x = live ? tx0 : 0;
+  const unsigned pix = (unsigned)y * (unsigned)w + (unsigned)x;
   if (threadIdx.x < 9) siK[threadIdx.x] = a.invK[b * 16 + (threadIdx.x / 3) * 4 + threadIdx.x % 3];
   __syncthreads();
   float ray[3];
@@ -392,7 +419,7 @@ extern "C" int ppea_match_features_dyn(const float* current_feats, const float* 
   da.pool = set_1 ? 0 : pool;          // (`if set_1 ... elif pool`, :202-205)
   da.pool_r = pool_radius;
   da.pool_th = pool_threshold;
-  const dim3 grid((unsigned)ceil_div(height * width, kMatchThreads), (unsigned)batch, (unsigned)ceil_div(num_bins, kMatchChunk));
+  const dim3 grid((unsigned)match_tiles(height, width), (unsigned)batch, (unsigned)ceil_div(num_bins, kMatchChunk));
   match_features_dyn_kernel<<<grid, kMatchThreads, 0, (cudaStream_t)stream>>>(da);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
@@ -440,7 +467,7 @@ extern "C" int ppea_match_features(const float* current_feats, const float* look
   a.D = num_bins;
   a.set_missing_to_max = set_missing_to_max;
   a.eps = eps;
-  const dim3 grid((unsigned)ceil_div(height * width, kMatchThreads), (unsigned)batch, (unsigned)ceil_div(num_bins, kMatchChunk));
+  const dim3 grid((unsigned)match_tiles(height, width), (unsigned)batch, (unsigned)ceil_div(num_bins, kMatchChunk));
   match_features_kernel<<<grid, kMatchThreads, 0, (cudaStream_t)stream>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;

@@ -28,7 +28,9 @@ def timed(fn, n=30):
 
 fwd = lambda i: C.check(C.lib().ppea_disp_head_forward(xs[i % 3].data_ptr(), w.data_ptr(), b.data_ptr(), disp.data_ptr(), None, B, Cn, H, W, 0.0, 0.0, st))
 bwd = lambda i: C.check(C.lib().ppea_disp_head_backward(xs[i % 3].data_ptr(), w.data_ptr(), disp.data_ptr(), g.data_ptr(), gx.data_ptr(), gw.data_ptr(), gb.data_ptr(), ws.data_ptr(), B, Cn, H, W, st))
-t_f, t_b = timed(fwd), timed(bwd)
+bwd_dx = lambda i: C.check(C.lib().ppea_disp_head_backward(None, w.data_ptr(), disp.data_ptr(), g.data_ptr(), gx.data_ptr(), None, None, None, B, Cn, H, W, st))
+bwd_dw = lambda i: C.check(C.lib().ppea_disp_head_backward(xs[i % 3].data_ptr(), w.data_ptr(), disp.data_ptr(), g.data_ptr(), None, gw.data_ptr(), gb.data_ptr(), ws.data_ptr(), B, Cn, H, W, st))
+t_f, t_b, t_dx, t_dw = timed(fwd), timed(bwd), timed(bwd_dx), timed(bwd_dw)
 
 pad, conv, sig = nn.ReflectionPad2d(1), nn.Conv2d(Cn, 1, 3).cuda(), nn.Sigmoid()
 def ref_f(i):
@@ -45,7 +47,7 @@ try:
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
 except Exception:
     pass
-print(json.dumps({"op": "disp head sigmoid(Conv3x3(x))", "shape": [B, Cn, H, W], "fused_forward_ms": t_f, "fused_backward_ms": t_b,
+print(json.dumps({"op": "disp head sigmoid(Conv3x3(x))", "shape": [B, Cn, H, W], "fused_forward_ms": t_f, "fused_backward_ms": t_b, "grad_x_ms": t_dx, "grad_weight_bias_ms": t_dw,
                   "forward_gb_s": bytes_f / t_f / 1e6, "backward_gb_s": bytes_b / t_b / 1e6, "forward_frac_of_hbm_peak": bytes_f / t_f / 1e6 / peak,
                   "backward_frac_of_hbm_peak": bytes_b / t_b / 1e6 / peak, "hbm_peak_gb_s": peak,
                   "torch_eager_forward_ms": r_f, "torch_eager_forward_backward_ms": r_fb}))
