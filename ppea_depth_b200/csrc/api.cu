@@ -320,7 +320,7 @@ static bool frame_tensor_map(CUtensorMap* tm, const float* base, int B, int H, i
 }
 
 static bool use_tiles(const PpeaVslParams* p) { return p->flags & PPEA_F_FUSED_TILES; }
-// rows per warp task of the streaming step on the current device (vsl_common.cuh stream_seg_rows)
+// rows per warp chunk of the streaming step on the current device (vsl_common.cuh stream_chunk_rows)
 static int stream_rows_for(const PpeaVslParams* p) {
   static int sm_count[64] = {};
   static int forced = -1;
@@ -337,11 +337,11 @@ static int stream_rows_for(const PpeaVslParams* p) {
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148, (void)cudaGetLastError();
     if (dev >= 0 && dev < 64) sm_count[dev] = sms;
   }
-  return stream_seg_rows(p->batch, p->height, p->width, p->num_scales, sms, forced);
+  return stream_chunk_rows(p->batch, p->height, p->width, p->num_scales, sms, forced);
 }
 static int fused_tiles(const PpeaVslParams* p) {
   return use_tiles(p) ? fused_blocks(p->batch, p->height, p->width)
-                      : p->batch * stream_strips(p->width) * ceil_div(p->height, stream_rows_for(p));
+                      : p->batch * stream_strips(p->width) * stream_pieces(p->height, stream_rows_for(p));
 }
 
 static void fused_args(const PpeaVslParams* p, const PpeaVslFused* f, VslArgs& a, bool forward) {
@@ -355,7 +355,7 @@ static void fused_args(const PpeaVslParams* p, const PpeaVslFused* f, VslArgs& a
   const FwdWorkspace ws = fwd_workspace(p->batch, p->height, p->width, p->num_scales);
   a.tiles_x = tiles ? ceil_div(a.W, kFusedTileWc) : stream_strips(a.W);
   a.seg_rows = stream_rows_for(p);
-  a.tiles_y = tiles ? ceil_div(a.H, kFusedTileHc) : ceil_div(a.H, a.seg_rows);
+  a.tiles_y = tiles ? ceil_div(a.H, kFusedTileHc) : stream_pieces(a.H, a.seg_rows);
   a.fmt_flag = reinterpret_cast<unsigned*>((float*)f->workspace + fw.off_flag);
   a.ident = (float*)f->workspace + fw.off_ident;
   a.pk[0] = reinterpret_cast<uint32_t*>((float*)f->workspace + fw.off_pk[0]);

@@ -39,7 +39,7 @@ struct VslArgs {
   unsigned flags;
   float disp_lo, disp_range, eps, disparity_smoothness;
   int tiles_x, tiles_y; // tiles per image (of the kernel being launched)
-  int seg_rows;         // streaming step: output rows per warp task (tiles_y = ceil(H / seg_rows))
+  int seg_rows;         // streaming step: rows per warp chunk (tiles_y = stream_pieces(H, seg_rows) tile slots per column)
   const float* tgt;
   const float* src[2];
   const float* K;
@@ -90,8 +90,8 @@ constexpr int kSmoothThreads = 128;
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// Streaming step (vsl_stream.cu): a warp task walks a segment of rows of one 28-column strip.  The segment length is chosen
-// per launch (stream_seg_rows below); workspaces are sized for the shortest one.
+// Streaming step (vsl_stream.cu): a warp walks a chunk of rows of the 28-column strips.  The chunk length is chosen per launch
+// (stream_chunk_rows below); workspaces are sized for the shortest one.
 #define PPEA_STREAM_MIN_SEG_ROWS 16
 inline int fwd_blocks(int B, int H, int W) { return B * ceil_div(W, kFwdTileW) * ceil_div(H, kFwdTileH); }
 inline int bwd_blocks(int B, int H, int W) { return B * ceil_div(W, kBwdTileW) * ceil_div(H, kBwdTileH); }
@@ -104,7 +104,7 @@ struct FwdWorkspace {
 inline FwdWorkspace fwd_workspace(int B, int H, int W, int S) {
   FwdWorkspace w;
   w.off_partials = 0;
-  const int stream = B * ceil_div(W, 28) * ceil_div(H, PPEA_STREAM_MIN_SEG_ROWS);     // warp tasks of the streaming step (vsl_stream.cu)
+  const int stream = B * ceil_div(W, 28) * ((H - 1) / PPEA_STREAM_MIN_SEG_ROWS + 2);     // tile slots of the streaming step (vsl_stream.cu)
   const int nblk = fwd_blocks(B, H, W) > stream ? fwd_blocks(B, H, W) : stream;
   w.off_smooth = align_up((size_t)nblk * S * 4, 4);
   w.total_floats = w.off_smooth + (size_t)S * B * kSmoothChunks * 3;
@@ -147,27 +147,20 @@ constexpr int kStripW = 28;           // output columns per warp (32 gathered, 3
 #endif
 constexpr int kStreamCtasPerSm = PPEA_STREAM_CTAS;   // resident one-warp CTAs per SM (168 registers, 17 KB of shared memory each)
 inline int stream_strips(int W) { return ceil_div(W, kStripW); }
-inline int stream_tiles_max(int B, int H, int W) { return B * stream_strips(W) * ceil_div(H, PPEA_STREAM_MIN_SEG_ROWS); }
-// Output rows per warp task.  A task costs rows + 4 iterations (two rows of run-in, two of run-out) and the grid runs in
-// waves of sm_count * kStreamCtasPerSm tasks, so the best segment length trades the run-in against a well-filled last
-// wave: efficiency = rows / (rows + 4) * waves / ceil(waves).  `forced` > 0 (environment PPEA_STREAM_SEG_ROWS, tuning only)
-// overrides the choice.
-inline int stream_seg_rows(int B, int H, int W, int S, int sm_count, int forced) {
+// Rows per warp of the streaming step.  The rows of all (image, strip, scale) columns form one line that is cut into equal
+// chunks, one per resident warp slot of the device (sm_count * kStreamCtasPerSm one-warp CTAs): a single, evenly loaded wave;
+// a chunk that crosses a column end becomes two pieces (each pays four rows of run-in / run-out).  `forced` > 0 (environment
+// PPEA_STREAM_SEG_ROWS, tuning only) overrides the choice.
+inline int stream_chunk_rows(int B, int H, int W, int S, int sm_count, int forced) {
   if (forced > 0) return forced < PPEA_STREAM_MIN_SEG_ROWS ? PPEA_STREAM_MIN_SEG_ROWS : forced;
-  const double slots = (double)(sm_count > 0 ? sm_count : 148) * kStreamCtasPerSm;
-  int best_rows = H;
-  double best = -1.0;
-  for (int segs = 1; segs <= ceil_div(H, PPEA_STREAM_MIN_SEG_ROWS); ++segs) {
-    const int rows = ceil_div(H, segs);
-    if (rows < PPEA_STREAM_MIN_SEG_ROWS) break;
-    const double tasks = (double)B * stream_strips(W) * S * ceil_div(H, rows);
-    const double waves = tasks / slots;
-    const double full = (double)(long long)waves;
-    const double eff = (double)rows / (rows + 4) * waves / (waves > full ? full + 1.0 : full);
-    if (eff > best + 1e-9) best = eff, best_rows = rows;
-  }
-  return best_rows;
+  const long long total = (long long)B * stream_strips(W) * S * H;
+  const long long slots = (long long)(sm_count > 0 ? sm_count : 148) * kStreamCtasPerSm;
+  const long long rows = (total + slots - 1) / slots;
+  return rows < PPEA_STREAM_MIN_SEG_ROWS ? PPEA_STREAM_MIN_SEG_ROWS : (int)rows;
 }
+// tile slots per column: pieces a column of H rows can be cut into by chunks of `rows` rows
+inline int stream_pieces(int H, int rows) { return (H - 1) / rows + 2; }
+inline int stream_tiles_max(int B, int H, int W) { return B * stream_strips(W) * stream_pieces(H, PPEA_STREAM_MIN_SEG_ROWS); }
 cudaError_t launch_vsl_prep(const VslArgs& a, cudaStream_t stream);
 cudaError_t launch_vsl_stream(const VslArgs& a, cudaStream_t stream);
 cudaError_t launch_vsl_grad_finish(const VslArgs& a, cudaStream_t stream);

@@ -407,16 +407,26 @@ __global__ void __launch_bounds__(kStreamThreads, PPEA_STREAM_CTAS) vsl_stream_k
 
   grid_launch_dependents();      // the dependent is the small finish kernel: let it take its place early
   const int lane = threadIdx.x & 31, wid = kStreamWarps == 1 ? 0 : threadIdx.x >> 5;
-  const int strips = a.tiles_x, segs = a.tiles_y;
-  int t = blockIdx.x * kStreamWarps + wid;
-  if (t >= a.B * strips * segs * a.S) return;          // (whole warp; nothing below synchronises across warps)
-  const int s = t % a.S;
-  t /= a.S;
-  const int strip = t % strips;
-  t /= strips;
-  const int seg = t % segs;
-  const int b = t / segs;
-  const int tile_id = (b * segs + seg) * strips + strip;
+  // Work = the rows of every (image, strip, scale) column laid end to end; warp j walks rows [j L, (j+1) L) of that line
+  // (L = a.seg_rows), i.e. the tail of one column and the head of the next where its chunk crosses a column end: all warps
+  // of the (single) wave carry the same number of rows.  A piece of a column is tile slot (image, piece index, strip).
+  const int strips = a.tiles_x, pmax = a.tiles_y;
+  const int n_total = a.B * strips * a.S * a.H;
+  const int chunk = blockIdx.x * kStreamWarps + wid;
+  const int g_begin = chunk * a.seg_rows, g_end = min(g_begin + a.seg_rows, n_total);
+  if (g_begin >= n_total) return;          // (whole warp; nothing below synchronises across warps)
+  grid_dependency_wait();        // packed sources, identity loss, window sums and the format flag come from the preparation launch
+  const bool packed = (*reinterpret_cast<const volatile unsigned*>(a.fmt_flag) == 0u);
+#pragma unroll 1
+  for (int g_cur = g_begin; g_cur < g_end;) {
+  const int col = g_cur / a.H;
+  const int y0 = g_cur - col * a.H, y1 = min(a.H, y0 + (g_end - g_cur));
+  g_cur += y1 - y0;
+  const int s = col % a.S;
+  const int strip = (col / a.S) % strips;
+  const int b = col / (a.S * strips);
+  const int piece = chunk - (col * a.H) / a.seg_rows;      // chunks that started inside this column before this one
+  const int tile_id = (b * pmax + piece) * strips + strip;
 
   const int H = a.H, W = a.W;
   const unsigned plane = (unsigned)(H * W), uW = (unsigned)W;
@@ -432,6 +442,7 @@ __global__ void __launch_bounds__(kStreamThreads, PPEA_STREAM_CTAS) vsl_stream_k
   const bool use_noise = automask && sc.noise != nullptr;
 
   f2* const G = s_G[wid];
+  __syncwarp();                  // (the previous piece of this warp is done with G)
   if (lane < 24) {
     const int f = lane / 12, e = lane % 12;
     const float v = geom_entry(a.K + b * 16, a.T[f] + b * 16, a.inv_K + b * 16, e);
@@ -443,7 +454,6 @@ __global__ void __launch_bounds__(kStreamThreads, PPEA_STREAM_CTAS) vsl_stream_k
   const bool col_in = gx >= 0 && gx < W;
   const bool q_lane = col_in && lane >= 1 && lane <= 30;
   const bool own_col = lane >= 2 && lane <= 29 && gx < W;
-  const int y0 = seg * a.seg_rows, y1 = min(y0 + a.seg_rows, H);
   ColCtx cc = make_col(G, gx, W);
   if (!same_res) cc.cx = up_coef(cc.px, ws, sc.up_sx);
   const float wmax = coord_max(W), hmax = coord_max(H);
@@ -454,8 +464,6 @@ __global__ void __launch_bounds__(kStreamThreads, PPEA_STREAM_CTAS) vsl_stream_k
   const float* tgt_b = a.tgt + (size_t)b * 3 * plane;
   const float* disp_b = sc.disp + (size_t)b * hs * ws;
 
-  grid_dependency_wait();        // packed sources, identity loss and the format flag come from the preparation launch
-  const bool packed = (*reinterpret_cast<const volatile unsigned*>(a.fmt_flag) == 0u);
   const uint32_t* pk0 = opaque_base(a.pk[0] + (size_t)b * plane);
   const uint32_t* pk1 = opaque_base(a.pk[1] + (size_t)b * plane);
   const SrcPlanes sp = make_planes(a.src[0] + (size_t)b * 3 * plane, a.src[1] + (size_t)b * 3 * plane, plane);
@@ -819,11 +827,20 @@ __global__ void __launch_bounds__(kStreamThreads, PPEA_STREAM_CTAS) vsl_stream_k
     const int e = warp_sum24_index(lane);
     if (e < 24) a.pose_partials[((size_t)tile_id * a.S + s) * 24 + e] = tsum;
   }
+  // the last piece of a column clears the column's unused tile slots (the finish launches sum every slot)
+  if (y1 == a.H) {
+    for (int k = piece + 1; k < pmax; ++k) {
+      const size_t slot = (size_t)((b * pmax + k) * strips + strip) * a.S + s;
+      if (lane == 0) *reinterpret_cast<float4*>(a.partials + slot * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (POSE && lane < 24) a.pose_partials[slot * 24 + lane] = 0.f;
+    }
+  }
+  }      // pieces of this warp's chunk
 }
 
 template <bool POSE, bool MULTI, bool DET>
 static cudaError_t launch_vsl_stream_as(const VslArgs& a, cudaStream_t stream) {
-  const int tasks = a.B * a.tiles_x * a.tiles_y * a.S;
+  const int tasks = ceil_div(a.B * a.tiles_x * a.S * a.H, a.seg_rows);      // chunks of seg_rows rows of the column line
   const int n_task_ctas = ceil_div(tasks, kStreamWarps);
   const cudaError_t e = ensure_max_carveout(vsl_stream_kernel<POSE, MULTI, DET>);
   if (e != cudaSuccess) return e;

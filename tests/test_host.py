@@ -104,3 +104,33 @@ def test_algorithmic_bytes_match_survey_table():
     assert abs(algorithmic_bytes(12, 192, 640, 4) / n - 375.9) < 0.05
     assert abs(algorithmic_bytes(12, 192, 640, 4, deterministic=True) / n - 407.9) < 0.05
     assert abs(algorithmic_bytes(12, 192, 640, 4, is_multi=True) / n - 423.9) < 0.05
+
+
+def test_streaming_step_row_partition_covers_every_column_once():
+    """The work split of the streaming step (vsl_common.cuh stream_chunk_rows / stream_pieces, vsl_stream.cu task decode), restated:
+    the rows of all (image, strip, scale) columns form one line cut into chunks of L rows; a chunk crossing a column end yields two
+    pieces; piece k of a column owns tile slot k, the column's last piece clears the slots above it.  Every (column, slot) is
+    written or cleared exactly once, the pieces of a column tile its rows, and no piece index reaches stream_pieces(H, L)."""
+    import random
+    rnd = random.Random(0)
+    for _ in range(400):
+        B, strips, S, H, L = rnd.randint(1, 5), rnd.randint(1, 6), rnd.randint(1, 4), rnd.randint(4, 200), rnd.randint(16, 400)
+        pmax = (H - 1) // L + 2
+        total = B * strips * S * H
+        written, cleared = {}, set()
+        for j in range(-(-total // L)):
+            g, g_end = j * L, min(j * L + L, total)
+            while g < g_end:
+                col = g // H
+                y0 = g - col * H
+                y1 = min(H, y0 + (g_end - g))
+                g += y1 - y0
+                piece = j - (col * H) // L
+                assert 0 <= piece < pmax and (col, piece) not in written
+                written[(col, piece)] = (y0, y1)
+                if y1 == H:
+                    cleared.update((col, k) for k in range(piece + 1, pmax))
+        for c in range(B * strips * S):
+            rows = [written[(c, k)] for k in range(pmax) if (c, k) in written]
+            assert all(((c, k) in written) != ((c, k) in cleared) for k in range(pmax))
+            assert rows[0][0] == 0 and rows[-1][1] == H and all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
