@@ -253,13 +253,23 @@ __global__ void __launch_bounds__(kSmoothThreads, PPEA_PREP_CTAS) vsl_prep_kerne
   const int g_lo = y0 - 1, g_hi = y1;      // one halo row above and below: the window sums of rows y0 .. y1-1
   float2* ys_b = a.ystat + (size_t)b * plane;
   const size_t ys_plane = (size_t)a.B * plane;
-  PrepRow nxt;
+#ifndef PPEA_PREP_DEPTH
+#define PPEA_PREP_DEPTH 1
+#endif
+  // rows in flight ahead of the one being processed: the launch is bound by DRAM latency x loads in flight, not by bytes
+  PrepRow nxt, nxt2;
   load_row(g_lo, nxt);
+  if (PPEA_PREP_DEPTH == 2) load_row(g_lo + 1 <= g_hi ? g_lo + 1 : g_lo, nxt2);
 
   auto step = [&](auto par, const int gi) {
     constexpr int P = decltype(par)::value, Q = 1 - P;
     const PrepRow cur = nxt;
-    load_row(gi + 1 <= g_hi ? gi + 1 : gi, nxt);       // next row in flight while this one is processed
+    if (PPEA_PREP_DEPTH == 2) {
+      nxt = nxt2;
+      load_row(gi + 2 <= g_hi ? gi + 2 : g_hi, nxt2);
+    } else {
+      load_row(gi + 1 <= g_hi ? gi + 1 : gi, nxt);     // next row in flight while this one is processed
+    }
     if (gi >= y0 && gi < y1) {                         // (then the row is not a reflected one)
       const unsigned w0 = pack_rgb(cur.x[0].x, cur.x[1].x, cur.x[2].x, exact), w1 = pack_rgb(cur.x[0].y, cur.x[1].y, cur.x[2].y, exact);
       if (own_col) {

@@ -145,6 +145,16 @@ def _materialize_warps(self, inputs, outputs, is_multi):
             outputs[("color", f, s)] = Fn.grid_sample_border(src, pix)
             if not _opt(self, "disable_automasking", False):
                 outputs[("color_identity", f, s)] = src
+        if is_multi:
+            # logging byproduct of the multi path (trainer.py:1134-1138; its only reader in the reference is commented out):
+            # 1 / (mono_depth * consistency_mask + multi_depth * (1 - consistency_mask)), a few elementwise launches
+            keep = torch.ones_like(depth)
+            if not _opt(self, "disable_motion_masking", False) and outputs.get("consistency_mask") is not None:
+                keep = keep * outputs["consistency_mask"].unsqueeze(1)
+            if not _opt(self, "no_matching_augmentation", False) and outputs.get("augmentation_mask") is not None:
+                keep = keep * (1 - outputs["augmentation_mask"][:o.batch_size])
+            cm = 1 - keep
+            outputs["consistency_target/{}".format(s)] = 1 / (outputs[("mono_depth", 0, s)].detach() * cm + depth.detach() * (1 - cm))
 
 
 def compute_reprojection_loss(self, pred, target):
@@ -183,10 +193,31 @@ def compute_losses(self, inputs, outputs, is_multi=False):
                 losses["consistency_loss/{}".format(s)] = v[k + 2]
             losses["loss/{}".format(s)] = v[k]
         total = v[0] if total is None else total + v[0]     # each call already divides by sclm+1
+        if _opt(self, "loss_pct", False):
+            _log_mask_fraction(self, outputs, res, first, n, is_multi)
     losses["loss"] = total
     if getattr(self, "ppea_keep_maps", False):
         outputs[("ppea_maps", bool(is_multi))] = results
     return losses, []
+
+
+def _log_mask_fraction(self, outputs, res, first, n, is_multi):
+    """The `--loss_pct` branch of compute_losses (trainer.py:1116-1123): the fraction of pixels the reprojection mask keeps,
+    per scale, from the sums the forward already reduced (row[1] = sum(mask), ppea_vsl.h) -- no extra pass over the mask.
+    Kept on the device in outputs[("loss_pct", mode, scale)]; printed with opt.debug and sent to wandb every 50th step by the
+    main process, exactly where the reference does."""
+    import sys
+    o = self.opt
+    stride = res.sums.numel() // n
+    for i in range(n):
+        scale = first + i
+        percent = res.sums[i * stride + 1] / (o.batch_size * o.height * o.width)
+        mode = "m" if is_multi else "t"
+        outputs[("loss_pct", mode, scale)] = percent
+        if _opt(self, "debug", False):
+            print(percent)
+        if getattr(self, "step", 1) % 50 == 0 and getattr(self, "is_main", False) and "wandb" in sys.modules:
+            sys.modules["wandb"].log({"Train/pp_{}_{}".format(mode, scale): percent}, step=self.step)
 
 
 def compute_matching_mask(self, outputs):

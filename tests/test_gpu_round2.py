@@ -303,3 +303,32 @@ def test_shapes_are_checked_before_any_launch():
         run_cuda(bad, outputs, opt, False, noise)
     with pytest.raises(ValueError):
         run_cuda(inputs, outputs, opt, False, [z[..., :-1] for z in noise])
+
+
+@pytest.mark.parametrize("multi", [False, True])
+def test_loss_pct_branch_reports_the_mask_fraction(multi):
+    """`--loss_pct` (trainer.py:1116-1123): percent = reprojection_loss_mask.sum() / (batch_size * height * width) per scale,
+    here read from the sums the forward already reduced; checked against the mask the kernel itself reports (sel bit 2 on the
+    mono path, 1 - consistency target mask on the multi path via the oracle)."""
+    B, H, W, S = 2, 40, 72, 3
+    cfg = SynthConfig(batch=B, height=H, width=W, num_scales=S, seed=5)
+    inputs, outputs = make_batch(cfg)
+    opt = _opt_ns(B, H, W, S)
+    opt.loss_pct, opt.debug = True, False
+    mod = ViewSynthesisLoss(opt, noise_mode="reference", keep_maps=True)
+    ins = {k: v.cuda() for k, v in inputs.items()}
+    outs = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in outputs.items()}
+    for s in range(S):
+        outs[("disp", s)].requires_grad_(True)
+    torch.manual_seed(3)
+    mod.generate_images_pred(ins, outs, multi)
+    losses, _ = mod.compute_losses(ins, outs, multi)
+    noise = None
+    if not multi:
+        torch.manual_seed(3)
+        noise = [torch.randn(B, 1, H, W) for _ in range(S)]
+    _, ref_maps = O.view_synthesis_losses(inputs, outputs, opt, is_multi=multi, noise=noise, want_maps=True)
+    for s in range(S):
+        pct = float(outs[("loss_pct", "m" if multi else "t", s)])
+        want = float(ref_maps[s]["mask"].sum()) / (B * H * W)
+        assert abs(pct - want) <= 2.0 / (B * H * W) + 1e-6, (s, pct, want)      # (near-tie automask flips: at most a pixel or two)
