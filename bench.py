@@ -503,57 +503,78 @@ def main():
         Ke = args.e2e_steps or min(K, 100)    # (the two-batch pipeline fill at the start is inside the timed region)
         copy_stream = torch.cuda.Stream(device=device)
 
-        def start_h2d(hs):
-            """Enqueues the step's host->device copy on the copy stream (as a pin_memory dataloader does ahead of
-            the step); returns the device tensors (views of the device arena) and the event that marks their arrival."""
-            arena, layout = hs
-            with torch.cuda.stream(copy_stream):
-                d_arena = arena.to(device, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(copy_stream)
-            return (d_arena, layout), ev
+        DEPTH = 2     # batches in flight on the copy stream (a pin_memory DataLoader's prefetch_factor)
+        NSLOT = DEPTH + 1
+        stage = {}    # device staging of the current leg: a ring of NSLOT input arenas with their tensor views built once
 
-        def e2e_compute(dev, ev):
-            from ppea_depth_b200 import images_to_float
-            d_arena, layout = dev
-            torch.cuda.current_stream().wait_event(ev)
-            d_arena.record_stream(torch.cuda.current_stream())
-            dev = {k: d_arena[o:o + _nbytes(shape, dt)].view(dt).view(shape) for k, (o, shape, dt) in layout.items()}
+        def build_stage(host_sets):
+            """The device side of the input pipeline, built once per leg: NSLOT arenas (step i uses slot i % NSLOT while the
+            copy stream fills the next two), the views of every input tensor inside each arena, and -- for uint8 frames --
+            the float32 block they are expanded into (images_to_float(out=...))."""
+            arena0, layout = host_sets[0]
+            assert all(h[1] == layout and h[0].numel() == arena0.numel() for h in host_sets)
             u8 = [k for k, (o, shape, dt) in layout.items() if dt == torch.uint8]
-            if u8:
-                # uint8 frames: one expansion call over their contiguous block (public API: images_to_float)
-                lo = min(layout[k][0] for k in u8)
-                hi = max(layout[k][0] + _nbytes(layout[k][1], layout[k][2]) for k in u8)
-                f32 = images_to_float(d_arena[lo:hi])
+            lo = min((layout[k][0] for k in u8), default=0)
+            hi = max((layout[k][0] + _nbytes(layout[k][1], layout[k][2]) for k in u8), default=0)
+            slots = []
+            for _ in range(NSLOT):
+                d_arena = torch.empty(arena0.numel(), dtype=torch.uint8, device=device)
+                dev = {k: d_arena[o:o + _nbytes(shape, dt)].view(dt).view(shape) for k, (o, shape, dt) in layout.items()}
+                f32 = torch.empty(hi - lo, dtype=torch.float32, device=device) if u8 else None
                 for k in u8:
                     o, shape, _ = layout[k]
                     dev[k] = f32[o - lo:o - lo + _nbytes(shape, torch.uint8)].view(shape)
-            ins = {k[1:]: v for k, v in dev.items() if k[0] == "in"}
-            outs = {(k[1] if len(k) == 2 else k[1:]): v for k, v in dev.items() if k[0] == "out"}
+                ins = {k[1:]: v for k, v in dev.items() if k[0] == "in"}
+                outs = {(k[1] if len(k) == 2 else k[1:]): v for k, v in dev.items() if k[0] == "out"}
+                slots.append({"arena": d_arena, "u8": d_arena[lo:hi] if u8 else None, "f32": f32, "ins": ins, "outs": outs,
+                              "arrived": torch.cuda.Event(), "free": None})
+            stage["slots"] = slots
+
+        def start_h2d(hs, i):
+            """Enqueues the host->device copy of step i's inputs on the copy stream (as a pin_memory dataloader does ahead of
+            the step) into slot i % NSLOT, once the step that last used the slot is done with it."""
+            sl = stage["slots"][i % NSLOT]
+            with torch.cuda.stream(copy_stream):
+                if sl["free"] is not None:
+                    copy_stream.wait_event(sl["free"])
+                sl["arena"].copy_(hs[0], non_blocking=True)
+                sl["arrived"].record(copy_stream)
+            return sl
+
+        def e2e_compute(sl):
+            from ppea_depth_b200 import images_to_float
+            cur = torch.cuda.current_stream()
+            cur.wait_event(sl["arrived"])
+            if sl["u8"] is not None:
+                # uint8 frames: one expansion call over their contiguous block (public API: images_to_float)
+                images_to_float(sl["u8"], out=sl["f32"])
+            ins, outs = sl["ins"], dict(sl["outs"])
             for s in range(S):
-                outs[("disp", s)].requires_grad_(True)
+                outs[("disp", s)] = outs[("disp", s)].detach().requires_grad_(True)
             if not is_multi:
                 for f in (-1, 1):
-                    outs[("cam_T_cam", 0, f)].requires_grad_(True)
+                    outs[("cam_T_cam", 0, f)] = outs[("cam_T_cam", 0, f)].detach().requires_grad_(True)
             mod.generate_images_pred(ins, outs, is_multi)
             losses, _ = mod.compute_losses(ins, outs, is_multi)
             losses["loss"].backward()
+            if sl["free"] is None:
+                sl["free"] = torch.cuda.Event()
+            sl["free"].record(cur)
             return losses["loss"]
 
         loss_host = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
         loss_ev = [torch.cuda.Event() for _ in range(2)]
-        DEPTH = 2     # batches in flight on the copy stream (a pin_memory DataLoader's prefetch_factor)
 
         def e2e_run(host_sets, n):
             """n steps; the inputs of steps i+1 .. i+DEPTH are copied on the copy stream while step i computes; every
             step ends with the D2H of its loss, which the host reads one step later (as a training loop logs it)."""
             from collections import deque
-            q = deque(start_h2d(host_sets[j % len(host_sets)]) for j in range(min(DEPTH, n)))
+            q = deque(start_h2d(host_sets[j % len(host_sets)], j) for j in range(min(DEPTH, n)))
             for i in range(n):
                 cur = q.popleft()
                 if i + DEPTH < n:
-                    q.append(start_h2d(host_sets[(i + DEPTH) % len(host_sets)]))
-                loss = e2e_compute(*cur)
+                    q.append(start_h2d(host_sets[(i + DEPTH) % len(host_sets)], i + DEPTH))
+                loss = e2e_compute(cur)
                 slot = i % 2
                 loss_host[slot].copy_(loss.detach().reshape(1), non_blocking=True)
                 loss_ev[slot].record()
@@ -563,26 +584,52 @@ def main():
             loss_ev[(n - 1) % 2].synchronize()
             return float(loss_host[(n - 1) % 2][0])
 
-        def time_e2e(host_sets, repeats=3):
-            """Ke steps, `repeats` times: the MEDIAN repetition is reported, every repetition is listed."""
+        def time_e2e(host_sets, repeats=3, alone=False):
+            """Ke steps, `repeats` times: the MEDIAN repetition is reported, every repetition is listed.  alone: this rank
+            only, the others idle (no barriers, no reduction)."""
             e2e_run(host_sets, 3)
             ms = []
             for _ in range(repeats):
-                barrier(world)
+                if not alone:
+                    barrier(world)
                 f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 f0.record()
                 e2e_run(host_sets, Ke)
                 f1.record()
-                barrier(world)
-                ms.append(max_over_ranks(f0.elapsed_time(f1), world, device) / Ke)
+                if alone:
+                    torch.cuda.synchronize()
+                    ms.append(f0.elapsed_time(f1) / Ke)
+                else:
+                    barrier(world)
+                    ms.append(max_over_ranks(f0.elapsed_time(f1), world, device) / Ke)
             return statistics.median(ms), ms
 
         def leg(tensors):
             host_sets = [collate(t) for t in tensors]
+            build_stage(host_sets)
             h2d = sum(v.numel() * v.element_size() for v in tensors[0].values())
+            alone_ms = None
+            if world > 1:
+                # one rank with the box to itself, then all ranks together: the ratio names what the ranks share (host memory
+                # and PCIe root complexes), with a number
+                if rank == 0:
+                    alone_ms, _ = time_e2e(host_sets, repeats=1, alone=True)
+                barrier(world)
             ms, reps = time_e2e(host_sets)
-            return {"value": world * B * H * W / (ms * 1e-3) / 1e6, "unit": "Mpixels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "ms_per_step": ms, "steps": Ke, "repeats_ms_per_step": reps, "h2d_gb_per_s": h2d / (ms * 1e-3) / 1e9}
+            # the pipeline's arithmetic: one step on host set 0 (what loss_check evaluated through the resident API; the
+            # device noise only breaks exact ties) must give that loss
+            last = e2e_run(host_sets[:1], 1)
+            if rank == 0 and loss_check is not None and not is_multi:
+                assert abs(last - loss_check["api_loss"]) <= 1e-4 * abs(loss_check["api_loss"]), (last, loss_check)
+            out = {"value": world * B * H * W / (ms * 1e-3) / 1e6, "unit": "Mpixels/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                   "ms_per_step": ms, "steps": Ke, "repeats_ms_per_step": reps, "h2d_gb_per_s": h2d / (ms * 1e-3) / 1e9,
+                   "loss_of_set0_through_the_pipeline": last}
+            if world > 1:
+                out["h2d_gb_per_s_all_ranks"] = world * h2d / (ms * 1e-3) / 1e9
+                if alone_ms is not None:
+                    out["rank0_alone_ms_per_step"] = alone_ms
+                    out["all_ranks_vs_rank0_alone"] = alone_ms / ms
+            return out
 
         f32_leg = leg(step_tensors)
         # the dataset's frames are uint8 (ToTensor divides them by 255 on the CPU, mono_dataset.py:62,106): handed over as
@@ -593,8 +640,8 @@ def main():
         e2e["float32_frames"] = f32_leg
         e2e["api"] = ("ppea_depth_b200.loss.ViewSynthesisLoss.generate_images_pred + compute_losses + backward (noise_mode=device, cached step "
                       "plans); colour frames cross PCIe as the dataset's uint8 planes and are expanded on the device (images_to_float); a "
-                      "step's inputs sit in one pinned arena and cross as one copy; the next two steps are copied on a second stream while "
-                      "step i computes; the loss is copied to pinned host memory every step and read by the host one step later.  With "
+                      "step's inputs sit in one pinned arena and cross as one copy into a ring of three device arenas (tensor views built "
+                      "once); the next two steps are copied on a second stream while step i computes; the loss is copied to pinned host memory every step and read by the host one step later.  With "
                       "the reference's own CPU noise (noise_mode=reference: 4 torch.randn of (B,1,H,W) on the host + 23.6 MB H2D) a step "
                       "is bound by ~50 ms of host RNG instead.")
 

@@ -17,9 +17,10 @@ import torch
 from . import _cabi as C
 
 
-def images_to_float(img: torch.Tensor) -> torch.Tensor:
+def images_to_float(img: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
     """uint8 CUDA tensor (any shape, planar like the float frames) -> float32 tensor ``img / 255`` of the same
-    shape; float32 tensors pass through untouched."""
+    shape; float32 tensors pass through untouched.  `out`: optional preallocated contiguous float32 CUDA tensor with as
+    many elements (an input pipeline's device staging buffer)."""
     if img.dtype == torch.float32:
         return img
     if img.dtype != torch.uint8:
@@ -28,7 +29,10 @@ def images_to_float(img: torch.Tensor) -> torch.Tensor:
         raise RuntimeError("ppea_depth_b200 has no CPU path: move the uint8 frames to the GPU first")
     src = img.contiguous()
     with torch.cuda.device(src.device):
-        out = torch.empty(src.shape, device=src.device, dtype=torch.float32)
+        if out is None:
+            out = torch.empty(src.shape, device=src.device, dtype=torch.float32)
+        elif out.dtype != torch.float32 or not out.is_cuda or not out.is_contiguous() or out.numel() != src.numel():
+            raise ValueError("images_to_float: `out` must be a contiguous float32 CUDA tensor with %d elements" % src.numel())
         C.check(C.lib().ppea_images_u8_to_f32(src.data_ptr(), out.data_ptr(), ctypes.c_size_t(src.numel()),
                                               torch.cuda.current_stream().cuda_stream))
     return out
