@@ -408,6 +408,7 @@ int ppea_vsl_fused_forward(const PpeaVslParams* p, const PpeaVslFused* f, void* 
     PPEA_TRY(launch_vsl_prep(a, stream));       // packed sources + identity loss, once for all scales
     PPEA_TRACE(p, 2);
     PPEA_TRY(launch_vsl_stream(a, stream));
+    PPEA_TRY(launch_vsl_smooth_tail(a, stream));   // smoothness term, in the shadow of the streaming kernel's last warps
   }
   PPEA_TRACE(p, 3);
   PPEA_TRY(launch_vsl_finish(a, fused_tiles(p), stream, (p->flags & PPEA_F_GRAD_POSE) && !(p->flags & PPEA_F_MULTI)));

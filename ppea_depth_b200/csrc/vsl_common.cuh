@@ -163,6 +163,7 @@ inline int stream_pieces(int H, int rows) { return (H - 1) / rows + 2; }
 inline int stream_tiles_max(int B, int H, int W) { return B * stream_strips(W) * stream_pieces(H, PPEA_STREAM_MIN_SEG_ROWS); }
 cudaError_t launch_vsl_prep(const VslArgs& a, cudaStream_t stream);
 cudaError_t launch_vsl_stream(const VslArgs& a, cudaStream_t stream);
+cudaError_t launch_vsl_smooth_tail(const VslArgs& a, cudaStream_t stream);
 cudaError_t launch_vsl_grad_finish(const VslArgs& a, cudaStream_t stream);
 
 // Programmatic dependent launch (sm_90+): a kernel launched with launch_pdl may become resident while its

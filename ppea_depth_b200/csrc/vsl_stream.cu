@@ -34,6 +34,7 @@
 // Arithmetic (vsl_math.cuh) and summation order of the window sums are those of the tile kernel:
 // the per-pixel maps are bit-identical on the planar path.
 #include "vsl_common.cuh"
+#include <cstdlib>
 #include <type_traits>
 
 #include "smooth.cuh"
@@ -196,7 +197,7 @@ struct PrepRow {
 #ifndef PPEA_PREP_CTAS
 #define PPEA_PREP_CTAS 3
 #endif
-__global__ void __launch_bounds__(kSmoothThreads, PPEA_PREP_CTAS) vsl_prep_kernel(const __grid_constant__ VslArgs a, int strips, int segs, int n_task_ctas) {
+__global__ void __launch_bounds__(kSmoothThreads, PPEA_PREP_CTAS) vsl_prep_kernel(const __grid_constant__ VslArgs a, int strips, int segs, int seg_rows, int n_task_ctas) {
   __shared__ float red[3 * kSmoothThreads / 32];
   grid_launch_dependents();      // the main launch may take idle SMs early (it waits for our results where it needs them)
   if ((int)blockIdx.x >= n_task_ctas) {
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(kSmoothThreads, PPEA_PREP_CTAS) vsl_prep_kerne
   const int x0 = strip * kPrepStripW - 1, gx = x0 + lane;
   const int px = reflect_index(gx, W);
   const bool own_col = lane >= 1 && lane <= 30 && gx < W;      // (gx >= 0 for lane >= 1)
-  const int y0 = seg * kPrepSegRows, y1 = min(y0 + kPrepSegRows, H);
+  const int y0 = seg * seg_rows, y1 = min(y0 + seg_rows, H);
   const float* tgt_b = a.tgt + (size_t)b * 3 * plane;
   const float* s0_b = a.src[0] + (size_t)b * 3 * plane;
   const float* s1_b = a.src[1] + (size_t)b * 3 * plane;
@@ -323,11 +324,77 @@ __global__ void __launch_bounds__(kSmoothThreads, PPEA_PREP_CTAS) vsl_prep_kerne
   if (!__all_sync(0xffffffffu, exact) && lane == 0) *a.fmt_flag = 1u;
 }
 
+// Smoothness term of every scale as a launch of its own that runs in the SHADOW of the streaming kernel: nothing the
+// streaming kernel reads or writes is touched here (inputs: disp_s, colour_s; outputs: the chunk sums and the stencil
+// field, read by the finish launches only), so the launch is made programmatically dependent on the streaming kernel
+// and never waits for it BEFORE its work -- its CTAs (128 threads, few registers) take the places the streaming warps
+// leave as the single wave drains.  Every CTA waits for the streaming grid at its END, so that "this grid complete"
+// implies "streaming grid complete" for the finish launch that follows.
+__global__ void __launch_bounds__(kSmoothThreads) vsl_smooth_tail_kernel(const __grid_constant__ VslArgs a) {
+  __shared__ float red[3 * kSmoothThreads / 32];
+  grid_launch_dependents();
+  smooth_fused_role(a, blockIdx.x, red);
+  grid_dependency_wait();
+}
+
+// Rows per warp task of the preparation launch: with the smoothness roles in a launch of their own the tasks alone
+// must fill the device, so the segment is the longest one whose tasks still cover every resident warp slot of ONE
+// wave (one halo row above and below each segment is recomputed: rows / (rows + 2) of the work is useful); batches
+// that fill several waves anyway keep kPrepSegRows.
+static int prep_seg_rows(const VslArgs& a, int strips) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("PPEA_PREP_SEG_ROWS");
+    forced = e ? atoi(e) : 0;
+  }
+  if (forced > 0) return forced;
+#ifdef PPEA_SMOOTH_IN_PREP
+  return kPrepSegRows;
+#else
+  static int sm_count[64] = {};
+  int dev = 0, sms = 0;
+  (void)cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && sm_count[dev] > 0) {
+    sms = sm_count[dev];
+  } else {
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148, (void)cudaGetLastError();
+    if (dev >= 0 && dev < 64) sm_count[dev] = sms;
+  }
+  const long long slots = (long long)sms * PPEA_PREP_CTAS * (kSmoothThreads / 32);
+  const long long cols = (long long)a.B * strips;
+  if (cols * ceil_div(a.H, kPrepSegRows) >= 2 * slots) return kPrepSegRows;
+  const int segs = (int)(slots / cols) > 0 ? (int)(slots / cols) : 1;
+  const int rows = ceil_div(a.H, segs);
+  return rows < 16 ? 16 : rows;
+#endif
+}
+
 cudaError_t launch_vsl_prep(const VslArgs& a, cudaStream_t stream) {
-  const int strips = ceil_div(a.W, kPrepStripW), segs = ceil_div(a.H, kPrepSegRows);
+  const int strips = ceil_div(a.W, kPrepStripW), seg_rows = prep_seg_rows(a, strips), segs = ceil_div(a.H, seg_rows);
   const int n_task_ctas = ceil_div(a.B * strips * segs, kSmoothThreads / 32);
-  vsl_prep_kernel<<<n_task_ctas + a.S * a.B * kSmoothChunks, kSmoothThreads, 0, stream>>>(a, strips, segs, n_task_ctas);
+#ifdef PPEA_SMOOTH_IN_PREP
+  const int n_smooth = a.S * a.B * kSmoothChunks;
+#else
+  const int n_smooth = 0;
+#endif
+#ifdef PPEA_PREP_MAX_CARVEOUT
+  const cudaError_t e = ensure_max_carveout(vsl_prep_kernel);
+  if (e != cudaSuccess) return e;
+#endif
+  vsl_prep_kernel<<<n_task_ctas + n_smooth, kSmoothThreads, 0, stream>>>(a, strips, segs, seg_rows, n_task_ctas);
   return cudaGetLastError();
+}
+
+cudaError_t launch_vsl_smooth_tail(const VslArgs& a, cudaStream_t stream) {
+#ifdef PPEA_SMOOTH_IN_PREP
+  (void)a, (void)stream;
+  return cudaSuccess;
+#else
+  // (same carve-out as the streaming kernel: an SM need not drain to change its configuration before it can take these CTAs)
+  const cudaError_t e = ensure_max_carveout(vsl_smooth_tail_kernel);
+  if (e != cudaSuccess) return e;
+  return launch_pdl(vsl_smooth_tail_kernel, dim3(a.S * a.B * kSmoothChunks), dim3(kSmoothThreads), 0, stream, a);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -471,8 +538,15 @@ __global__ void __launch_bounds__(kStreamThreads, PPEA_STREAM_CTAS) vsl_stream_k
   const unsigned upx = (unsigned)cc.px, ugx = (unsigned)(col_in ? gx : 0);
   const unsigned img0 = (unsigned)b * plane;          // first pixel of image b in the (B,1,H,W) maps (B*H*W < 2^31 is checked by the API)
 
+#ifdef PPEA_STREAM_PIN
+  // per-piece constants the optimiser would otherwise re-derive from the argument block inside the row loop (uniform-datapath
+  // instructions that cost issue slots every row): pinned in registers
+  const float* tgt_b = opaque_base(a.tgt + (size_t)b * 3 * plane);
+  const float* disp_b = opaque_base(sc.disp + (size_t)b * hs * ws);
+#else
   const float* tgt_b = a.tgt + (size_t)b * 3 * plane;
   const float* disp_b = sc.disp + (size_t)b * hs * ws;
+#endif
 
   const uint32_t* pk0 = opaque_base(a.pk[0] + (size_t)b * plane);
   const uint32_t* pk1 = opaque_base(a.pk[1] + (size_t)b * plane);
