@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define PPEA_ABI_VERSION 10
+#define PPEA_ABI_VERSION 11
 
 /* error codes (negative) */
 #define PPEA_OK 0
@@ -249,6 +249,16 @@ int ppea_match_features(const float* current_feats, const float* lookup_feats, c
                         const float* inv_K, const float* depth_bins, float* cost_volume, float* missing_mask, int batch,
                         int num_lookup, int channels, int height, int width, int num_bins, int set_missing_to_max, float eps,
                         void* stream);
+
+/* The same call with a scratch buffer of ppea_match_workspace_bytes(...) bytes (16-byte aligned; 0 bytes: the shape has no
+ * fast path, e.g. channels % 4 != 0): both feature tensors are first re-laid as (N, C/4, h, w, 4) -- four channels of a cell in
+ * one 16-byte word -- so that a bilinear corner is one 128-bit load for four channels; results are bit-identical to
+ * ppea_match_features (same arithmetic, same channel order).  workspace == NULL takes the planar kernel. */
+size_t ppea_match_workspace_bytes(int batch, int num_lookup, int channels, int height, int width);
+int ppea_match_features_ws(const float* current_feats, const float* lookup_feats, const float* relative_poses, const float* K,
+                           const float* inv_K, const float* depth_bins, float* cost_volume, float* missing_mask, int batch,
+                           int num_lookup, int channels, int height, int width, int num_bins, int set_missing_to_max, float eps,
+                           void* workspace, size_t workspace_bytes, void* stream);
 
 /* `match_features_dyn`, networks/replk_matching_adapter.py:163-258 -- the variant the encoder takes when it is given a teacher
  * depth (:400, :439-442; no caller inside the reference does): the same plane sweep with (a) an occlusion map of the lookup image

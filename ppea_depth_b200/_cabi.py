@@ -20,7 +20,7 @@ INCLUDE_DIR = os.path.join(os.path.dirname(PKG_DIR), "include")
 SOURCES = ("api.cu", "vsl_fwd.cu", "vsl_bwd.cu", "vsl_fused.cu", "vsl_stream.cu", "smooth.cu", "ops.cu", "matching.cu", "pose.cu", "decoder_tail.cu", "pyramid.cu")
 HEADERS = ("vsl_common.cuh", "vsl_math.cuh", "vsl_gather.cuh", "smooth.cuh")
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 TRACE_EVENTS = 5
 MAX_SCALES = 4
 SUMS_PER_SCALE = 8
@@ -131,6 +131,8 @@ SIGNATURES = {
     "ppea_pack_rgbx_u8": (_I, [_P, _P, _SZ, _I, _I, _I, _P]),
     "ppea_match_tail": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "ppea_match_features": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P]),
+    "ppea_match_workspace_bytes": (_SZ, [_I, _I, _I, _I, _I]),
+    "ppea_match_features_ws": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P, _SZ, _P]),
     "ppea_match_features_dyn": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P]),
 }
 

@@ -209,6 +209,134 @@ __global__ void __launch_bounds__(kMatchThreads) match_features_kernel(const Mat
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Channel-quad variant (the path ppea_match_features_ws takes when C % 4 == 0).  The planar kernel issues one 32-bit
+// load per channel and corner (21 instructions per hypothesis and channel, a warp's 33-float corner row straddles two
+// 128-byte lines).  Here both feature tensors are first re-laid (match_repack_kernel, one pass over 2 x 23.6 MB at the
+// KITTI shape, inside the timed call) as (N, C/4, h, w, 4): the four channels of a cell are one aligned 16-byte word,
+// adjacent pixels are adjacent words, so a corner of a hypothesis is ONE 128-bit load for four channels and a warp's
+// corner row is 33 words = 528 contiguous bytes.  Same arithmetic in the same channel order as the planar kernel: the
+// two produce bit-identical volumes (tests/test_matching.py).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) match_repack_kernel(const float* __restrict__ cur, const float* __restrict__ look, float4* __restrict__ out,
+                                                           unsigned plane, size_t n_cur, size_t total) {
+  // one launch for both tensors: output word i = (n * C/4 + group) * plane + pixel, the current features first
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  const bool second = i >= n_cur;
+  const size_t k = second ? i - n_cur : i;
+  const size_t g = k / plane;
+  const unsigned pix = (unsigned)(k - g * plane);
+  const float* p = (second ? look : cur) + g * 4 * (size_t)plane + pix;
+  out[i] = make_float4(__ldg(p), __ldg(p + plane), __ldg(p + 2 * (size_t)plane), __ldg(p + 3 * (size_t)plane));
+}
+
+#ifndef PPEA_MATCHQ_BINS
+#define PPEA_MATCHQ_BINS 4
+#endif
+#ifndef PPEA_MATCHQ_CTAS
+#define PPEA_MATCHQ_CTAS 4
+#endif
+#ifndef PPEA_MATCHQ_CHUNK
+#define PPEA_MATCHQ_CHUNK 4
+#endif
+constexpr int kMatchQBins = PPEA_MATCHQ_BINS;      // depth hypotheses in flight per thread (16 x 128-bit loads at four)
+constexpr int kMatchQChunk = PPEA_MATCHQ_CHUNK;    // depth bins per CTA (measured: 4 -> 0.484 ms, 8 -> 0.513, 16 -> 0.530 at the KITTI shape)
+
+__global__ void __launch_bounds__(kMatchThreads, PPEA_MATCHQ_CTAS) match_features_quad_kernel(const MatchArgs a, const float4* __restrict__ cur_q,
+                                                                                              const float4* __restrict__ look_q) {
+  __shared__ float sP[12];         // (K @ T)[:3,:] of the current lookup frame
+  __shared__ float siK[9];
+  __shared__ int s_skip;
+  const int b = blockIdx.y;
+  const int h = a.h, w = a.w, D = a.D, C4 = a.C >> 2;
+  const unsigned plane = (unsigned)(h * w);
+  const int tiles_x = (w + 31) / 32;
+  const int tx0 = (blockIdx.x % tiles_x) * 32 + (threadIdx.x & 31), ty0 = (blockIdx.x / tiles_x) * (kMatchThreads / 32) + (threadIdx.x >> 5);
+  const bool live = tx0 < w && ty0 < h;
+  const int y = live ? ty0 : 0, x = live ? tx0 : 0;
+  const unsigned pix = (unsigned)y * (unsigned)w + (unsigned)x;
+  if (threadIdx.x < 9) siK[threadIdx.x] = a.invK[b * 16 + (threadIdx.x / 3) * 4 + threadIdx.x % 3];
+  __syncthreads();
+  float ray[3];
+  pixel_ray(siK, (float)x, (float)y, ray);
+  const float cur_mask = (y >= 2 && y < h - 2 && x >= 2 && x < w - 2) ? 1.f : 0.f;      // current_mask[:, 2:-2, 2:-2] = 1 (:310-312)
+  const float4* cur_p = cur_q + (size_t)b * C4 * plane + pix;
+  float* cost_b = a.cost + (size_t)b * D * plane + pix;
+  float* miss_b = a.missing + (size_t)b * D * plane + pix;
+  const float fC = (float)a.C;
+  const int d_lo = blockIdx.z * kMatchQChunk, d_hi = min(D, d_lo + kMatchQChunk);
+
+  for (int d0 = d_lo; d0 < d_hi; d0 += kMatchQBins) {
+    float cost[kMatchQBins], cnt[kMatchQBins];
+#pragma unroll
+    for (int j = 0; j < kMatchQBins; ++j) cost[j] = cnt[j] = 0.f;
+    for (int f = 0; f < a.F; ++f) {
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const float* T = a.poses + ((size_t)b * a.F + f) * 16;
+        float s = 0.f;
+        for (int e = 0; e < 16; ++e) s += T[e];
+        s_skip = (s == 0.f) ? 1 : 0;                      // "missing lookup frame" (:289-291)
+        compose_P(a.K + b * 16, T, sP);
+      }
+      __syncthreads();
+      if (s_skip) continue;
+      MatchTap tap[kMatchQBins];
+      float acc[kMatchQBins];
+#pragma unroll
+      for (int j = 0; j < kMatchQBins; ++j) {
+        const int d = min(d0 + j, D - 1);
+        tap[j] = match_setup(sP, ray, __ldg(a.bins + d), h, w, a.eps, cur_mask);
+        acc[j] = 0.f;
+      }
+      if (live) {
+        const float4* look_f = look_q + ((size_t)b * a.F + f) * C4 * plane;
+#pragma unroll 1
+        for (int g = 0; g < C4; ++g) {
+          const float4 cv = __ldg(cur_p + (size_t)g * plane);
+          const float4* lp = look_f + (size_t)g * plane;
+          float4 nw[kMatchQBins], ne[kMatchQBins], sw[kMatchQBins], se[kMatchQBins];
+#pragma unroll
+          for (int j = 0; j < kMatchQBins; ++j) {          // all loads of the group first: 4 x kMatchQBins requests in flight
+            const float4* q = lp + tap[j].off;
+            nw[j] = __ldg(q), ne[j] = __ldg(q + 1), sw[j] = __ldg(q + w), se[j] = __ldg(q + w + 1);
+          }
+#pragma unroll
+          for (int j = 0; j < kMatchQBins; ++j) {
+            const MatchTap& t = tap[j];
+            const float v0 = fmaf(t.wse, se[j].x, fmaf(t.wsw, sw[j].x, fmaf(t.wne, ne[j].x, t.wnw * nw[j].x)));
+            acc[j] += fabsf(v0 - cv.x);
+            const float v1 = fmaf(t.wse, se[j].y, fmaf(t.wsw, sw[j].y, fmaf(t.wne, ne[j].y, t.wnw * nw[j].y)));
+            acc[j] += fabsf(v1 - cv.y);
+            const float v2 = fmaf(t.wse, se[j].z, fmaf(t.wsw, sw[j].z, fmaf(t.wne, ne[j].z, t.wnw * nw[j].z)));
+            acc[j] += fabsf(v2 - cv.z);
+            const float v3 = fmaf(t.wse, se[j].w, fmaf(t.wsw, sw[j].w, fmaf(t.wne, ne[j].w, t.wnw * nw[j].w)));
+            acc[j] += fabsf(v3 - cv.w);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kMatchQBins; ++j) {
+        const float diff = mul_rn(div_rn(acc[j], fC), tap[j].edge);        // .mean(1) * edge_mask (:314-315)
+        cost[j] += diff;
+        cnt[j] += diff > 0.f ? 1.f : 0.f;
+      }
+    }
+    if (live) {
+#pragma unroll
+      for (int j = 0; j < kMatchQBins; ++j) {
+        const int d = d0 + j;
+        if (d < d_hi) {
+          const float v = cost[j] / (cnt[j] + 1e-7f);             // average over lookup images (:321)
+          cost_b[(size_t)d * plane] = v;
+          miss_b[(size_t)d * plane] = (v == 0.f) ? 1.f : 0.f;     // missing_val_mask (:324)
+        }
+      }
+    }
+  }
+}
+
 // cost = cost * (1 - missing) + max_d(cost) * missing   (:325-328): one thread per pixel, two sweeps over its bins
 __global__ void __launch_bounds__(256) match_fill_missing_kernel(float* __restrict__ cost, int D, unsigned plane) {
   const unsigned pix = blockIdx.x * 256 + threadIdx.x;
@@ -442,13 +570,19 @@ extern "C" int ppea_match_tail(float* cost_volume, const float* missing_mask_or_
   return (int)cudaGetLastError();
 }
 
-extern "C" int ppea_match_features(const float* current_feats, const float* lookup_feats, const float* relative_poses, const float* K,
-                                   const float* inv_K, const float* depth_bins, float* cost_volume, float* missing_mask, int batch,
-                                   int num_lookup, int channels, int height, int width, int num_bins, int set_missing_to_max, float eps,
-                                   void* stream) {
+// bytes of the channel-quad copies of current_feats and lookup_feats (0: this shape takes the planar kernel)
+extern "C" size_t ppea_match_workspace_bytes(int batch, int num_lookup, int channels, int height, int width) {
+  if (batch <= 0 || num_lookup <= 0 || channels <= 0 || (channels & 3) || height < 2 || width < 2) return 0;
+  return ((size_t)batch * (1 + (size_t)num_lookup) * channels * height * width) * sizeof(float);
+}
+
+extern "C" int ppea_match_features_ws(const float* current_feats, const float* lookup_feats, const float* relative_poses, const float* K,
+                                      const float* inv_K, const float* depth_bins, float* cost_volume, float* missing_mask, int batch,
+                                      int num_lookup, int channels, int height, int width, int num_bins, int set_missing_to_max, float eps,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
   if (!current_feats || !lookup_feats || !relative_poses || !K || !inv_K || !depth_bins || !cost_volume || !missing_mask) return PPEA_E_NULL;
   if (batch <= 0 || batch > 65535 || num_lookup < 0 || channels <= 0 || height < 2 || width < 2 || num_bins <= 0 || num_bins > kMatchMaxBins || ceil_div(num_bins, kMatchChunk) > 65535 ||
-      (long long)height * width >= (1ll << 30))
+      ceil_div(num_bins, kMatchQChunk) > 65535 || (long long)height * width >= (1ll << 30))
     return PPEA_E_SHAPE;
   MatchArgs a;
   a.cur = current_feats;
@@ -467,9 +601,23 @@ extern "C" int ppea_match_features(const float* current_feats, const float* look
   a.D = num_bins;
   a.set_missing_to_max = set_missing_to_max;
   a.eps = eps;
-  const dim3 grid((unsigned)match_tiles(height, width), (unsigned)batch, (unsigned)ceil_div(num_bins, kMatchChunk));
-  match_features_kernel<<<grid, kMatchThreads, 0, (cudaStream_t)stream>>>(a);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e;
+  const size_t need = ppea_match_workspace_bytes(batch, num_lookup, channels, height, width);
+  if (workspace && need > 0) {
+    if (workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 15)) return PPEA_E_WORKSPACE;
+    const unsigned plane = (unsigned)(height * width);
+    float4* cur_q = reinterpret_cast<float4*>(workspace);
+    float4* look_q = cur_q + (size_t)batch * (channels / 4) * plane;
+    const size_t n_cur = (size_t)batch * (channels / 4) * plane, n_look = n_cur * num_lookup;
+    match_repack_kernel<<<(unsigned)((n_cur + n_look + 255) / 256), 256, 0, (cudaStream_t)stream>>>(current_feats, lookup_feats, cur_q, plane, n_cur,
+                                                                                                     n_cur + n_look);
+    const dim3 grid((unsigned)(ceil_div(width, 32) * ceil_div(height, kMatchThreads / 32)), (unsigned)batch, (unsigned)ceil_div(num_bins, kMatchQChunk));
+    match_features_quad_kernel<<<grid, kMatchThreads, 0, (cudaStream_t)stream>>>(a, cur_q, look_q);
+  } else {
+    const dim3 grid((unsigned)match_tiles(height, width), (unsigned)batch, (unsigned)ceil_div(num_bins, kMatchChunk));
+    match_features_kernel<<<grid, kMatchThreads, 0, (cudaStream_t)stream>>>(a);
+  }
+  e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   if (set_missing_to_max) {
     const dim3 g2((unsigned)ceil_div(height * width, 256), (unsigned)batch);
@@ -477,6 +625,14 @@ extern "C" int ppea_match_features(const float* current_feats, const float* look
     e = cudaGetLastError();
   }
   return (int)e;
+}
+
+extern "C" int ppea_match_features(const float* current_feats, const float* lookup_feats, const float* relative_poses, const float* K,
+                                   const float* inv_K, const float* depth_bins, float* cost_volume, float* missing_mask, int batch,
+                                   int num_lookup, int channels, int height, int width, int num_bins, int set_missing_to_max, float eps,
+                                   void* stream) {
+  return ppea_match_features_ws(current_feats, lookup_feats, relative_poses, K, inv_K, depth_bins, cost_volume, missing_mask, batch, num_lookup,
+                                channels, height, width, num_bins, set_missing_to_max, eps, nullptr, 0, stream);
 }
 
 }  // namespace ppea

@@ -252,6 +252,21 @@ __global__ void __launch_bounds__(kSmoothThreads, PPEA_PREP_CTAS) vsl_prep_kerne
     }
   };
   const int g_lo = y0 - 1, g_hi = y1;      // one halo row above and below: the window sums of rows y0 .. y1-1
+#ifndef PPEA_PREP_PREFETCH
+#define PPEA_PREP_PREFETCH 0
+#endif
+  // rows further ahead are pulled into L2 (no registers held): the tasks are bound by DRAM latency, not by bytes
+  auto prefetch_row = [&](int gi) {
+    if (PPEA_PREP_PREFETCH > 0 && gi <= g_hi) {
+      const unsigned o = (unsigned)reflect_index(gi, H) * (unsigned)W + (unsigned)px;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(tgt_b + (c * plane + o)));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(s0_b + (c * plane + o)));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(s1_b + (c * plane + o)));
+      }
+    }
+  };
   float2* ys_b = a.ystat + (size_t)b * plane;
   const size_t ys_plane = (size_t)a.B * plane;
 #ifndef PPEA_PREP_DEPTH
@@ -260,6 +275,8 @@ __global__ void __launch_bounds__(kSmoothThreads, PPEA_PREP_CTAS) vsl_prep_kerne
   // rows in flight ahead of the one being processed: the launch is bound by DRAM latency x loads in flight, not by bytes
   PrepRow nxt, nxt2;
   load_row(g_lo, nxt);
+#pragma unroll
+  for (int k = 1; k <= PPEA_PREP_PREFETCH; ++k) prefetch_row(g_lo + k);
   if (PPEA_PREP_DEPTH == 2) load_row(g_lo + 1 <= g_hi ? g_lo + 1 : g_lo, nxt2);
 
   auto step = [&](auto par, const int gi) {
@@ -271,6 +288,7 @@ __global__ void __launch_bounds__(kSmoothThreads, PPEA_PREP_CTAS) vsl_prep_kerne
     } else {
       load_row(gi + 1 <= g_hi ? gi + 1 : gi, nxt);     // next row in flight while this one is processed
     }
+    prefetch_row(gi + 1 + PPEA_PREP_PREFETCH);
     if (gi >= y0 && gi < y1) {                         // (then the row is not a reflected one)
       const unsigned w0 = pack_rgb(cur.x[0].x, cur.x[1].x, cur.x[2].x, exact), w1 = pack_rgb(cur.x[0].y, cur.x[1].y, cur.x[2].y, exact);
       if (own_col) {

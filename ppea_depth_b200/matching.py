@@ -20,9 +20,27 @@ def _f32c(t, name):
     return t.detach().contiguous().float()
 
 
-def match_features(current_feats, lookup_feats, relative_poses, K, invK, depth_bins, set_missing_to_max=True, eps=1e-7):
+_WORKSPACES = {}      # (device, bytes) -> scratch of the channel-quad feature copies (ppea_match_features_ws), reused across calls
+
+
+def _match_workspace(device, B, F, Cn, h, w):
+    need = C.lib().ppea_match_workspace_bytes(B, F, Cn, h, w)
+    if need == 0:
+        return None, 0
+    key = (device.index, need)
+    ws = _WORKSPACES.get(key)
+    if ws is None:
+        if len(_WORKSPACES) > 8:
+            _WORKSPACES.clear()
+        ws = _WORKSPACES[key] = torch.empty(need, device=device, dtype=torch.uint8)
+    return ws, need
+
+
+def match_features(current_feats, lookup_feats, relative_poses, K, invK, depth_bins, set_missing_to_max=True, eps=1e-7, planar=False):
     """current_feats (B,C,h,w), lookup_feats (B,F,C,h,w), relative_poses (B,F,4,4), K / invK (B,4,4) of the matching scale,
-    depth_bins (D,) hypothesised depths -> (cost_volume (B,D,h,w), missing_mask (B,D,h,w)), both float32."""
+    depth_bins (D,) hypothesised depths -> (cost_volume (B,D,h,w), missing_mask (B,D,h,w)), both float32.  With C % 4 == 0 the
+    features are re-laid channel-quad first (128-bit gathers, include/ppea_vsl.h ppea_match_features_ws); `planar=True` forces the
+    planar kernel (bit-identical results; tests and A/B runs)."""
     cur = _f32c(current_feats, "current_feats")
     look = _f32c(lookup_feats, "lookup_feats")
     poses = _f32c(relative_poses, "relative_poses")
@@ -36,9 +54,11 @@ def match_features(current_feats, lookup_feats, relative_poses, K, invK, depth_b
     with torch.cuda.device(cur.device):
         cost = torch.empty(B, D, h, w, device=cur.device, dtype=torch.float32)
         missing = torch.empty(B, D, h, w, device=cur.device, dtype=torch.float32)
-        C.check(C.lib().ppea_match_features(cur.data_ptr(), look.data_ptr(), poses.data_ptr(), K.data_ptr(), invK.data_ptr(),
-                                            bins.data_ptr(), cost.data_ptr(), missing.data_ptr(), B, F, Cn, h, w, D,
-                                            1 if set_missing_to_max else 0, float(eps), torch.cuda.current_stream().cuda_stream))
+        ws, ws_bytes = (None, 0) if planar else _match_workspace(cur.device, B, F, Cn, h, w)
+        C.check(C.lib().ppea_match_features_ws(cur.data_ptr(), look.data_ptr(), poses.data_ptr(), K.data_ptr(), invK.data_ptr(),
+                                               bins.data_ptr(), cost.data_ptr(), missing.data_ptr(), B, F, Cn, h, w, D,
+                                               1 if set_missing_to_max else 0, float(eps), ws.data_ptr() if ws is not None else None, ws_bytes,
+                                               torch.cuda.current_stream().cuda_stream))
     return cost, missing
 
 

@@ -154,6 +154,49 @@ def test_matching_no_out_of_bounds_writes():
             assert bool(torch.isnan(guard).all()) if dt == torch.float32 else bool((guard == sent).all())
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [dict(B=2, Fr=2, C=8, h=33, w=47, D=13, seed=41, min_bin=0.05, max_bin=60.0, zero_pose_item=1),
+                                  dict(B=2, Fr=1, C=64, h=48, w=160, D=96, seed=42, min_bin=0.3, max_bin=30.0),
+                                  dict(B=1, Fr=1, C=12, h=5, w=70, D=3, seed=43)])
+def test_channel_quad_path_is_bit_identical_to_planar(case):
+    """ppea_match_features_ws (features re-laid as (N, C/4, h, w, 4), 128-bit gathers) against the planar kernel: same
+    arithmetic in the same channel order -> identical bits; guard regions around the scratch buffer and both outputs."""
+    from unittest import mock
+    import ppea_depth_b200 as P
+    from ppea_depth_b200 import matching as MM
+    cur, look, poses, K, invK, bins = M.synthetic_case(**case)
+    g = [t.cuda() for t in (cur, look, poses, K, invK)]
+    want_cost, want_missing = P.match_features(*g, bins, True, planar=True)
+    G = 4096
+    tracked = []
+
+    def guarded_empty(*size, **kw):
+        dt = kw.get("dtype", torch.float32)
+        n = 1
+        for d in size:
+            n *= int(d)
+        sent = float("nan") if dt == torch.float32 else 0xA5
+        buf = torch.full((n + 2 * G,), sent, device=kw["device"], dtype=dt)
+        tracked.append((buf, n, dt, sent))
+        return buf[G:G + n].view(*size)
+
+    MM._WORKSPACES.clear()
+    with mock.patch.object(MM.torch, "empty", guarded_empty):
+        cost, missing = P.match_features(*g, bins, True)
+        torch.cuda.synchronize()
+    MM._WORKSPACES.clear()
+    assert len(tracked) == 3          # cost, missing, scratch (first use)
+    scratch = [t for t in tracked if t[2] == torch.uint8]
+    assert len(scratch) == 1 and scratch[0][1] == P._cabi.lib().ppea_match_workspace_bytes(case["B"], case["Fr"], case["C"], case["h"], case["w"]) > 0
+    for buf, n, dt, sent in tracked:
+        for guard in (buf[:G], buf[G + n:]):
+            assert bool(torch.isnan(guard).all()) if dt == torch.float32 else bool((guard == sent).all())
+    assert torch.equal(missing, want_missing) and (case["D"] < 8 or 0.02 < float(missing.mean()) < 0.98)
+    assert torch.equal(cost, want_cost)
+    # a shape without the fast path (C % 4 != 0) reports no scratch and takes the planar kernel
+    assert P._cabi.lib().ppea_match_workspace_bytes(2, 1, 7, 33, 47) == 0
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # match_features_dyn (replk_matching_adapter.py:163-258)
 # ---------------------------------------------------------------------------------------------------------------
