@@ -377,7 +377,7 @@ def main():
     sets = probe + make_sets(wl, n_sets - 1, 1000 * rank + 1, is_multi)
     plans = [build_plan(t, wl, device, is_multi, args.deterministic, fused=fused_arg) for t in sets]
     fused, tiles = plans[0].fused, plans[0].tiles
-    kernels = ("fused step: preparation launch (packed sources, identity loss, smoothness CTAs) + warp-streaming kernel + finish + gradient finish "
+    kernels = ("fused step: preparation launch (packed sources, identity loss, target window sums) + warp-streaming kernel + smoothness launch in its shadow + finish + gradient finish "
                "(tails launched programmatically)" if fused and not tiles else
                "fused step: tile kernel (TMA-staged tiles) + finish + gradient finish" if fused else
                "vsl_forward_kernel + finish + vsl_backward_kernel + pose finish")

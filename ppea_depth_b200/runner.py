@@ -97,7 +97,7 @@ class FusedPlan:
     @property
     def launches_forward(self):
         if self.fused and not self.tiles:
-            return 3        # preparation (packed sources, identity loss, smoothness CTAs), streaming step, finish
+            return 4        # preparation (packed sources, identity loss, target window sums), streaming step, smoothness (in its shadow), finish
         return 2            # fused forward / fused step (tiles + smoothness CTAs), finish
 
     @property

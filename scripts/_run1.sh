@@ -1,3 +1,4 @@
-python -m pytest tests/test_matching.py tests/test_cabi.py -x -q -m gpu 2>&1 | tail -4 | tee gpurun_out/r2k_tests.log
-python scripts/bench_matching.py > gpurun_out/r2k_bench_matching.json 2> gpurun_out/r2k_bench_matching.err; cat gpurun_out/r2k_bench_matching.json
-ncu --set full --clock-control none --import-source on -k regex:"match_" -s 24 -c 3 -o gpurun_out/prof_r2k_matching -f python scripts/bench_matching.py > gpurun_out/r2k_ncu.log 2>&1; tail -2 gpurun_out/r2k_ncu.log | cut -c1-200
+python -m pytest tests -x -q -m gpu 2>&1 | tail -3 | tee gpurun_out/r2l_tests.log
+python bench.py --steps 100 --warmup 10 > gpurun_out/r2l_bench.json 2> gpurun_out/r2l_bench.err; tail -c 600 gpurun_out/r2l_bench.json
+bash scripts/ncu_stream.sh r2l
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2l_launches.csv python bench.py --steps 4 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/r2l_launches.log 2>&1; tail -3 gpurun_out/r2l_launches.csv | cut -c1-200
