@@ -60,7 +60,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="kitti", choices=sorted(WORKLOADS))
     ap.add_argument("--path", default="mono", choices=["mono", "multi"])
-    ap.add_argument("--deterministic", action="store_true")
+    ap.add_argument("--deterministic", action="store_true", help="(the default) coarse-scale gradient fields accumulated in 64-bit fixed point: bit-reproducible")
+    ap.add_argument("--float-atomics", action="store_true", help="float atomics for the coarse-scale gradient fields instead (run-to-run summation order)")
     ap.add_argument("--shard", action="store_true", help="strong scaling: the workload's batch is split over the ranks")
     ap.add_argument("--no-fused", action="store_true", help="forward + backward kernel pair instead of the fused step")
     ap.add_argument("--tiles", action="store_true", help="fused step by the shared-memory tile kernel (round 1) instead of the streaming kernel")
@@ -68,7 +69,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the sharded sweep / all-reduce legs (N > 1) and the torch-CUDA eager leg (N = 1)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of one repetition of the e2e leg (default: min(steps, 100))")
-    return ap.parse_args()
+    args = ap.parse_args()
+    args.deterministic = not args.float_atomics
+    return args
 
 
 def dist_env():
@@ -451,7 +454,7 @@ def main():
         n_px = B * H * W
         # 86 + 24/4^s bytes per full-resolution pixel and scale on the mono path (forward 49 + 16/4^s,
         # backward 37 + 8/4^s), 98 + 24/4^s on the multi path, +8 with the deterministic backward: 375.9 B/px for 4 scales.
-        step_bytes_alg = algorithmic_bytes(B, H, W, S, is_multi, args.deterministic)
+        step_bytes_alg = algorithmic_bytes(B, H, W, S, is_multi, args.deterministic and not fused)   # (the fused step has no full-resolution scratch in either mode: SURVEY 8d bytes)
         if fused:
             dom = "vsl_fused_kernel" if tiles else "vsl_stream_kernel"
         else:
@@ -466,7 +469,7 @@ def main():
         achieved = dom_bytes / (stage_ms[dom] * 1e-3) / 1e9
         traffic = None            # DRAM bytes of one launch of that kernel from the committed ncu capture (same workload only)
         tpath = os.path.join(ROOT, "profiles", "r2_traffic.json" if (fused and not tiles) else ("r1j_traffic.json" if fused else "r1f_traffic.json"))
-        if os.path.exists(tpath) and args.workload == "kitti" and not is_multi and not args.deterministic and not args.shard:
+        if os.path.exists(tpath) and args.workload == "kitti" and not is_multi and (not args.deterministic or (fused and not tiles)) and not args.shard:
             traffic = json.load(open(tpath)).get(dom)
         roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,

@@ -188,10 +188,11 @@ int ppea_vsl_backward(const PpeaVslParams* p, const PpeaVslGrads* g, void* strea
  * grad_T) are the same tensors, to the same tolerances, as the two-call path.
  * PPEA_F_DETERMINISTIC: the coarse-scale fields are accumulated as 64-bit fixed-point integers (2^-40
  * resolution, contributions clamped to +-8.3e6), so the gradients are bit-reproducible without a
- * full-resolution scratch field or a second pass.  Limits of that mode: a contribution beyond +-8.3e6
- * saturates and a NaN contribution is stored as -8.3e6 (the float-atomic default propagates both); a
- * NaN or Inf in disp / T still reaches `losses` through the forward products, which is where a caller
- * should look for degenerate geometry.  Pass PPEA_F_GRAD_POSE to BOTH calls if dL/dT is
+ * full-resolution scratch field or a second pass (and, on the streaming step, faster than float atomics:
+ * the host mirror makes it the default).  A contribution that is not a finite number within +-8.3e6
+ * cannot be represented: on the streaming step it raises a sticky word in the workspace instead and
+ * ppea_vsl_fused_backward returns NaN for the coarse-scale gradients of that step (what float atomics
+ * would carry in the cells it reaches); the tile kernel (PPEA_F_FUSED_TILES) saturates it.  Pass PPEA_F_GRAD_POSE to BOTH calls if dL/dT is
  * wanted (ignored with PPEA_F_MULTI: T is detached there, trainer.py:900-902). */
 typedef struct PpeaVslFused {
   uint32_t struct_size;

@@ -769,6 +769,9 @@ __global__ void __launch_bounds__(kGradFinishThreads) vsl_grad_finish_kernel(con
   const bool coarse = (h != a.H || w != a.W);
   const bool fixed = coarse && (a.flags & PPEA_F_DETERMINISTIC);
   const bool rezero = coarse && (a.flags & PPEA_F_RAW_PREZEROED);
+  // streaming step, fixed-point fields: some contribution of this step was not representable (NaN / Inf / beyond +-8.3e6,
+  // vsl_stream.cu fixed_add_s) -> the coarse-scale gradients are NaN, as the float-atomic fields would be where it landed
+  const bool poisoned = fixed && !(a.flags & PPEA_F_FUSED_TILES) && a.fmt_flag != nullptr && a.fmt_flag[1] != 0u;
   // every load is issued before the first use (the kernel is latency-bound: one DRAM round trip, not three)
   RawVec<VEC> o;
   if (VEC == 4) {
@@ -784,6 +787,10 @@ __global__ void __launch_bounds__(kGradFinishThreads) vsl_grad_finish_kernel(con
   if (multi) rc = load_raw<VEC>(sc.grad_raw2, idx, fixed);
 #pragma unroll
   for (int k = 0; k < VEC; ++k) o.v[k] = fmaf(w_cons, rc.v[k], fmaf(w_raw, raw.v[k], w_st * (o.v[k] - mean_term)));
+  if (poisoned) {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) o.v[k] = __int_as_float(0x7fc00000);
+  }
   if (VEC == 4)
     *reinterpret_cast<float4*>(sc.grad_disp + idx) = make_float4(o.v[0], o.v[1 % VEC], o.v[2 % VEC], o.v[3 % VEC]);
   else

@@ -216,6 +216,7 @@ __global__ void __launch_bounds__(kSmoothThreads, PPEA_PREP_CTAS) vsl_prep_kerne
     return;
   }
   const int lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.fmt_flag[1] = 0u;      // sticky "non-finite contribution" word of the fixed-point fields (fixed_add_s)
   int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= a.B * strips * segs) return;
   const int strip = t % strips;
@@ -530,15 +531,21 @@ cudaError_t launch_vsl_smooth_tail(const VslArgs& a, cudaStream_t stream) {
 // Deterministic mode: 64-bit fixed-point accumulation of the coarse-scale fields (see vsl_fused.cu).
 // ---------------------------------------------------------------------------------------------------
 constexpr float kFixScaleS = 1099511627776.f;          // 2^40
-__device__ __forceinline__ void fixed_add_s(float* field, unsigned idx, float v) {
-  const long long q = __float2ll_rn(fminf(fmaxf(v, -8.3e6f), 8.3e6f) * kFixScaleS);
+// A contribution that is not a finite number within +-8.3e6 cannot be represented in the fixed-point field: it is clamped
+// and noted in `bad`; the warp raises the sticky word fmt_flag[1] (cleared by the preparation launch) once per piece, and the
+// gradient finish turns the coarse-scale gradients of the step into NaN -- what the float-atomic fields would carry in the
+// cells such a contribution reaches.
+__device__ __forceinline__ void fixed_add_s(float* field, unsigned idx, float v, bool& bad) {
+  const float c = fminf(fmaxf(v, -8.3e6f), 8.3e6f);      // (NaN -> -8.3e6: c != v)
+  bad = bad || (c != v);
+  const long long q = __float2ll_rn(c * kFixScaleS);
   atomicAdd(reinterpret_cast<unsigned long long*>(field) + idx, (unsigned long long)q);
 }
 template <bool DET>
-__device__ __forceinline__ void field_add(float* field, unsigned idx, float v) {
+__device__ __forceinline__ void field_add(float* field, unsigned idx, float v, bool& bad) {
   if (v == 0.f) return;
   if (DET)
-    fixed_add_s(field, idx, v);
+    fixed_add_s(field, idx, v, bad);
   else
     atomicAdd(field + idx, v);
 }
@@ -554,16 +561,16 @@ struct UpAgg {
     a00 = a01 = a10 = a11 = 0.f;
     cur = i0;
   }
-  __device__ __forceinline__ void flush_row0(float* field, int ws, const UpCoef& cx, bool own) {
+  __device__ __forceinline__ void flush_row0(float* field, int ws, const UpCoef& cx, bool own, bool& bad) {
     if (own) {
-      field_add<DET>(field, (unsigned)(cur * ws + cx.i0), a00);
-      field_add<DET>(field, (unsigned)(cur * ws + cx.i1), a01);
+      field_add<DET>(field, (unsigned)(cur * ws + cx.i0), a00, bad);
+      field_add<DET>(field, (unsigned)(cur * ws + cx.i1), a01, bad);
     }
   }
   // cy is warp-uniform (the row), cx this lane's column
-  __device__ __forceinline__ void add(float* field, int ws, float g, const UpCoef& cy, const UpCoef& cx, bool own) {
+  __device__ __forceinline__ void add(float* field, int ws, float g, const UpCoef& cy, const UpCoef& cx, bool own, bool& bad) {
     if (cy.i0 != cur) {          // (warp-uniform; the coarse row index grows by at most one per full-resolution row)
-      flush_row0(field, ws, cx, own);
+      flush_row0(field, ws, cx, own, bad);
       a00 = a10, a01 = a11;
       a10 = a11 = 0.f;
       cur = cy.i0;
@@ -579,11 +586,11 @@ struct UpAgg {
       a01 = fmaf(t1, cx.l1, a01);
     }
   }
-  __device__ __forceinline__ void finish(float* field, int ws, int hs, const UpCoef& cx, bool own) {
-    flush_row0(field, ws, cx, own);
+  __device__ __forceinline__ void finish(float* field, int ws, int hs, const UpCoef& cx, bool own, bool& bad) {
+    flush_row0(field, ws, cx, own, bad);
     if (own && cur + 1 < hs) {
-      field_add<DET>(field, (unsigned)((cur + 1) * ws + cx.i0), a10);
-      field_add<DET>(field, (unsigned)((cur + 1) * ws + cx.i1), a11);
+      field_add<DET>(field, (unsigned)((cur + 1) * ws + cx.i0), a10, bad);
+      field_add<DET>(field, (unsigned)((cur + 1) * ws + cx.i1), a11, bad);
     }
   }
 };
@@ -710,6 +717,7 @@ __global__ void __launch_bounds__(kStreamThreads, PPEA_STREAM_CTAS) vsl_stream_k
   float* gr_b = sc.grad_raw + (DET && !same_res ? 2 * img_off : img_off);          // (fixed-point fields: 8 bytes per pixel)
   float* gc_b = MULTI ? sc.grad_raw2 + (DET && !same_res ? 2 * img_off : img_off) : nullptr;
   UpAgg<DET> agg, agg2;
+  bool bad_add = false;          // fixed-point fields: some contribution of this piece was not representable (fixed_add_s)
   {
     const int i0 = same_res ? 0 : up_coef(y0, hs, sc.up_sy).i0;
     agg.init(i0);
@@ -990,8 +998,8 @@ __global__ void __launch_bounds__(kStreamThreads, PPEA_STREAM_CTAS) vsl_stream_k
       }
       if (!same_res) {          // (warp-uniform: the aggregation decides its flushes on the row)
         const UpCoef cy = up_coef(pi, hs, sc.up_sy);
-        agg.add(gr_b, ws, g_dup, cy, cc.cx, own_col);
-        if (MULTI) agg2.add(gc_b, ws, c_dup, cy, cc.cx, own_col);
+        agg.add(gr_b, ws, g_dup, cy, cc.cx, own_col, bad_add);
+        if (MULTI) agg2.add(gc_b, ws, c_dup, cy, cc.cx, own_col, bad_add);
       }
     }
 
@@ -1006,8 +1014,8 @@ __global__ void __launch_bounds__(kStreamThreads, PPEA_STREAM_CTAS) vsl_stream_k
     dslot = dslot == 2 ? 0 : dslot + 1;
   }
   if (!same_res) {
-    agg.finish(gr_b, ws, hs, cc.cx, own_col);
-    if (MULTI) agg2.finish(gc_b, ws, hs, cc.cx, own_col);
+    agg.finish(gr_b, ws, hs, cc.cx, own_col, bad_add);
+    if (MULTI) agg2.finish(gc_b, ws, hs, cc.cx, own_col, bad_add);
   }
   };
   if (packed)
@@ -1015,6 +1023,7 @@ __global__ void __launch_bounds__(kStreamThreads, PPEA_STREAM_CTAS) vsl_stream_k
   else
     run_rows(std::false_type{});
 
+  if (DET && __any_sync(0xffffffffu, bad_add) && lane == 0) atomicOr(a.fmt_flag + 1, 1u);
   // ---- task sums: masked loss sums, consistency sum, pose partials (fixed order)
   s_rm = warp_sum(s_rm);
   s_m = warp_sum(s_m);

@@ -243,10 +243,12 @@ def compute_matching_mask(self, outputs):
     return mask
 
 
-def install(trainer_cls, deterministic=False, noise_mode="reference", fused=None, plan_cache=True, materialize_warps=False):
+def install(trainer_cls, deterministic=True, noise_mode="reference", fused=None, plan_cache=True, materialize_warps=False):
     """Rebinds the reference Trainer's loss methods to the fused implementation.
 
-    deterministic      bit-reproducible gradients (64-bit fixed-point accumulation of the coarse-scale fields)
+    deterministic      bit-reproducible gradients (64-bit fixed-point accumulation of the coarse-scale fields; the default: on the
+                       fused step it is also the faster accumulation, 0.374 against 0.381 ms at the KITTI shape); False: float
+                       atomics, whose summation order varies from run to run like the reference's own CUDA grid_sample backward
     noise_mode         "reference": the automask's tie-break noise from the CPU generator exactly as the reference draws it;
                        "device": one torch.randn on the GPU per call
     fused              None: the fused training step whenever gradients are needed; "tiles" / False: see VslConfig.fused
@@ -271,7 +273,7 @@ class ViewSynthesisLoss:
     """Stand-alone holder of the four methods for callers without the reference Trainer
     (tests, bench.py): ``ViewSynthesisLoss(opt).generate_images_pred(inputs, outputs)`` etc."""
 
-    def __init__(self, opt, deterministic=False, noise_mode="reference", keep_maps=False, fused=None, plan_cache=True,
+    def __init__(self, opt, deterministic=True, noise_mode="reference", keep_maps=False, fused=None, plan_cache=True,
                  materialize_warps=False):
         self.opt = opt
         self.ppea_fused = fused

@@ -12,8 +12,8 @@ def bench(*args):
     st = {k: round(v, 4) for k, v in d["roofline"]["stage_ms"].items() if "unused" not in k}
     print("bench %-48s ms/step %.4f  Mpix/s %.0f  frac_step %.4f  %s" % (" ".join(args), d["ms_per_step"], d["value"], d["roofline"]["step_frac_of_peak"], st), flush=True)
 
-MODES = ([], ["--path", "multi"], ["--deterministic"], ["--path", "multi", "--deterministic"], ["--workload", "cityscapes"],
-         ["--workload", "cityscapes", "--path", "multi"], ["--workload", "hires", "--deterministic"], ["--workload", "sweep96"])
+MODES = ([], ["--path", "multi"], ["--float-atomics"], ["--path", "multi", "--float-atomics"], ["--workload", "cityscapes"],
+         ["--workload", "cityscapes", "--path", "multi"], ["--workload", "hires"], ["--workload", "sweep96"])
 for a in MODES:
     bench(*a)
     if "--pair" in sys.argv:

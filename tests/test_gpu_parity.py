@@ -98,6 +98,26 @@ def test_cuda_deterministic_backward_matches_and_repeats(multi, fused):
     check_against_oracle(inputs, outputs, opt, multi, make_noise(cfg, 4), l_det, g_det1, maps)
 
 
+@pytest.mark.parametrize("multi", [False, True])
+def test_fixed_point_fields_do_not_hide_non_finite_contributions(multi):
+    """Deterministic mode of the streaming step: a contribution that the 64-bit fixed-point fields cannot represent (here: NaN
+    from a NaN disparity at a coarse scale) must not be stored as a finite number -- the coarse-scale gradients of that step
+    come back NaN, as they do with float atomics -- and the sticky word is cleared by the next step on the same workspace."""
+    cfg = SynthConfig(batch=2, height=64, width=96, num_scales=4, seed=37)
+    inputs, outputs = make_batch(cfg)
+    noise = None if multi else make_noise(cfg, 4)
+    opt = O.default_opt(sclm=3, height=64, width=96, batch_size=2)
+    _, g_clean, _ = run_cuda(inputs, outputs, opt, multi, noise, deterministic=True)
+    bad = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in outputs.items()}
+    bad[("disp", 1)][0, 0, 5, 7] = float("nan")
+    for det in (False, True):
+        _, g_bad, _ = run_cuda(inputs, bad, opt, multi, noise, deterministic=det)
+        assert bool(torch.isnan(g_bad[("disp", 1)]).any()), det
+    _, g_again, _ = run_cuda(inputs, outputs, opt, multi, noise, deterministic=True)      # same cached plan / workspace
+    for k in g_clean:
+        assert torch.isfinite(g_again[k]).all() and torch.equal(g_again[k], g_clean[k]), k
+
+
 @pytest.mark.parametrize("fused", [None, "tiles", False])
 def test_cuda_upstream_gradient_is_linear(fused):
     """backward honours the upstream gradient of every entry of the loss dict (not just "loss")."""
