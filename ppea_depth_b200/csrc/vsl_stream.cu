@@ -673,14 +673,29 @@ __global__ void __launch_bounds__(kStreamThreads, PPEA_STREAM_CTAS) vsl_stream_k
   const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
   const unsigned upx = (unsigned)cc.px, ugx = (unsigned)(col_in ? gx : 0);
   const unsigned img0 = (unsigned)b * plane;          // first pixel of image b in the (B,1,H,W) maps (B*H*W < 2^31 is checked by the API)
+  // this lane's column inside the per-pixel maps, as ONE register the optimiser cannot re-derive (it otherwise rebuilds the
+  // clamped column from gx in five places of the row loop: 1 003 -> 987 instructions per row, step 0.3717 -> 0.3680 ms)
+#ifndef PPEA_STREAM_NO_OCOL
+  unsigned o_col = img0 + ugx;
+  asm volatile("" : "+r"(o_col));
+#else
+  const unsigned o_col = img0 + ugx;
+#endif
 
-#ifdef PPEA_STREAM_PIN
-  // per-piece constants the optimiser would otherwise re-derive from the argument block inside the row loop (uniform-datapath
-  // instructions that cost issue slots every row): pinned in registers
+  // Per-piece base pointers the optimiser otherwise re-derives from the argument block inside the row loop can be pinned in
+  // registers (opaque_base).  Whether that pays is decided by what it does to the register allocation of the loop, and was
+  // measured per instantiation (profiles/README.md r2r): the target base helps the multi path (0.3850 -> 0.3778 ms) and costs
+  // the mono path 0.3 %; the disparity base and the window-sum base lose on both.
+#if defined(PPEA_STREAM_PIN) || defined(PPEA_STREAM_PIN_TGT)
   const float* tgt_b = opaque_base(a.tgt + (size_t)b * 3 * plane);
+#elif defined(PPEA_STREAM_NO_PIN_TGT)
+  const float* tgt_b = a.tgt + (size_t)b * 3 * plane;
+#else
+  const float* tgt_b = MULTI ? opaque_base(a.tgt + (size_t)b * 3 * plane) : a.tgt + (size_t)b * 3 * plane;
+#endif
+#if defined(PPEA_STREAM_PIN) || defined(PPEA_STREAM_PIN_DISP)
   const float* disp_b = opaque_base(sc.disp + (size_t)b * hs * ws);
 #else
-  const float* tgt_b = a.tgt + (size_t)b * 3 * plane;
   const float* disp_b = sc.disp + (size_t)b * hs * ws;
 #endif
 
@@ -777,7 +792,7 @@ __global__ void __launch_bounds__(kStreamThreads, PPEA_STREAM_CTAS) vsl_stream_k
     idv = nzv = 0.f;
     cmv = 1.f;
     if (q_lane && qi >= 0 && qi < H) {
-      const unsigned o = img0 + (unsigned)qi * uW + ugx;
+      const unsigned o = o_col + (unsigned)qi * uW;
       if (automask) idv = __ldg(a.ident + o);
       if (use_noise) nzv = __ldg(sc.noise + o);
       if (motion) cmv = __ldg(a.cons_mask + o);
@@ -836,11 +851,11 @@ __global__ void __launch_bounds__(kStreamThreads, PPEA_STREAM_CTAS) vsl_stream_k
       dst[64] = make_float4(dy[1].x, dy[1].y, dy[2].x, dy[2].y);
     }
     load_tgt(gi + 1, y_pf);
-    if (gi >= y0 && gi < y1 && own_col) sc.depth[img0 + (unsigned)gi * uW + ugx] = d;   // trainer.py:893
+    if (gi >= y0 && gi < y1 && own_col) sc.depth[o_col + (unsigned)gi * uW] = d;   // trainer.py:893
     const int pi = gi - 2;
     float md = 0.f, cmf = 1.f;                        // fold row: mono depth / consistency mask (multi path)
     if (MULTI && own_col && pi >= y0) {
-      const unsigned o = img0 + (unsigned)pi * uW + ugx;
+      const unsigned o = o_col + (unsigned)pi * uW;
       md = __ldg(sc.mono_depth + o);
       if (motion) cmf = __ldg(a.cons_mask + o);
     }
@@ -907,7 +922,7 @@ __global__ void __launch_bounds__(kStreamThreads, PPEA_STREAM_CTAS) vsl_stream_k
       if (!q_ok) mq = 0.f;
       indn = mk2(sl.src == 0 ? mq : 0.f, sl.src == 1 ? mq : 0.f);
       if (own_col && qi >= y0 && qi < y1) {      // owner of q: forward products
-        const unsigned o = img0 + (unsigned)qi * uW + ugx;
+        const unsigned o = o_col + (unsigned)qi * uW;
         if (sc.loss_px) sc.loss_px[o] = sl.r;
         sc.sel[o] = (uint8_t)((unsigned)sl.src | (on ? PPEA_SEL_AUTOMASK : 0u));
         s_rm = fmaf(sl.r, mq, s_rm);
