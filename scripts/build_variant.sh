@@ -13,7 +13,7 @@ if r.returncode != 0:
 import re
 txt = r.stdout
 # registers / spills of the two launches of the streaming step
-for m in re.finditer(r"Compiling entry function '(_ZN4ppea(?:17vsl_stream_kernelILb1ELb0ELb0|15vsl_prep_kernel|22vsl_smooth_tail_kernel|21match_features_kernel|26match_features_quad_kernel|26match_features_pair_kernel)[^']*)'.*?\n(?:.*\n){0,3}?.*?(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads\n.*?Used (\d+) registers", txt):
+for m in re.finditer(r"Compiling entry function '(_ZN4ppea(?:17vsl_stream_kernelILb1ELb0ELb0|15vsl_prep_kernel|22vsl_smooth_tail_kernel|21match_features_kernel|26match_features_quad_kernel|19disp_head_dw_kernel)[^']*)'.*?\n(?:.*\n){0,3}?.*?(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads\n.*?Used (\d+) registers", txt):
     print(sys.argv[1], m.group(1)[8:40], "regs", m.group(5), "spill", m.group(3), m.group(4))
 print("built", out)
 P
