@@ -337,138 +337,9 @@ __global__ void __launch_bounds__(kMatchThreads, PPEA_MATCHQ_CTAS) match_feature
   }
 }
 
-// (Measured and NOT the default, compiled only with -DPPEA_MATCH_PAIRS: 0.505 ms against 0.482 ms -- ncu r2u: L1 wavefronts only
-// -7 % at the bench shape, +22 % instructions for the second set of taps and the selects, L1 hit rate 85 -> 70 %.)
-// Row-pair variant of the channel-quad kernel.  The volume kernel sits on the L1 data pipe (ncu r2k: 83 % of peak): every
-// feature cell is read as a corner by up to four pixels.  Here a thread owns TWO vertically adjacent pixels (x, y) and
-// (x, y + 1): for a smooth warp the lower pixel's north corners are the upper pixel's south corners (same clamped base one
-// row down, tested per thread and hypothesis), so the pair reads six cells instead of eight; where the footprints do not
-// abut the two north corners are loaded like any other (predicated loads: only those lanes generate wavefronts).  Same
-// arithmetic per pixel as the other two kernels: bit-identical volumes.
-#ifdef PPEA_MATCH_PAIRS
-#ifndef PPEA_MATCHP_BINS
-#define PPEA_MATCHP_BINS 2
-#endif
-constexpr int kMatchPBins = PPEA_MATCHP_BINS;
-constexpr int kMatchPRows = 2 * (kMatchThreads / 32);      // rows of a CTA's tile
-
-__device__ __forceinline__ float quad_abs_diff(const MatchTap& t, const float4& nw, const float4& ne, const float4& sw, const float4& se,
-                                               const float4& cv, float acc) {
-  const float v0 = fmaf(t.wse, se.x, fmaf(t.wsw, sw.x, fmaf(t.wne, ne.x, t.wnw * nw.x)));
-  acc += fabsf(v0 - cv.x);
-  const float v1 = fmaf(t.wse, se.y, fmaf(t.wsw, sw.y, fmaf(t.wne, ne.y, t.wnw * nw.y)));
-  acc += fabsf(v1 - cv.y);
-  const float v2 = fmaf(t.wse, se.z, fmaf(t.wsw, sw.z, fmaf(t.wne, ne.z, t.wnw * nw.z)));
-  acc += fabsf(v2 - cv.z);
-  const float v3 = fmaf(t.wse, se.w, fmaf(t.wsw, sw.w, fmaf(t.wne, ne.w, t.wnw * nw.w)));
-  acc += fabsf(v3 - cv.w);
-  return acc;
-}
-
-__global__ void __launch_bounds__(kMatchThreads, 4) match_features_pair_kernel(const MatchArgs a, const float4* __restrict__ cur_q,
-                                                                               const float4* __restrict__ look_q) {
-  __shared__ float sP[12];         // (K @ T)[:3,:] of the current lookup frame
-  __shared__ float siK[9];
-  __shared__ int s_skip;
-  const int b = blockIdx.y;
-  const int h = a.h, w = a.w, D = a.D, C4 = a.C >> 2;
-  const unsigned plane = (unsigned)(h * w);
-  const int tiles_x = (w + 31) / 32;
-  const int tx0 = (blockIdx.x % tiles_x) * 32 + (threadIdx.x & 31), ty0 = (blockIdx.x / tiles_x) * kMatchPRows + 2 * (threadIdx.x >> 5);
-  const bool liveA = tx0 < w && ty0 < h, liveB = tx0 < w && ty0 + 1 < h;
-  const int x = tx0 < w ? tx0 : 0, yA = ty0 < h ? ty0 : 0, yB = ty0 + 1 < h ? ty0 + 1 : yA;
-  const unsigned pixA = (unsigned)yA * (unsigned)w + (unsigned)x, pixB = (unsigned)yB * (unsigned)w + (unsigned)x;
-  if (threadIdx.x < 9) siK[threadIdx.x] = a.invK[b * 16 + (threadIdx.x / 3) * 4 + threadIdx.x % 3];
-  __syncthreads();
-  float rayA[3], rayB[3];
-  pixel_ray(siK, (float)x, (float)yA, rayA);
-  pixel_ray(siK, (float)x, (float)yB, rayB);
-  const float xm = (x >= 2 && x < w - 2) ? 1.f : 0.f;                                   // current_mask[:, 2:-2, 2:-2] = 1 (:310-312)
-  const float maskA = (yA >= 2 && yA < h - 2) ? xm : 0.f, maskB = (yB >= 2 && yB < h - 2) ? xm : 0.f;
-  const float4* cur_p = cur_q + (size_t)b * C4 * plane;
-  float* cost_b = a.cost + (size_t)b * D * plane;
-  float* miss_b = a.missing + (size_t)b * D * plane;
-  const float fC = (float)a.C;
-  const int d_lo = blockIdx.z * kMatchQChunk, d_hi = min(D, d_lo + kMatchQChunk);
-
-  for (int d0 = d_lo; d0 < d_hi; d0 += kMatchPBins) {
-    float costA[kMatchPBins], cntA[kMatchPBins], costB[kMatchPBins], cntB[kMatchPBins];
-#pragma unroll
-    for (int j = 0; j < kMatchPBins; ++j) costA[j] = cntA[j] = costB[j] = cntB[j] = 0.f;
-    for (int f = 0; f < a.F; ++f) {
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        const float* T = a.poses + ((size_t)b * a.F + f) * 16;
-        float s = 0.f;
-        for (int e = 0; e < 16; ++e) s += T[e];
-        s_skip = (s == 0.f) ? 1 : 0;                      // "missing lookup frame" (:289-291)
-        compose_P(a.K + b * 16, T, sP);
-      }
-      __syncthreads();
-      if (s_skip) continue;
-      MatchTap tA[kMatchPBins], tB[kMatchPBins];
-      bool sh[kMatchPBins];
-      float accA[kMatchPBins], accB[kMatchPBins];
-#pragma unroll
-      for (int j = 0; j < kMatchPBins; ++j) {
-        const float depth = __ldg(a.bins + min(d0 + j, D - 1));
-        tA[j] = match_setup(sP, rayA, depth, h, w, a.eps, maskA);
-        tB[j] = match_setup(sP, rayB, depth, h, w, a.eps, maskB);
-        sh[j] = tB[j].off == tA[j].off + w;               // B's north corner cells are A's south corner cells
-        accA[j] = accB[j] = 0.f;
-      }
-      if (liveA) {          // (liveB implies liveA; a dead B repeats A's pixel and is not stored)
-        const float4* look_f = look_q + ((size_t)b * a.F + f) * C4 * plane;
-#pragma unroll 1
-        for (int g = 0; g < C4; ++g) {
-          const float4 cvA = __ldg(cur_p + (size_t)g * plane + pixA), cvB = __ldg(cur_p + (size_t)g * plane + pixB);
-          const float4* lp = look_f + (size_t)g * plane;
-          float4 anw[kMatchPBins], ane[kMatchPBins], asw[kMatchPBins], ase[kMatchPBins];
-          float4 bnw[kMatchPBins], bne[kMatchPBins], bsw[kMatchPBins], bse[kMatchPBins];
-#pragma unroll
-          for (int j = 0; j < kMatchPBins; ++j) {          // all loads of the group first
-            const float4* qa = lp + tA[j].off;
-            const float4* qb = lp + tB[j].off;
-            anw[j] = __ldg(qa), ane[j] = __ldg(qa + 1), asw[j] = __ldg(qa + w), ase[j] = __ldg(qa + w + 1);
-            bsw[j] = __ldg(qb + w), bse[j] = __ldg(qb + w + 1);
-            if (!sh[j]) bnw[j] = __ldg(qb), bne[j] = __ldg(qb + 1);
-          }
-#pragma unroll
-          for (int j = 0; j < kMatchPBins; ++j) {
-            if (sh[j]) bnw[j] = asw[j], bne[j] = ase[j];
-            accA[j] = quad_abs_diff(tA[j], anw[j], ane[j], asw[j], ase[j], cvA, accA[j]);
-            accB[j] = quad_abs_diff(tB[j], bnw[j], bne[j], bsw[j], bse[j], cvB, accB[j]);
-          }
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < kMatchPBins; ++j) {
-        const float dA = mul_rn(div_rn(accA[j], fC), tA[j].edge), dB = mul_rn(div_rn(accB[j], fC), tB[j].edge);   // .mean(1) * edge_mask (:314-315)
-        costA[j] += dA;
-        cntA[j] += dA > 0.f ? 1.f : 0.f;
-        costB[j] += dB;
-        cntB[j] += dB > 0.f ? 1.f : 0.f;
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < kMatchPBins; ++j) {
-      const int d = d0 + j;
-      if (d < d_hi) {
-        if (liveA) {
-          const float v = costA[j] / (cntA[j] + 1e-7f);             // average over lookup images (:321)
-          cost_b[(size_t)d * plane + pixA] = v;
-          miss_b[(size_t)d * plane + pixA] = (v == 0.f) ? 1.f : 0.f;     // missing_val_mask (:324)
-        }
-        if (liveB) {
-          const float v = costB[j] / (cntB[j] + 1e-7f);
-          cost_b[(size_t)d * plane + pixB] = v;
-          miss_b[(size_t)d * plane + pixB] = (v == 0.f) ? 1.f : 0.f;
-        }
-      }
-    }
-  }
-}
-#endif      // PPEA_MATCH_PAIRS
+// (A row-pair variant -- a thread owning two vertically adjacent pixels and re-using the upper pixel's south corners as the
+// lower pixel's north corners where the footprints abut -- was measured bit-identical and slower, 0.505 ms against 0.482 ms:
+// profiles/README.md; it lives in the history, commit "match_features: row-pair channel-quad variant".)
 
 // cost = cost * (1 - missing) + max_d(cost) * missing   (:325-328): one thread per pixel, two sweeps over its bins
 __global__ void __launch_bounds__(256) match_fill_missing_kernel(float* __restrict__ cost, int D, unsigned plane) {
@@ -744,13 +615,8 @@ extern "C" int ppea_match_features_ws(const float* current_feats, const float* l
     const size_t n_cur = (size_t)batch * (channels / 4) * plane, n_look = n_cur * num_lookup;
     match_repack_kernel<<<(unsigned)((n_cur + n_look + 255) / 256), 256, 0, (cudaStream_t)stream>>>(current_feats, lookup_feats, cur_q, plane, n_cur,
                                                                                                      n_cur + n_look);
-#ifndef PPEA_MATCH_PAIRS
     const dim3 grid((unsigned)(ceil_div(width, 32) * ceil_div(height, kMatchThreads / 32)), (unsigned)batch, (unsigned)ceil_div(num_bins, kMatchQChunk));
     match_features_quad_kernel<<<grid, kMatchThreads, 0, (cudaStream_t)stream>>>(a, cur_q, look_q);
-#else
-    const dim3 grid((unsigned)(ceil_div(width, 32) * ceil_div(height, kMatchPRows)), (unsigned)batch, (unsigned)ceil_div(num_bins, kMatchQChunk));
-    match_features_pair_kernel<<<grid, kMatchThreads, 0, (cudaStream_t)stream>>>(a, cur_q, look_q);
-#endif
   } else {
     const dim3 grid((unsigned)match_tiles(height, width), (unsigned)batch, (unsigned)ceil_div(num_bins, kMatchChunk));
     match_features_kernel<<<grid, kMatchThreads, 0, (cudaStream_t)stream>>>(a);

@@ -195,18 +195,10 @@ struct PrepRow {
 };
 
 #ifndef PPEA_PREP_CTAS
-#ifndef PPEA_PREP_RING
 #define PPEA_PREP_CTAS 3
-#else
-#define PPEA_PREP_CTAS 5
 #endif
-#endif
-constexpr int kPrepRingK = 8;         // float4 words per thread and ring slot of the preparation launch
 __global__ void __launch_bounds__(kSmoothThreads, PPEA_PREP_CTAS) vsl_prep_kernel(const __grid_constant__ VslArgs a, int strips, int segs, int seg_rows, int n_task_ctas) {
   __shared__ float red[3 * kSmoothThreads / 32];
-#ifdef PPEA_PREP_RING
-  __shared__ float4 s_pring[2][kPrepRingK][kSmoothThreads];
-#endif
   grid_launch_dependents();      // the main launch may take idle SMs early (it waits for our results where it needs them)
   if ((int)blockIdx.x >= n_task_ctas) {
     // Smoothness term of every scale (smooth.cuh: sums + un-normalised stencil field) as extra CTAs of this launch: like
@@ -239,7 +231,6 @@ __global__ void __launch_bounds__(kSmoothThreads, PPEA_PREP_CTAS) vsl_prep_kerne
   uint32_t* pk1 = a.pk[1] + (size_t)b * plane;
   float* ident_b = a.ident + (size_t)b * plane;
 
-#ifndef PPEA_PREP_RING
   f2 hx[2][9], xr[2][3];
   float yh[2][6], ycr[2][3];
 #pragma unroll
@@ -349,108 +340,6 @@ __global__ void __launch_bounds__(kSmoothThreads, PPEA_PREP_CTAS) vsl_prep_kerne
     step(std::integral_constant<int, 0>{}, gi);
     if (gi + 1 <= g_hi) step(std::integral_constant<int, 1>{}, gi + 1);
   }
-#else
-  // (PPEA_PREP_RING, measured and NOT the default: 0.0436 ms against 0.0395 ms for the register version at five CTAs per SM,
-  // slower still at four and six -- the extra 15 LDS.128 + 8 STS.128 per row cost more than the added warps hide.)
-  // What a row hands to the next two iterations -- its horizontal 3-tap sums (x, x^2, x y per channel and source; y, y^2 per
-  // channel) and its source values -- goes through a per-thread ring in shared memory (two slots of eight 128-bit words,
-  // slot = parity of the row; a thread only touches its own words, so program order is the only synchronisation): the kernel
-  // fits ~100 registers instead of 168 and twice the warps are resident to cover the dependent-issue latency of the walk.
-  //   k 0..3  hx[0..7]      k 4  hx[8], yh[0..1]      k 5  yh[2..5]      k 6  x[0], x[1]      k 7  x[2], -
-  constexpr int kSlot = kPrepRingK * kSmoothThreads;
-  float4* const ring = &s_pring[0][0][threadIdx.x];
-#pragma unroll
-  for (int i = 0; i < 2 * kPrepRingK; ++i) ring[i * kSmoothThreads] = make_float4(0.f, 0.f, 0.f, 0.f);
-  float ycq[3] = {0.f, 0.f, 0.f};      // target values of the previous row
-  bool exact = true;
-
-  auto load_row = [&](int gi, PrepRow& r) {
-    const unsigned o = (unsigned)reflect_index(gi, H) * (unsigned)W + (unsigned)px;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      r.y[c] = __ldg(tgt_b + (c * plane + o));
-      r.x[c] = mk2(__ldg(s0_b + (c * plane + o)), __ldg(s1_b + (c * plane + o)));
-    }
-  };
-  const int g_lo = y0 - 1, g_hi = y1;      // one halo row above and below: the window sums of rows y0 .. y1-1
-  float2* ys_b = a.ystat + (size_t)b * plane;
-  const size_t ys_plane = (size_t)a.B * plane;
-  PrepRow nxt;
-  load_row(g_lo, nxt);
-#pragma unroll 1
-  for (int gi = g_lo; gi <= g_hi; ++gi) {
-    float4* const sP = ring + (gi & 1) * kSlot;            // row gi-2, replaced by row gi below
-    float4* const sQ = ring + ((gi & 1) ^ 1) * kSlot;      // row gi-1
-    const PrepRow cur = nxt;
-    load_row(gi + 1 <= g_hi ? gi + 1 : gi, nxt);           // next row in flight while this one is processed
-    if (gi >= y0 && gi < y1) {                             // (then the row is not a reflected one)
-      const unsigned w0 = pack_rgb(cur.x[0].x, cur.x[1].x, cur.x[2].x, exact), w1 = pack_rgb(cur.x[0].y, cur.x[1].y, cur.x[2].y, exact);
-      if (own_col) {
-        pk0[(unsigned)gi * (unsigned)W + (unsigned)gx] = w0;
-        pk1[(unsigned)gi * (unsigned)W + (unsigned)gx] = w1;
-      }
-    }
-    f2 hxn[9];
-    float yhn[6];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float yl = __shfl_up_sync(0xffffffffu, cur.y[c], 1), yr = __shfl_down_sync(0xffffffffu, cur.y[c], 1);
-      row_sums_y<float>(yl, cur.y[c], yr, yhn[2 * c], yhn[2 * c + 1]);
-      if (automask) {
-        const f2 xl = shfl_up2(cur.x[c]), xrt = shfl_down2(cur.x[c]);
-        row_sums_x<f2>(xl, cur.x[c], xrt, dup2(yl), dup2(cur.y[c]), dup2(yr), hxn[3 * c], hxn[3 * c + 1], hxn[3 * c + 2]);
-      } else {
-        hxn[3 * c] = hxn[3 * c + 1] = hxn[3 * c + 2] = dup2(0.f);
-      }
-    }
-    const int qi = gi - 1;
-    if (qi >= y0) {                                    // (qi < y1 by the loop bounds)
-      const float4 p4 = sP[4 * kSmoothThreads], p5 = sP[5 * kSmoothThreads];
-      const float4 q4 = sQ[4 * kSmoothThreads], q5 = sQ[5 * kSmoothThreads];
-      const float yhP[6] = {p4.z, p4.w, p5.x, p5.y, p5.z, p5.w}, yhQ[6] = {q4.z, q4.w, q5.x, q5.y, q5.z, q5.w};
-      float Sy[3], Syy[3];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        // target window sums: the streaming kernel reads them at every scale instead of re-forming them
-        Sy[c] = add_rn(add_rn(yhP[2 * c], yhQ[2 * c]), yhn[2 * c]);
-        Syy[c] = add_rn(add_rn(yhP[2 * c + 1], yhQ[2 * c + 1]), yhn[2 * c + 1]);
-        if (own_col) ys_b[c * ys_plane + ((unsigned)qi * (unsigned)W + (unsigned)gx)] = make_float2(Sy[c], Syy[c]);
-      }
-      if (automask) {
-        const float4 p0 = sP[0], p1 = sP[kSmoothThreads], p2 = sP[2 * kSmoothThreads], p3 = sP[3 * kSmoothThreads];
-        const float4 q0 = sQ[0], q1 = sQ[kSmoothThreads], q2 = sQ[2 * kSmoothThreads], q3 = sQ[3 * kSmoothThreads];
-        const float4 q6 = sQ[6 * kSmoothThreads], q7 = sQ[7 * kSmoothThreads];
-        const f2 hxP[9] = {mk2(p0.x, p0.y), mk2(p0.z, p0.w), mk2(p1.x, p1.y), mk2(p1.z, p1.w), mk2(p2.x, p2.y),
-                           mk2(p2.z, p2.w), mk2(p3.x, p3.y), mk2(p3.z, p3.w), mk2(p4.x, p4.y)};
-        const f2 hxQ[9] = {mk2(q0.x, q0.y), mk2(q0.z, q0.w), mk2(q1.x, q1.y), mk2(q1.z, q1.w), mk2(q2.x, q2.y),
-                           mk2(q2.z, q2.w), mk2(q3.x, q3.y), mk2(q3.z, q3.w), mk2(q4.x, q4.y)};
-        const f2 xq[3] = {mk2(q6.x, q6.y), mk2(q6.z, q6.w), mk2(q7.x, q7.y)};
-        f2 L = dup2(0.f), cs = dup2(0.f);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const f2 Sx = vadd(vadd(hxP[3 * c], hxQ[3 * c]), hxn[3 * c]);
-          const f2 Sxx = vadd(vadd(hxP[3 * c + 1], hxQ[3 * c + 1]), hxn[3 * c + 1]);
-          const f2 Sxy = vadd(vadd(hxP[3 * c + 2], hxQ[3 * c + 2]), hxn[3 * c + 2]);
-          photo_channel<false>(Sx, Sxx, Sxy, Sy[c], Syy[c], xq[c], ycq[c], w_ssim, l1w, L, cs, nullptr);
-        }
-        if (own_col) ident_b[(unsigned)qi * (unsigned)W + (unsigned)gx] = fminf(L.x, L.y);
-      }
-    }
-    // this row takes the place of row gi-2
-    if (automask) {
-      sP[0] = make_float4(hxn[0].x, hxn[0].y, hxn[1].x, hxn[1].y);
-      sP[kSmoothThreads] = make_float4(hxn[2].x, hxn[2].y, hxn[3].x, hxn[3].y);
-      sP[2 * kSmoothThreads] = make_float4(hxn[4].x, hxn[4].y, hxn[5].x, hxn[5].y);
-      sP[3 * kSmoothThreads] = make_float4(hxn[6].x, hxn[6].y, hxn[7].x, hxn[7].y);
-      sP[6 * kSmoothThreads] = make_float4(cur.x[0].x, cur.x[0].y, cur.x[1].x, cur.x[1].y);
-      sP[7 * kSmoothThreads] = make_float4(cur.x[2].x, cur.x[2].y, 0.f, 0.f);
-    }
-    sP[4 * kSmoothThreads] = make_float4(hxn[8].x, hxn[8].y, yhn[0], yhn[1]);
-    sP[5 * kSmoothThreads] = make_float4(yhn[2], yhn[3], yhn[4], yhn[5]);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) ycq[c] = cur.y[c];
-  }
-#endif
   if (!__all_sync(0xffffffffu, exact) && lane == 0) *a.fmt_flag = 1u;
 }
 
@@ -507,7 +396,7 @@ cudaError_t launch_vsl_prep(const VslArgs& a, cudaStream_t stream) {
 #else
   const int n_smooth = 0;
 #endif
-#if defined(PPEA_PREP_MAX_CARVEOUT) || defined(PPEA_PREP_RING)
+#ifdef PPEA_PREP_MAX_CARVEOUT
   const cudaError_t e = ensure_max_carveout(vsl_prep_kernel);      // (the ring: 32 KB per CTA, five or six CTAs per SM)
   if (e != cudaSuccess) return e;
 #endif
