@@ -3,6 +3,8 @@ synthetic batch generator, algorithmic-byte accounting."""
 from types import SimpleNamespace
 
 import pytest
+import os
+
 import torch
 
 import ppea_depth_b200 as P
@@ -36,6 +38,27 @@ def test_install_rebinds_trainer_methods():
     assert m.tolist() == [1.0, 0.0]
     assert FakeTrainer.compute_loss_masks(torch.ones(2), None).tolist() == [1.0, 1.0]
     assert FakeTrainer.compute_loss_masks(torch.tensor([2.0]), torch.tensor([2.0])).tolist() == [1.0]   # first-min tie rule
+
+
+def test_bit_reproducible_gradients_are_the_default_of_the_host_mirror():
+    """install() / ViewSynthesisLoss default to the fixed-point (deterministic) coarse-scale fields; the low-level VslConfig
+    stays explicit; bench.py follows the host mirror and `--float-atomics` opts out."""
+    import subprocess
+    import sys
+    from types import SimpleNamespace
+
+    class FakeTrainer:
+        pass
+    P.install(FakeTrainer)
+    assert FakeTrainer.ppea_deterministic is True
+    assert P.ViewSynthesisLoss(SimpleNamespace()).ppea_deterministic is True
+    assert P.ViewSynthesisLoss(SimpleNamespace(), deterministic=False).ppea_deterministic is False
+    assert VslConfig().deterministic is False
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys; sys.argv = ['bench.py'] + %r; import bench; a = bench.parse(); print(int(a.deterministic))")
+    for argv, want in (([], "1"), (["--deterministic"], "1"), (["--float-atomics"], "0")):
+        out = subprocess.run([sys.executable, "-c", code % (argv,)], cwd=root, capture_output=True, text=True)
+        assert out.stdout.strip().splitlines()[-1] == want, (argv, out.stdout, out.stderr[-500:])
 
 
 def test_flags():
