@@ -275,14 +275,20 @@ __global__ void __launch_bounds__(kT) project3d_backward_kernel(const float* __r
   }
 }
 
+// one warp per image: lane l sums the blocks l, l + 32, ... of each of the 12 entries in double, then a fixed xor tree (fixed order of
+// addition => bit-reproducible; a single thread per entry walking every block was one dependent DRAM round trip after another)
 __global__ void __launch_bounds__(32) project3d_finish_kernel(const float* __restrict__ K, const float* __restrict__ partials,
                                                               float* __restrict__ gT, int blocks_per_image) {
   __shared__ double gP[12];
   const int b = blockIdx.x, tid = threadIdx.x;
-  if (tid < 12) {
+  const float* p = partials + (size_t)b * blocks_per_image * 12;
+#pragma unroll 1
+  for (int e = 0; e < 12; ++e) {
     double t = 0;
-    for (int i = 0; i < blocks_per_image; ++i) t += (double)partials[((size_t)b * blocks_per_image + i) * 12 + tid];
-    gP[tid] = t;
+    for (int i = tid; i < blocks_per_image; i += 32) t += (double)__ldg(p + (size_t)i * 12 + e);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (tid == 0) gP[e] = t;
   }
   __syncwarp();
   if (tid < 16) {
@@ -382,13 +388,18 @@ __global__ void __launch_bounds__(kT) smooth_op_forward_kernel(const float* __re
 
 __global__ void __launch_bounds__(32) smooth_op_finish_kernel(const float* __restrict__ partials, int nblk, float* out, int B,
                                                               int H, int W) {
-  if (threadIdx.x != 0) return;
+  // one warp: lane-strided sums in double + a fixed xor tree (fixed order of addition)
   double sx = 0, sy = 0;
-  for (int i = 0; i < nblk; ++i) {
-    sx += (double)partials[i * 2];
-    sy += (double)partials[i * 2 + 1];
+  for (int i = threadIdx.x; i < nblk; i += 32) {
+    sx += (double)__ldg(partials + i * 2);
+    sy += (double)__ldg(partials + i * 2 + 1);
   }
-  out[0] = (float)(sx / ((double)B * H * (W - 1))) + (float)(sy / ((double)B * (H - 1) * W));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sx += __shfl_xor_sync(0xffffffffu, sx, o);
+    sy += __shfl_xor_sync(0xffffffffu, sy, o);
+  }
+  if (threadIdx.x == 0) out[0] = (float)(sx / ((double)B * H * (W - 1))) + (float)(sy / ((double)B * (H - 1) * W));
 }
 
 __global__ void __launch_bounds__(kT) smooth_op_backward_kernel(const float* __restrict__ disp, const float* __restrict__ img,
