@@ -359,6 +359,56 @@ __global__ void __launch_bounds__(256) match_fill_missing_kernel(float* __restri
     if (c[(size_t)d * plane] == 0.f) c[(size_t)d * plane] = vmax;
 }
 
+// The same fix-up with the bins of a pixel split over the four warps of a CTA (lane == pixel, warp == quarter of the bins, held in
+// registers): four times the loads in flight, one read of the volume instead of two (the one-thread-per-pixel sweep above is
+// latency-bound: 26 us for 35 MB, ncu r2k).  max is exact, so the split does not change a bit.  Used when D <= 4 * kFillMaxPer.
+constexpr int kFillParts = 4, kFillMaxPer = 32;
+__global__ void __launch_bounds__(32 * kFillParts) match_fill_missing_split_kernel(float* __restrict__ cost, int D, unsigned plane, int per) {
+  __shared__ float s_max[kFillParts][32];
+  __shared__ int s_any[kFillParts][32];
+  const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
+  const unsigned pix = blockIdx.x * 32 + lane;
+  const bool live = pix < plane;
+  float* c = cost + (size_t)blockIdx.y * D * plane + (live ? pix : 0u);
+  const int d0 = part * per;
+  float v[kFillMaxPer];
+  float vmax = -INFINITY;
+  bool any = false;
+#pragma unroll
+  for (int k = 0; k < kFillMaxPer; ++k) {
+    const bool ok = live && k < per && d0 + k < D;
+    v[k] = ok ? c[(size_t)(d0 + k) * plane] : -INFINITY;
+  }
+#pragma unroll
+  for (int k = 0; k < kFillMaxPer; ++k) {
+    vmax = fmaxf(vmax, v[k]);
+    any = any || v[k] == 0.f;
+  }
+  s_max[part][lane] = vmax;
+  s_any[part][lane] = any ? 1 : 0;
+  __syncthreads();
+  float m = s_max[0][lane];
+  int a = s_any[0][lane];
+#pragma unroll
+  for (int q = 1; q < kFillParts; ++q) m = fmaxf(m, s_max[q][lane]), a |= s_any[q][lane];
+  if (!any || !a || m == 0.f) return;          // (nothing of this thread's quarter to fill)
+#pragma unroll
+  for (int k = 0; k < kFillMaxPer; ++k)
+    if (v[k] == 0.f) c[(size_t)(d0 + k) * plane] = m;
+}
+
+static cudaError_t launch_match_fill_missing(float* cost, int batch, int D, int height, int width, cudaStream_t stream) {
+  const unsigned plane = (unsigned)(height * width);
+  if (D <= kFillParts * kFillMaxPer) {
+    const dim3 g((unsigned)ceil_div(height * width, 32), (unsigned)batch);
+    match_fill_missing_split_kernel<<<g, 32 * kFillParts, 0, stream>>>(cost, D, plane, ceil_div(D, kFillParts));
+  } else {
+    const dim3 g((unsigned)ceil_div(height * width, 256), (unsigned)batch);
+    match_fill_missing_kernel<<<g, 256, 0, stream>>>(cost, D, plane);
+  }
+  return cudaGetLastError();
+}
+
 // Tail of the encoder's matching block (replk_matching_adapter.py:380-387, :439-453), one sweep per pixel over its bins:
 //   confidence = [ #(cost * (1 - missing) > 0) == threshold ]                       compute_confidence_mask
 //   (mins, argmin) = min_d viz,  viz = cost with exact zeros replaced by 100          (first minimum, like torch.min)
@@ -555,11 +605,7 @@ extern "C" int ppea_match_features_dyn(const float* current_feats, const float* 
   match_features_dyn_kernel<<<grid, kMatchThreads, 0, (cudaStream_t)stream>>>(da);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
-  if (set_missing_to_max) {
-    const dim3 g2((unsigned)ceil_div(height * width, 256), (unsigned)batch);
-    match_fill_missing_kernel<<<g2, 256, 0, (cudaStream_t)stream>>>(cost_volume, num_bins, (unsigned)(height * width));
-    e = cudaGetLastError();
-  }
+  if (set_missing_to_max) e = launch_match_fill_missing(cost_volume, batch, num_bins, height, width, (cudaStream_t)stream);
   return (int)e;
 }
 
@@ -623,11 +669,7 @@ extern "C" int ppea_match_features_ws(const float* current_feats, const float* l
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
-  if (set_missing_to_max) {
-    const dim3 g2((unsigned)ceil_div(height * width, 256), (unsigned)batch);
-    match_fill_missing_kernel<<<g2, 256, 0, (cudaStream_t)stream>>>(cost_volume, num_bins, (unsigned)(height * width));
-    e = cudaGetLastError();
-  }
+  if (set_missing_to_max) e = launch_match_fill_missing(cost_volume, batch, num_bins, height, width, (cudaStream_t)stream);
   return (int)e;
 }
 
