@@ -444,6 +444,69 @@ __global__ void __launch_bounds__(256) match_tail_kernel(float* __restrict__ cos
     for (int d = 0; d < D; ++d) c[(size_t)d * plane] = mul_rn(c[(size_t)d * plane], 0.f);
 }
 
+// The same tail with the bins of a pixel split over the four warps of a CTA (like match_fill_missing_split_kernel): every warp
+// holds its quarter of the bins in registers, the partial (count, min, first argmin) are combined in ascending bin order -- a
+// later quarter only wins with a strictly smaller value, which is torch.min's first-minimum rule -- and the masking writes come
+// from the registers instead of a second read.
+__global__ void __launch_bounds__(32 * kFillParts) match_tail_split_kernel(float* __restrict__ cost, const float* __restrict__ missing,
+                                                                           float* __restrict__ confidence, float* __restrict__ mins,
+                                                                           long long* __restrict__ argmin, int D, unsigned plane, int threshold,
+                                                                           int mask_volume, int per) {
+  __shared__ float s_min[kFillParts][32];
+  __shared__ int s_cnt[kFillParts][32], s_best[kFillParts][32];
+  const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
+  const unsigned pix = blockIdx.x * 32 + lane;
+  const bool live = pix < plane;
+  const size_t base = (size_t)blockIdx.y * D * plane + (live ? pix : 0u);
+  float* c = cost + base;
+  const float* m = missing ? missing + base : nullptr;
+  const int d0 = part * per;
+  float v[kFillMaxPer], keep[kFillMaxPer];
+#pragma unroll
+  for (int k = 0; k < kFillMaxPer; ++k) {
+    const bool ok = live && k < per && d0 + k < D;
+    v[k] = ok ? c[(size_t)(d0 + k) * plane] : INFINITY;
+    keep[k] = (ok && m) ? __ldg(m + (size_t)(d0 + k) * plane) : 0.f;
+  }
+  int count = 0, best = 0;
+  float vmin = INFINITY;
+#pragma unroll
+  for (int k = 0; k < kFillMaxPer; ++k) {
+    const bool ok = live && k < per && d0 + k < D;
+    const float kv = m ? mul_rn(v[k], sub_rn(1.f, keep[k])) : v[k];
+    count += (ok && kv > 0.f) ? 1 : 0;
+    const float viz = (v[k] == 0.f) ? 100.f : v[k];
+    if (ok && viz < vmin) {
+      vmin = viz;
+      best = d0 + k;
+    }
+  }
+  s_min[part][lane] = vmin;
+  s_cnt[part][lane] = count;
+  s_best[part][lane] = best;
+  __syncthreads();
+  float gmin = s_min[0][lane];
+  int gcnt = s_cnt[0][lane], gbest = s_best[0][lane];
+#pragma unroll
+  for (int q = 1; q < kFillParts; ++q) {
+    gcnt += s_cnt[q][lane];
+    if (s_min[q][lane] < gmin) gmin = s_min[q][lane], gbest = s_best[q][lane];
+  }
+  if (!live) return;
+  const float conf = (gcnt == threshold) ? 1.f : 0.f;
+  if (part == 0) {
+    const size_t o = (size_t)blockIdx.y * plane + pix;
+    if (confidence) confidence[o] = conf;
+    if (mins) mins[o] = gmin;
+    if (argmin) argmin[o] = gbest;
+  }
+  if (mask_volume && conf == 0.f) {
+#pragma unroll
+    for (int k = 0; k < kFillMaxPer; ++k)
+      if (k < per && d0 + k < D) c[(size_t)(d0 + k) * plane] = mul_rn(v[k], 0.f);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // match_features_dyn (replk_matching_adapter.py:163-258), the variant the encoder takes when it is handed a teacher depth
 // (:400, :439-442): the same plane sweep, plus (a) an occlusion map of the lookup image projected into every layer of the
@@ -614,9 +677,16 @@ extern "C" int ppea_match_tail(float* cost_volume, const float* missing_mask_or_
                                int mask_volume, void* stream) {
   if (!cost_volume) return PPEA_E_NULL;
   if (batch <= 0 || batch > 65535 || num_bins <= 0 || height <= 0 || width <= 0 || (long long)height * width >= (1ll << 30)) return PPEA_E_SHAPE;
-  const dim3 grid((unsigned)ceil_div(height * width, 256), (unsigned)batch);
-  match_tail_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(cost_volume, missing_mask_or_null, confidence_or_null, mins_or_null, argmin_or_null,
-                                                         num_bins, (unsigned)(height * width), threshold, mask_volume);
+  if (num_bins <= kFillParts * kFillMaxPer) {
+    const dim3 grid((unsigned)ceil_div(height * width, 32), (unsigned)batch);
+    match_tail_split_kernel<<<grid, 32 * kFillParts, 0, (cudaStream_t)stream>>>(cost_volume, missing_mask_or_null, confidence_or_null, mins_or_null,
+                                                                                argmin_or_null, num_bins, (unsigned)(height * width), threshold,
+                                                                                mask_volume, ceil_div(num_bins, kFillParts));
+  } else {
+    const dim3 grid((unsigned)ceil_div(height * width, 256), (unsigned)batch);
+    match_tail_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(cost_volume, missing_mask_or_null, confidence_or_null, mins_or_null, argmin_or_null,
+                                                           num_bins, (unsigned)(height * width), threshold, mask_volume);
+  }
   return (int)cudaGetLastError();
 }
 
