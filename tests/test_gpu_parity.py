@@ -55,6 +55,32 @@ def test_cuda_matches_oracle_synthetic(shape, multi, fused, det):
     check_against_oracle(inputs, outputs, opt, multi, noise, losses, grads, maps)
 
 
+@pytest.mark.parametrize("seed", list(range(8)))
+def test_random_small_shapes_against_oracle(seed):
+    """Shapes drawn at random around the launch-geometry boundaries of the streaming step (fewer rows than a chunk, narrower than
+    a strip, heights that are not multiples of the preparation segment, 1..4 scales, ragged pyramids), both paths, both
+    accumulation modes: the chunk / segment / strip arithmetic of the three launches must hold for any size."""
+    import random
+    rng = random.Random(1000 + seed)
+    B = rng.choice([1, 2, 3])
+    H = rng.choice([8, 13, 17, 31, 32, 33, 48, 70])
+    W = rng.choice([9, 27, 28, 29, 30, 31, 57, 61, 96, 130])
+    S = rng.choice([1, 2, 3, 4])
+    while (H >> (S - 1)) < 2 or (W >> (S - 1)) < 2:
+        S -= 1
+    multi, det = rng.random() < 0.5, rng.random() < 0.5
+    cfg = SynthConfig(batch=B, height=H, width=W, num_scales=S, seed=500 + seed)
+    inputs, outputs = make_batch(cfg)
+    for s in range(1, S):
+        hs, ws = H >> s, W >> s
+        outputs[("disp", s)] = outputs[("disp", s)][..., :hs, :ws].contiguous()
+        inputs[("color", 0, s)] = inputs[("color", 0, s)][..., :hs, :ws].contiguous()
+    noise = make_noise(cfg, S)
+    opt = O.default_opt(sclm=S - 1, height=H, width=W, batch_size=B)
+    losses, grads, maps = run_cuda(inputs, outputs, opt, multi, None if multi else noise, deterministic=det)
+    check_against_oracle(inputs, outputs, opt, multi, noise, losses, grads, maps)
+
+
 @pytest.mark.parametrize("multi", [False, True])
 def test_fused_step_equals_kernel_pair(multi):
     """Same selection maps bit for bit, same losses, gradients equal up to summation order."""
