@@ -197,6 +197,33 @@ def test_channel_quad_path_is_bit_identical_to_planar(case):
     assert P._cabi.lib().ppea_match_workspace_bytes(2, 1, 7, 33, 47) == 0
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", list(range(6)))
+def test_random_shapes_quad_path_fixup_and_tail(seed):
+    """Random small shapes around the kernels' partition boundaries (bins not a multiple of four, more bins than the split fix-up
+    and tail kernels hold in registers, images narrower than a tile): channel-quad volume == planar volume bit for bit, the
+    volume against the oracle, and the tail against the oracle's tail of the SAME volume."""
+    import random
+    import ppea_depth_b200 as P
+    rng = random.Random(7000 + seed)
+    case = dict(B=rng.choice([1, 2]), Fr=rng.choice([1, 2]), C=rng.choice([4, 8, 20, 64]), h=rng.choice([3, 7, 16, 33, 40]),
+                w=rng.choice([5, 31, 32, 33, 70]), D=rng.choice([1, 5, 31, 33, 96, 128, 130]), seed=90 + seed,
+                min_bin=rng.choice([0.05, 0.5]), max_bin=rng.choice([12.0, 60.0]))
+    cur, look, poses, K, invK, bins = M.synthetic_case(**case)
+    g = [t.cuda() for t in (cur, look, poses, K, invK)]
+    for stm in (True, False):
+        cost, missing = P.match_features(*g, bins, stm)
+        cost_p, missing_p = P.match_features(*g, bins, stm, planar=True)
+        assert torch.equal(cost, cost_p) and torch.equal(missing, missing_p), (case, stm)
+        want_cost, want_missing = M.match_features(cur, look, poses, K, invK, bins, stm)
+        _check_kernel(cur, look, poses, K, invK, bins, stm, want_cost, want_missing)
+        want = M.cost_volume_tail(cost.cpu(), missing.cpu())
+        vol = cost.clone()
+        conf, mins, argmin = P.cost_volume_tail(vol, missing)
+        assert torch.equal(conf.cpu(), want[0]) and torch.equal(mins.cpu(), want[1]) and torch.equal(argmin.cpu(), want[2]), (case, stm)
+        assert torch.equal(vol.cpu(), want[3]), (case, stm)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # match_features_dyn (replk_matching_adapter.py:163-258)
 # ---------------------------------------------------------------------------------------------------------------
