@@ -181,7 +181,10 @@ __global__ void __launch_bounds__(kHeadThreads) disp_head_dx_kernel(const float*
 // grad_w[c][ky][kx] = sum_q g(q) xpad[c](q + k - 1) = sum_p x[c](p) * tap[ky][kx](p) with the same folded taps as above.
 // A warp walks kDwRows rows of one strip for kDwGroup channels at once: the taps of a row are formed once and used by the
 // four channels; 36 + 1 per-lane partial sums, reduced over the warp once per task.
-__global__ void __launch_bounds__(kHeadThreads) disp_head_dw_kernel(const float* __restrict__ x, const float* __restrict__ disp,
+#ifndef PPEA_DW_CTAS
+#define PPEA_DW_CTAS 4
+#endif
+__global__ void __launch_bounds__(kHeadThreads, PPEA_DW_CTAS) disp_head_dw_kernel(const float* __restrict__ x, const float* __restrict__ disp,
                                                                     const float* __restrict__ grad_disp, float* __restrict__ partials, int B,
                                                                     int C, int H, int W, int strips, int segs, int groups) {
   int id = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -216,21 +219,26 @@ __global__ void __launch_bounds__(kHeadThreads) disp_head_dw_kernel(const float*
   const float* gd_c = grad_disp + (size_t)img + (unsigned)(in_col ? t.gx : 0);
   const float* sd_c = disp + (size_t)img + (unsigned)(in_col ? t.gx : 0);
   const float* x_c = xb + (unsigned)(t.own ? t.gx : 0);
+  unsigned koff[kDwGroup];              // plane offsets of the group's channels
+#pragma unroll
+  for (int k = 0; k < kDwGroup; ++k) koff[k] = (unsigned)min(k, C - c0 - 1) * plane;
   constexpr int R = PPEA_DW_BLOCK;      // rows per block: R x (kDwGroup + 2) loads in flight per lane (the kernel is bound by loads in flight)
 #pragma unroll 1
   for (int yb = r0; yb < r1; yb += R) {
     float xv[R][kDwGroup], gr[R], sr[R];
+    // Loads of the block, with no per-load tests: a row past the segment is clamped to its last row (the block loop below
+    // skips it), a channel past C to the last channel of the group (its sums land in partial slots nobody reads), offsets are
+    // 32-bit (C * H * W < 2^31 is checked by the entry point).  The first version spent ~9 integer instructions per load on
+    // row / channel predicates and 64-bit addresses: 42 % of the loop's SASS.
 #pragma unroll
     for (int i = 0; i < R; ++i) {
-      const int y = yb + i;
-      const bool row_ok = y < r1;
-      const unsigned orow = (unsigned)(row_ok ? y : r1 - 1) * (unsigned)W;
+      const int yc = min(yb + i, r1 - 1);
+      const unsigned orow = (unsigned)yc * (unsigned)W;
 #pragma unroll
-      for (int k = 0; k < kDwGroup; ++k) xv[i][k] = (row_ok && t.own && c0 + k < C) ? __ldg(x_c + (size_t)k * plane + orow) : 0.f;
-      const bool dn_ok = row_ok && y + 1 < H && in_col;      // row y + 1 of g (zero outside the image)
-      const unsigned odn = (unsigned)(dn_ok ? y + 1 : 0) * (unsigned)W;
-      gr[i] = dn_ok ? __ldg(gd_c + odn) : 0.f;
-      sr[i] = dn_ok ? __ldg(sd_c + odn) : 0.f;
+      for (int k = 0; k < kDwGroup; ++k) xv[i][k] = t.own ? __ldg(x_c + (koff[k] + orow)) : 0.f;
+      const bool dn_ok = yc + 1 < H && in_col;               // row y + 1 of g (zero outside the image)
+      gr[i] = dn_ok ? __ldg(gd_c + (orow + (unsigned)W)) : 0.f;
+      sr[i] = dn_ok ? __ldg(sd_c + (orow + (unsigned)W)) : 0.f;
     }
 #pragma unroll
     for (int i = 0; i < R; ++i) {
