@@ -216,9 +216,15 @@ __global__ void __launch_bounds__(kHeadThreads, PPEA_DW_CTAS) disp_head_dw_kerne
   GRow up = grad_row(grad_disp, disp, r0 - 1, H, W, t, img), cur = grad_row(grad_disp, disp, r0, H, W, t, img);
   const GRow top = grad_row(grad_disp, disp, 0, H, W, t, img), bot = grad_row(grad_disp, disp, H - 1, H, W, t, img);
   const bool in_col = t.gx >= 0 && t.gx < W;
-  const float* gd_c = grad_disp + (size_t)img + (unsigned)(in_col ? t.gx : 0);
-  const float* sd_c = disp + (size_t)img + (unsigned)(in_col ? t.gx : 0);
-  const float* x_c = xb + (unsigned)(t.own ? t.gx : 0);
+  // (bases the optimiser cannot see through: every address formed from them is one IMAD.WIDE.U32 of a 32-bit offset)
+  auto opaque = [](const float* p) {
+    unsigned long long v = reinterpret_cast<unsigned long long>(p);
+    asm volatile("" : "+l"(v));
+    return reinterpret_cast<const float*>(v);
+  };
+  const float* gd_c = opaque(grad_disp + (size_t)img + (unsigned)(in_col ? t.gx : 0));
+  const float* sd_c = opaque(disp + (size_t)img + (unsigned)(in_col ? t.gx : 0));
+  const float* x_c = opaque(xb + (unsigned)(t.own ? t.gx : 0));
   unsigned koff[kDwGroup];              // plane offsets of the group's channels
 #pragma unroll
   for (int k = 0; k < kDwGroup; ++k) koff[k] = (unsigned)min(k, C - c0 - 1) * plane;
