@@ -346,7 +346,9 @@ static StreamSplit stream_split_for(const PpeaVslParams* p) {
   unsigned full = 0;
   for (int s = 0; s < p->num_scales; ++s)
     if (p->scales[s].disp_h == p->height && p->scales[s].disp_w == p->width) full |= 1u << s;
-  return stream_split(p->batch, p->height, p->width, p->num_scales, full, sms, forced, cost_full, cost_coarse);
+  // (the multi path keeps unit costs: its kernel instantiations use the plain decode, vsl_stream.cu)
+  const bool multi = p->flags & PPEA_F_MULTI;
+  return stream_split(p->batch, p->height, p->width, p->num_scales, full, sms, forced, multi ? 1 : cost_full, multi ? 1 : cost_coarse);
 }
 static int fused_tiles(const PpeaVslParams* p) {
   if (use_tiles(p)) return fused_blocks(p->batch, p->height, p->width);
