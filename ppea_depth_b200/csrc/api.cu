@@ -4,7 +4,6 @@
 #include "vsl_common.cuh"
 
 #include <algorithm>
-#include <cstdio>
 #include <cstdlib>
 
 using namespace ppea;
@@ -321,19 +320,14 @@ static bool frame_tensor_map(CUtensorMap* tm, const float* base, int B, int H, i
 }
 
 static bool use_tiles(const PpeaVslParams* p) { return p->flags & PPEA_F_FUSED_TILES; }
-// work split of the streaming step on the current device (vsl_common.cuh stream_split)
-static StreamSplit stream_split_for(const PpeaVslParams* p) {
+// rows per warp chunk of the streaming step on the current device (vsl_common.cuh stream_chunk_rows)
+static int stream_rows_for(const PpeaVslParams* p) {
   static int sm_count[64] = {};
-  static int forced = -1, cost_full = kRowCostFull, cost_coarse = kRowCostCoarse;
+  static int forced = -1;
   int dev = 0;
   (void)cudaGetDevice(&dev);
   if (forced < 0) {
     const char* e = getenv("PPEA_STREAM_SEG_ROWS");
-    const char* c = getenv("PPEA_STREAM_ROW_COST");      // "full,coarse" (tuning only; "1,1" = equal rows)
-    if (c) {
-      int cf = 0, cc = 0;
-      if (sscanf(c, "%d,%d", &cf, &cc) == 2 && cf > 0 && cc > 0 && cf <= 64 && cc <= 64) cost_full = cf, cost_coarse = cc;
-    }
     forced = e ? atoi(e) : 0;
   }
   int sms = 0;
@@ -343,17 +337,11 @@ static StreamSplit stream_split_for(const PpeaVslParams* p) {
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148, (void)cudaGetLastError();
     if (dev >= 0 && dev < 64) sm_count[dev] = sms;
   }
-  unsigned full = 0;
-  for (int s = 0; s < p->num_scales; ++s)
-    if (p->scales[s].disp_h == p->height && p->scales[s].disp_w == p->width) full |= 1u << s;
-  // (the multi path keeps unit costs: its kernel instantiations use the plain decode, vsl_stream.cu)
-  const bool multi = p->flags & PPEA_F_MULTI;
-  return stream_split(p->batch, p->height, p->width, p->num_scales, full, sms, forced, multi ? 1 : cost_full, multi ? 1 : cost_coarse);
+  return stream_chunk_rows(p->batch, p->height, p->width, p->num_scales, sms, forced);
 }
 static int fused_tiles(const PpeaVslParams* p) {
-  if (use_tiles(p)) return fused_blocks(p->batch, p->height, p->width);
-  const StreamSplit sp = stream_split_for(p);
-  return p->batch * stream_strips(p->width) * stream_pieces(p->height, sp.unit, sp.max_cost);
+  return use_tiles(p) ? fused_blocks(p->batch, p->height, p->width)
+                      : p->batch * stream_strips(p->width) * stream_pieces(p->height, stream_rows_for(p));
 }
 
 static void fused_args(const PpeaVslParams* p, const PpeaVslFused* f, VslArgs& a, bool forward) {
@@ -366,14 +354,8 @@ static void fused_args(const PpeaVslParams* p, const PpeaVslFused* f, VslArgs& a
   const FusedWorkspace fw = fused_workspace(p);
   const FwdWorkspace ws = fwd_workspace(p->batch, p->height, p->width, p->num_scales);
   a.tiles_x = tiles ? ceil_div(a.W, kFusedTileWc) : stream_strips(a.W);
-  const StreamSplit sp = stream_split_for(p);
-  a.seg_rows = sp.unit;
-  a.group_cost = 0;
-  for (int s = 0; s < kMaxScales; ++s) {
-    a.row_cost[s] = sp.cost[s];
-    if (s < a.S) a.group_cost += a.H * sp.cost[s];
-  }
-  a.tiles_y = tiles ? ceil_div(a.H, kFusedTileHc) : stream_pieces(a.H, sp.unit, sp.max_cost);
+  a.seg_rows = stream_rows_for(p);
+  a.tiles_y = tiles ? ceil_div(a.H, kFusedTileHc) : stream_pieces(a.H, a.seg_rows);
   a.fmt_flag = reinterpret_cast<unsigned*>((float*)f->workspace + fw.off_flag);
   a.ident = (float*)f->workspace + fw.off_ident;
   a.pk[0] = reinterpret_cast<uint32_t*>((float*)f->workspace + fw.off_pk[0]);

@@ -39,9 +39,7 @@ struct VslArgs {
   unsigned flags;
   float disp_lo, disp_range, eps, disparity_smoothness;
   int tiles_x, tiles_y; // tiles per image (of the kernel being launched)
-  int seg_rows;         // streaming step: cost units per warp chunk (StreamSplit::unit; rows when every row costs 1)
-  int row_cost[kMaxScales];   // streaming step: cost units of one row of a column of scale s (StreamSplit::cost)
-  int group_cost;       // streaming step: H * sum_s row_cost[s], the cost of the S columns of one (image, strip)
+  int seg_rows;         // streaming step: rows per warp chunk (tiles_y = stream_pieces(H, seg_rows) tile slots per column)
   const float* tgt;
   const float* src[2];
   const float* K;
@@ -93,7 +91,7 @@ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // Streaming step (vsl_stream.cu): a warp walks a chunk of rows of the 28-column strips.  The chunk length is chosen per launch
-// (stream_split below); workspaces are sized for the shortest one.
+// (stream_chunk_rows below); workspaces are sized for the shortest one.
 #define PPEA_STREAM_MIN_SEG_ROWS 16
 inline int fwd_blocks(int B, int H, int W) { return B * ceil_div(W, kFwdTileW) * ceil_div(H, kFwdTileH); }
 inline int bwd_blocks(int B, int H, int W) { return B * ceil_div(W, kBwdTileW) * ceil_div(H, kBwdTileH); }
@@ -149,52 +147,19 @@ constexpr int kStripW = 28;           // output columns per warp (32 gathered, 3
 #endif
 constexpr int kStreamCtasPerSm = PPEA_STREAM_CTAS;   // resident one-warp CTAs per SM (168 registers, 17 KB of shared memory each)
 inline int stream_strips(int W) { return ceil_div(W, kStripW); }
-// Work split of the streaming step.  The rows of all (image, strip, scale) columns form one line that is cut into equal
+// Rows per warp of the streaming step.  The rows of all (image, strip, scale) columns form one line that is cut into equal
 // chunks, one per resident warp slot of the device (sm_count * kStreamCtasPerSm one-warp CTAs): a single, evenly loaded wave;
-// a chunk that crosses a column end becomes two pieces (each pays four rows of run-in / run-out).  "Equal" is measured in
-// COST units: a row of a full-resolution scale (no upsample coefficients, no upsample adjoint, plain stores instead of
-// atomics) issues ~0.86 of the instructions of a row of a coarse scale, so a chunk inside a full-resolution column carries
-// proportionally more rows.  The kernel ends with its slowest warp: weights below the instruction ratio (the per-chunk clocks
-// say 0.80 under contention) make the full-resolution chunks the last ones and lose (profiles/README.md r2z: 16:16 0.3189 ms,
-// 14:16 0.3141, 13:16 0.3220, 12:16 0.3390, 11:16 0.3592).
-// `forced` > 0 (environment PPEA_STREAM_SEG_ROWS, tuning only) gives every row cost 1 and chunks of `forced` rows.
-constexpr int kRowCostFull = 14, kRowCostCoarse = 16;
-struct StreamSplit {
-  int unit;                  // cost units per chunk
-  int cost[kMaxScales];      // cost units per row of scale s
-  int max_cost;
-};
-inline StreamSplit stream_split(int B, int H, int W, int S, unsigned full_res_mask, int sm_count, int forced, int cost_full = kRowCostFull,
-                                int cost_coarse = kRowCostCoarse) {
-  StreamSplit sp;
-  long long per_group = 0;
-  const bool weighted = forced <= 0 && cost_full > 0 && cost_coarse > 0;
-  sp.max_cost = 1;
-  for (int s = 0; s < kMaxScales; ++s) {
-    sp.cost[s] = !weighted ? 1 : ((full_res_mask >> s) & 1u) ? cost_full : cost_coarse;
-    if (s < S) {
-      per_group += (long long)H * sp.cost[s];
-      if (sp.cost[s] > sp.max_cost) sp.max_cost = sp.cost[s];
-    }
-  }
-  long long total = (long long)B * stream_strips(W) * per_group;
-  if (total >= (1ll << 30)) {      // (32-bit positions on the cost line: fall back to unit costs)
-    for (int s = 0; s < kMaxScales; ++s) sp.cost[s] = 1;
-    sp.max_cost = 1;
-    total = (long long)B * stream_strips(W) * S * H;
-  }
-  const long long min_unit = (long long)PPEA_STREAM_MIN_SEG_ROWS * sp.max_cost;
-  if (forced > 0) {
-    sp.unit = forced < PPEA_STREAM_MIN_SEG_ROWS ? PPEA_STREAM_MIN_SEG_ROWS : forced;
-    return sp;
-  }
+// a chunk that crosses a column end becomes two pieces (each pays four rows of run-in / run-out).  `forced` > 0 (environment
+// PPEA_STREAM_SEG_ROWS, tuning only) overrides the choice.
+inline int stream_chunk_rows(int B, int H, int W, int S, int sm_count, int forced) {
+  if (forced > 0) return forced < PPEA_STREAM_MIN_SEG_ROWS ? PPEA_STREAM_MIN_SEG_ROWS : forced;
+  const long long total = (long long)B * stream_strips(W) * S * H;
   const long long slots = (long long)(sm_count > 0 ? sm_count : 148) * kStreamCtasPerSm;
-  const long long unit = (total + slots - 1) / slots;
-  sp.unit = (int)(unit < min_unit ? min_unit : unit);
-  return sp;
+  const long long rows = (total + slots - 1) / slots;
+  return rows < PPEA_STREAM_MIN_SEG_ROWS ? PPEA_STREAM_MIN_SEG_ROWS : (int)rows;
 }
-// tile slots per column: pieces the most expensive column (H rows of max_cost units) can be cut into by chunks of `unit` units
-inline int stream_pieces(int H, int unit, int max_cost = 1) { return (H * max_cost - 1) / unit + 2; }
+// tile slots per column: pieces a column of H rows can be cut into by chunks of `rows` rows
+inline int stream_pieces(int H, int rows) { return (H - 1) / rows + 2; }
 inline int stream_tiles_max(int B, int H, int W) { return B * stream_strips(W) * stream_pieces(H, PPEA_STREAM_MIN_SEG_ROWS); }
 cudaError_t launch_vsl_prep(const VslArgs& a, cudaStream_t stream);
 cudaError_t launch_vsl_stream(const VslArgs& a, cudaStream_t stream);

@@ -494,7 +494,7 @@ __device__ __forceinline__ const T* opaque_base(const T* p) {
 }
 
 #ifdef PPEA_STREAM_CLOCKS
-// Diagnostic build only (scripts/stream_clocks.py): start / end time and SM of every chunk of the last launch.
+// Diagnostic build only (scripts/stream_clocks.py): start / end time, SM and row range of every chunk of the last launch.
 __device__ unsigned long long g_stream_clk[8192][2];
 __device__ unsigned g_stream_sm[8192];
 __device__ int g_stream_rows[8192][2];
@@ -532,35 +532,13 @@ __global__ void __launch_bounds__(kStreamThreads, PPEA_STREAM_CTAS) vsl_stream_k
   const int strips = a.tiles_x, pmax = a.tiles_y;
   const int n_total = a.B * strips * a.S * a.H;
   const int chunk = blockIdx.x * kStreamWarps + wid;
-  // Chunk j covers the cost interval [j U, (j+1) U) of the line (U = a.seg_rows cost units, a row of scale s costs
-  // a.row_cost[s]: vsl_common.cuh stream_split); row_at maps a cost position to the first row at or after it.  The multi
-  // path keeps unit costs and the plain decode (the host passes row_cost = 1 for it): the weighted decode costs its
-  // instantiations 12 % through the register allocation of the row loop (profiles/README.md r2z).
-  int g_begin, g_end;
-  if constexpr (MULTI) {
-    g_begin = chunk * a.seg_rows, g_end = min(g_begin + a.seg_rows, n_total);
-    if (g_begin >= n_total) return;          // (whole warp; nothing below synchronises across warps)
-  } else {
-    const int cost_total = a.B * strips * a.group_cost;
-    auto row_at = [&](int x) -> int {
-      if (x >= cost_total) return n_total;
-      const int grp = x / a.group_cost;
-      int rem = x - grp * a.group_cost, sx = 0;
-#pragma unroll
-      for (int k = 0; k < kMaxScales - 1; ++k) {
-        const int c = a.H * a.row_cost[sx];
-        if (sx + 1 < a.S && rem >= c) rem -= c, ++sx;
-      }
-      const int w = a.row_cost[sx];
-      return (grp * a.S + sx) * a.H + min(a.H, (rem + w - 1) / w);
-    };
-    if (chunk * a.seg_rows >= cost_total) return;          // (whole warp; nothing below synchronises across warps)
-    g_begin = row_at(chunk * a.seg_rows), g_end = row_at((chunk + 1) * a.seg_rows);
-  }
+  const int g_begin = chunk * a.seg_rows, g_end = min(g_begin + a.seg_rows, n_total);
+  if (g_begin >= n_total) return;          // (whole warp; nothing below synchronises across warps)
   grid_dependency_wait();        // packed sources, identity loss, window sums and the format flag come from the preparation launch
   const bool packed = (*reinterpret_cast<const volatile unsigned*>(a.fmt_flag) == 0u);
 #ifdef PPEA_STREAM_CLOCKS
-  if (lane == 0 && chunk < 8192) g_stream_clk[chunk][0] = global_ns(), g_stream_sm[chunk] = sm_id(), g_stream_rows[chunk][0] = g_begin, g_stream_rows[chunk][1] = g_end;
+  if (lane == 0 && chunk < 8192)
+    g_stream_clk[chunk][0] = global_ns(), g_stream_sm[chunk] = sm_id(), g_stream_rows[chunk][0] = g_begin, g_stream_rows[chunk][1] = g_end;
 #endif
 #pragma unroll 1
   for (int g_cur = g_begin; g_cur < g_end;) {
@@ -570,14 +548,7 @@ __global__ void __launch_bounds__(kStreamThreads, PPEA_STREAM_CTAS) vsl_stream_k
   const int s = col % a.S;
   const int strip = (col / a.S) % strips;
   const int b = col / (a.S * strips);
-  int piece;                                               // chunks that reached into this column before this one
-  if constexpr (MULTI) {
-    piece = chunk - (col * a.H) / a.seg_rows;
-  } else {
-    int col_cost = (col / a.S) * a.group_cost;             // cost position of the column's first row
-    for (int k = 0; k < s; ++k) col_cost += a.H * a.row_cost[k];
-    piece = chunk - col_cost / a.seg_rows;
-  }
+  const int piece = chunk - (col * a.H) / a.seg_rows;      // chunks that started inside this column before this one
   const int tile_id = (b * pmax + piece) * strips + strip;
 
   const int H = a.H, W = a.W;
@@ -1019,7 +990,7 @@ __global__ void __launch_bounds__(kStreamThreads, PPEA_STREAM_CTAS) vsl_stream_k
 
 template <bool POSE, bool MULTI, bool DET>
 static cudaError_t launch_vsl_stream_as(const VslArgs& a, cudaStream_t stream) {
-  const int tasks = ceil_div(a.B * a.tiles_x * a.group_cost, a.seg_rows);      // chunks of seg_rows cost units of the column line
+  const int tasks = ceil_div(a.B * a.tiles_x * a.S * a.H, a.seg_rows);      // chunks of seg_rows rows of the column line
   const int n_task_ctas = ceil_div(tasks, kStreamWarps);
   const cudaError_t e = ensure_max_carveout(vsl_stream_kernel<POSE, MULTI, DET>);
   if (e != cudaSuccess) return e;

@@ -130,42 +130,25 @@ def test_algorithmic_bytes_match_survey_table():
 
 
 def test_streaming_step_row_partition_covers_every_column_once():
-    """The work split of the streaming step (vsl_common.cuh stream_split / stream_pieces, vsl_stream.cu task decode), restated:
-    the rows of all (image, strip, scale) columns form one line measured in cost units (a row of scale s costs w[s]) and cut into
-    chunks of U units; a chunk crossing a column end yields two pieces; piece k of a column owns tile slot k, the column's last
-    piece clears the slots above it.  Every (column, slot) is written or cleared exactly once, the pieces of a column tile its
-    rows, and no piece index reaches stream_pieces(H, U, max w).  Unit costs give the equal-row split."""
+    """The work split of the streaming step (vsl_common.cuh stream_chunk_rows / stream_pieces, vsl_stream.cu task decode), restated:
+    the rows of all (image, strip, scale) columns form one line cut into chunks of L rows; a chunk crossing a column end yields two
+    pieces; piece k of a column owns tile slot k, the column's last piece clears the slots above it.  Every (column, slot) is
+    written or cleared exactly once, the pieces of a column tile its rows, and no piece index reaches stream_pieces(H, L)."""
     import random
     rnd = random.Random(0)
-    for it in range(600):
-        B, strips, S, H = rnd.randint(1, 5), rnd.randint(1, 6), rnd.randint(1, 4), rnd.randint(4, 200)
-        w = [1] * S if it % 3 == 0 else [rnd.choice((13, 16, 5, 1)) for _ in range(S)]
-        U = rnd.randint(16 * max(w), 400 * max(w))
-        pmax = (H * max(w) - 1) // U + 2
-        group = H * sum(w)
-        cost_total, total = B * strips * group, B * strips * S * H
-
-        def row_at(x):
-            if x >= cost_total:
-                return total
-            grp, rem, s = x // group, x % group, 0
-            for _ in range(3):
-                if s + 1 < S and rem >= H * w[s]:
-                    rem -= H * w[s]
-                    s += 1
-            return (grp * S + s) * H + min(H, -(-rem // w[s]))
-
+    for _ in range(400):
+        B, strips, S, H, L = rnd.randint(1, 5), rnd.randint(1, 6), rnd.randint(1, 4), rnd.randint(4, 200), rnd.randint(16, 400)
+        pmax = (H - 1) // L + 2
+        total = B * strips * S * H
         written, cleared = {}, set()
-        for j in range(-(-cost_total // U)):
-            g, g_end = row_at(j * U), row_at((j + 1) * U)
-            assert g <= g_end
+        for j in range(-(-total // L)):
+            g, g_end = j * L, min(j * L + L, total)
             while g < g_end:
                 col = g // H
                 y0 = g - col * H
                 y1 = min(H, y0 + (g_end - g))
                 g += y1 - y0
-                col_cost = (col // S) * group + sum(H * w[k] for k in range(col % S))
-                piece = j - col_cost // U
+                piece = j - (col * H) // L
                 assert 0 <= piece < pmax and (col, piece) not in written
                 written[(col, piece)] = (y0, y1)
                 if y1 == H:
